@@ -1,0 +1,151 @@
+"""Named parity cases shared by oracle/make_golden.py (reference run ->
+fixtures), tests/test_oracle_golden.py (oracle vs fixtures) and the GPU parity
+tests (CUDA path vs oracle and vs fixtures).  Inputs are regenerated from seeds,
+so the fixtures only hold the reference's OUTPUTS.
+"""
+import numpy as np
+import scipy.sparse as sp
+
+from krypy_b200 import problems
+
+
+def _diag100():
+    return np.diag([1.0e-3] + list(range(2, 101))).astype(np.float64)
+
+
+def case_inputs(name):
+    """Returns dict(A, b, solver, ls_kwargs, solver_kwargs)."""
+    rng = np.random.default_rng(1234)
+    c = dict(ls={}, kw={})
+    if name.startswith("c1_"):
+        # BASELINE config 1: README example, test_convenience_wrappers.py:10-31
+        c["A"] = _diag100()
+        c["b"] = np.ones(100)
+        c["solver"] = name.split("_")[1]           # gmres | cg | minres
+        if c["solver"] in ("cg",):
+            c["ls"] = dict(self_adjoint=True, positive_definite=True)
+        if c["solver"] == "minres":
+            c["ls"] = dict(self_adjoint=True)
+            c["kw"] = dict(ortho="mgs")            # _convenience.py:91
+        if name.endswith("_defl"):
+            U = np.zeros((100, 1)); U[0] = 1.0     # test_convenience_wrappers.py:34-55
+            c["kw"]["U"] = U
+        if name.endswith("_store"):
+            c["kw"]["store_arnoldi"] = True
+    elif name in ("lap2d_gmres30", "lap2d_gmres_mgs", "lap2d_gmres_dmgs"):
+        n = 24
+        c["A"] = problems.laplace2d(n)
+        c["b"] = problems.rhs_normal(n * n)
+        if name == "lap2d_gmres30":
+            c["solver"] = "restarted_gmres"
+            c["kw"] = dict(maxiter=30, max_restarts=2, tol=1e-12)
+        else:
+            c["solver"] = "gmres"
+            c["kw"] = dict(maxiter=40, tol=1e-12, store_arnoldi=True,
+                           ortho=name.rsplit("_", 1)[1])
+    elif name == "poisson3d_cg_jacobi":
+        n = 8
+        A = problems.poisson3d(n)
+        c["A"] = A
+        c["b"] = problems.rhs_normal(n ** 3)
+        M = problems.jacobi_csr(A)
+        c["ls"] = dict(M=M, Minv=sp.diags(A.diagonal()).tocsr(), self_adjoint=True,
+                       positive_definite=True)
+        c["solver"] = "cg"
+        c["kw"] = dict(tol=1e-8, maxiter=200, store_arnoldi=True)
+    elif name == "convdiff_defl_gmres":
+        n = 20
+        c["A"] = problems.convdiff2d(n, c=0.1)
+        c["b"] = np.ones((n * n, 1))
+        c["solver"] = "gmres"
+        c["kw"] = dict(U=rng.standard_normal((n * n, 5)), maxiter=30, tol=1e-10,
+                       store_arnoldi=True)
+    elif name == "shifted_minres_ipB":
+        n = 16
+        A, B = problems.shifted_laplace_B(n, sigma=0.3, dtype=np.float32)
+        c["A"] = A
+        c["b"] = problems.rhs_normal(n * n, dtype=np.float32)
+        c["ls"] = dict(ip_B=B, self_adjoint=True)
+        c["solver"] = "minres"
+        c["kw"] = dict(tol=1e-5, maxiter=50)
+    elif name == "shifted_minres_ipB_f64":
+        n = 16
+        A, B = problems.shifted_laplace_B(n, sigma=0.3, dtype=np.float64)
+        c["A"] = A
+        c["b"] = problems.rhs_normal(n * n)
+        c["ls"] = dict(ip_B=B, self_adjoint=True)
+        c["solver"] = "minres"
+        c["kw"] = dict(tol=1e-9, maxiter=120, store_arnoldi=True)
+    elif name in ("dense_gmres_M_ipB", "dense_minres_M_ipB", "dense_cg_M_ipB"):
+        # preconditioned + non-Euclidean inner product (test_utils.py:355-383 style)
+        N = 30
+        d = np.linspace(1, 4, N)
+        Bm = np.diag(np.linspace(1, 2, N))
+        S = rng.standard_normal((N, N)); S = S + S.T
+        K = np.diag(d) + 0.05 * S + 2 * np.eye(N)          # SPD-ish, symmetric
+        c["A"] = np.linalg.solve(Bm, K)                    # self-adjoint in <.,.>_B
+        c["b"] = rng.standard_normal((N, 1))
+        # M must be self-adjoint pos.def. w.r.t. <.,.>_B and keep M*A self-adjoint
+        # in <.,.>_{M^{-1}B}: a scalar multiple of the identity is.
+        Mm = 0.5 * np.eye(N)
+        c["ls"] = dict(M=Mm, Minv=2.0 * np.eye(N), ip_B=Bm, self_adjoint=True,
+                       positive_definite=True)
+        c["solver"] = name.split("_")[1]
+        c["kw"] = dict(tol=1e-11, maxiter=40, store_arnoldi=True)
+    elif name == "dense_gmres_MlMr":
+        N = 40
+        A = np.diag(np.linspace(1, 10, N)) + 0.3 * rng.standard_normal((N, N))
+        c["A"] = A
+        c["b"] = rng.standard_normal((N,))
+        c["ls"] = dict(Ml=np.diag(1.0 / np.linspace(1, 10, N)),
+                       Mr=np.diag(np.linspace(0.5, 1.5, N)))
+        c["solver"] = "gmres"
+        c["kw"] = dict(tol=1e-12, maxiter=40, x0=rng.standard_normal((N, 1)),
+                       store_arnoldi=True)
+    elif name == "lucky_breakdown":
+        # 3 distinct eigenvalues, tol 1e-14
+        N = 10
+        c["A"] = np.diag([1.0] * 4 + [2.0] * 3 + [5.0] * 3)
+        c["b"] = np.ones((N, 1))
+        c["solver"] = "gmres"
+        c["kw"] = dict(tol=1e-14, store_arnoldi=True)
+    elif name == "zero_rhs":
+        c["A"] = _diag100()
+        c["b"] = np.zeros((100, 1))
+        c["solver"] = "gmres"
+    elif name == "maxiter_noconv":
+        c["A"] = _diag100()
+        c["b"] = np.ones((100, 1))
+        c["solver"] = "gmres"
+        c["kw"] = dict(maxiter=10, store_arnoldi=True)
+    elif name == "cg_explicit_residual":
+        n = 12
+        c["A"] = problems.laplace2d(n)
+        c["b"] = problems.rhs_normal(n * n)
+        c["ls"] = dict(self_adjoint=True, positive_definite=True)
+        c["solver"] = "cg"
+        c["kw"] = dict(tol=1e-9, maxiter=80, explicit_residual=True)
+    elif name == "convdiff_defl_minres_cg":
+        raise KeyError(name)
+    elif name in ("lap2d_defl_cg", "lap2d_defl_minres"):
+        n = 14
+        c["A"] = problems.laplace2d(n)
+        c["b"] = problems.rhs_normal(n * n)
+        c["ls"] = dict(self_adjoint=True, positive_definite=True)
+        c["solver"] = name.rsplit("_", 1)[1]
+        c["kw"] = dict(U=rng.standard_normal((n * n, 3)), tol=1e-9, maxiter=60,
+                       store_arnoldi=True)
+    else:
+        raise KeyError(name)
+    return c
+
+
+ALL_CASES = [
+    "c1_gmres", "c1_cg", "c1_minres", "c1_gmres_defl", "c1_cg_defl", "c1_minres_defl",
+    "c1_gmres_store", "c1_cg_store", "c1_minres_store",
+    "lap2d_gmres30", "lap2d_gmres_mgs", "lap2d_gmres_dmgs", "poisson3d_cg_jacobi",
+    "convdiff_defl_gmres", "shifted_minres_ipB", "shifted_minres_ipB_f64",
+    "dense_gmres_M_ipB", "dense_minres_M_ipB", "dense_cg_M_ipB", "dense_gmres_MlMr",
+    "lucky_breakdown", "zero_rhs", "maxiter_noconv", "cg_explicit_residual",
+    "lap2d_defl_cg", "lap2d_defl_minres",
+]
