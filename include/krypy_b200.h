@@ -1,0 +1,176 @@
+/* krypy_b200 -- C ABI of the B200 (sm_100a) Krylov hot path.
+ *
+ * The reference (andrenarchy/krypy v2.2.0) is pure Python and has no FFI; its
+ * plugin surface is the Python operator/solver API.  This
+ * header is the boundary a maintainer binds with ctypes/cffi:
+ * every entry point replaces the NumPy/SciPy call(s) cited next to it
+ * (paths relative to the reference repository root).
+ *
+ * Conventions
+ *  - plain C types only; every pointer named *_dev / V / q / x / y ... is a DEVICE
+ *    pointer owned by the caller (e.g. torch.Tensor.data_ptr()); nothing here
+ *    allocates caller-visible memory.
+ *  - dtype: KRY_F32 / KRY_F64 selects the storage type of the N-sized vectors
+ *    and matrix values.  All small quantities (inner products, Hessenberg
+ *    entries, Givens rotations, coefficients) are double on both paths.
+ *  - a basis is stored VECTOR-MAJOR: vector j starts at V + j*ldv elements.
+ *  - all calls are asynchronous on the context's stream; kry_sync() is the only
+ *    blocking call.  Results the host needs for convergence control are written
+ *    by the kernels into a pinned "mailbox" (kry_mailbox_host) and are valid
+ *    after kry_sync().
+ *  - return value: 0 on success, negative error class otherwise; the message is
+ *    available from kry_last_error() (thread-local).  Never throws.
+ */
+#ifndef KRYPY_B200_H
+#define KRYPY_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KRY_ABI_VERSION 1
+
+#define KRY_OK               0
+#define KRY_ERR_ARG         -1
+#define KRY_ERR_CUDA        -2
+#define KRY_ERR_UNSUPPORTED -3
+
+#define KRY_F32 0
+#define KRY_F64 1
+
+#define KRY_MAILBOX_DOUBLES 16384
+
+typedef struct kry_ctx kry_ctx;
+
+/* ---- context ---------------------------------------------------------- */
+int         kry_version(void);
+const char* kry_last_error(void);
+/* stream: a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); 0 = default */
+int         kry_ctx_create(int device, void* stream, kry_ctx** out);
+int         kry_ctx_destroy(kry_ctx* ctx);
+int         kry_ctx_set_stream(kry_ctx* ctx, void* stream);
+/* info[0]=SM count, [1]=10*major+minor, [2]=L2 bytes, [3]=max opt-in smem/block,
+ * [4]=cooperative launch supported, [5]=max co-resident CTAs of the fused
+ * orthogonalisation kernel (f64) */
+int         kry_device_info(kry_ctx* ctx, long long info[8]);
+double*     kry_mailbox_host(kry_ctx* ctx);  /* pinned host view, KRY_MAILBOX_DOUBLES */
+double*     kry_mailbox_dev(kry_ctx* ctx);   /* device alias of the same memory      */
+int         kry_sync(kry_ctx* ctx);          /* cudaStreamSynchronize(stream)        */
+long long   kry_launch_count(kry_ctx* ctx);  /* kernels launched through this ctx    */
+void        kry_reset_launch_count(kry_ctx* ctx);
+
+/* ---- operators -------------------------------------------------------- */
+/* y = A x for CSR A (int32 indices).  Replaces scipy csr_matvec behind
+ * krypy/utils.py:1593-1594 (MatrixLinearOperator._dot) as called from
+ * utils.py:968 (Arnoldi.advance), linsys.py:631 (Cg), linsys.py:156.
+ * Optional fused epilogue (w_dev != NULL): dot_out_dev[0] = sum_i w[i]*y[i]
+ * (linsys.py:634, <p,Ap>).  y may be NULL when only the dot is wanted. */
+int kry_spmv_csr(kry_ctx* ctx, int dtype, long long nrows, long long ncols, long long nnz,
+                 const int* rowptr, const int* colidx, const void* vals,
+                 const void* x, void* y, const void* w_dev, double* dot_out_dev);
+/* y = A x for a dense row-major m x n matrix (numpy.ndarray.dot,
+ * krypy/utils.py:1593-1594; BASELINE config 1 and the reference's N<=100 tests) */
+int kry_gemv_dense(kry_ctx* ctx, int dtype, long long m, long long n,
+                   const void* A, long long lda, const void* x, void* y);
+/* y = d .* x  (a diagonal operator such as the Jacobi M of config C3,
+ * applied at linsys.py:661 / utils.py:1031) */
+int kry_diag_mul(kry_ctx* ctx, int dtype, long long n, const void* d, const void* x, void* y);
+
+/* ---- N-sized elementwise updates ---------------------------------------- */
+/* z = a*x + b*y (y may be NULL if b == 0; z may alias x or y).
+ * linsys.py:156 (b - A z), :427 (x0 + Mr yk), :627 (p = z + beta p). */
+int kry_axpby(kry_ctx* ctx, int dtype, long long n, double a, const void* x,
+              double b, const void* y, void* z);
+/* y += sign * coef_dev[0] * x   (utils.py:1007-1009, 1027-1029) */
+int kry_axpy_dev(kry_ctx* ctx, int dtype, long long n, const double* coef_dev, double sign,
+                 const void* x, void* y);
+/* out = mul * x / s_dev[0]   (divide != 0)   or   out = mul * x * s_dev[0]
+ * (utils.py:938, 950, 1042-1045; linsys.py:614-618, 669-671) */
+int kry_scale_dev(kry_ctx* ctx, int dtype, long long n, const double* s_dev, int divide,
+                  double mul, const void* x, void* out);
+
+/* ---- tall-skinny reductions / updates ----------------------------------- */
+/* out_dev[j] = sum_i V_j[i]*q[i], j < nv (deterministic two-stage reduction).
+ * post: 0 none, 1 out = sqrt(out).  acc_dev (may be NULL): acc_dev[j] += out[j].
+ * utils.py:183,191,193 (inner), :226-238 (norm), :540 (Projection._apply). */
+int kry_block_dot(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv,
+                  const void* q, double* out_dev, int post, double* acc_dev);
+/* q += sign * sum_j coef_dev[j] * V_j   (utils.py:549 + :621-624) */
+int kry_block_axpy(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv,
+                   const double* coef_dev, double sign, void* q);
+/* out = x0 + sum_j coef_dev[j] * V_j  (x0 may be NULL)
+ * (linsys.py:947-948 Gmres._get_xk; deflation.py:68) */
+int kry_block_combine(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv,
+                      const double* coef_dev, const void* x0, void* out);
+
+/* ---- fused Gram-Schmidt step (one cooperative kernel) ------------------- */
+/* Orthogonalise q against basis vectors j0..nv-1 (krypy/utils.py:996-1045):
+ *   algo KRY_ORTH_CGS: per pass c = Vdot^H q ; q -= Vsub c       (block, fused)
+ *   algo KRY_ORTH_MGS: per pass, for j: c_j = <Vdot_j,q>; q -= c_j Vsub_j
+ *                      (the reference's exact MGS order, utils.py:1012-1029)
+ * passes = 1 (mgs/cgs) or 2 (dmgs/cgs2).  h_dev[j] += c_j.
+ * pre_vec/pre_coef_dev (may be NULL): q -= pre_coef_dev[0]*pre_vec first
+ *   (Lanczos three-term recurrence, utils.py:1000-1009).
+ * nrm_dev (may be NULL): nrm_dev[0] = ||q||_2 afterwards (utils.py:1034).
+ * vnext (may be NULL; needs nrm_dev): vnext = q / nrm (utils.py:1045), zeros if
+ *   nrm == 0.
+ * Vdot/Vsub are the V and P bases of utils.py:1015,1027 (equal when M is None). */
+#define KRY_ORTH_CGS 0
+#define KRY_ORTH_MGS 1
+int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub,
+                   long long ldv, int j0, int nv, void* q, int passes, int algo,
+                   const void* pre_vec, const double* pre_coef_dev,
+                   double* h_dev, double* nrm_dev, void* vnext);
+
+/* ---- oblique projection for deflation (one cooperative kernel) ---------- */
+/* a <- (I - V (R^-1 Q^H) W^H)^iterations a  (krypy/utils.py:604-627 with
+ * :522-552; called from deflation.py:135-143).  W, V: d vectors each; Q, R:
+ * d x d row-major device matrices (Q may be NULL: identity transform, the
+ * orthogonal-projection case utils.py:510-512).  c_first_dev[0..d) receives the
+ * raw W^H a of the first application (Ya = WR^H c, utils.py:542-545). */
+int kry_project(kry_ctx* ctx, int dtype, long long n, const void* W, long long ldw,
+                const void* V, long long ldv, int d, void* a,
+                const double* Q_dev, const double* R_dev, int iterations,
+                double* c_first_dev);
+
+/* ---- small (latency-bound) device recurrences --------------------------- */
+/* GMRES Hessenberg update (krypy/linsys.py:982-993 + utils.py:405-436, drotg
+ * semantics): hcol_dev[0..k+1] is column k of H; applies the k stored
+ * rotations cs_dev[2i],cs_dev[2i+1], builds rotation k, rotates y_dev[k..k+1].
+ * rcol_dev[0..k+1] receives column k of R; hcol_dev is zeroed afterwards (the
+ * orthogonalisation kernels accumulate into it with +=).  Mailbox layout at
+ * mailbox[off..]: [ |y[k+1]|, H[0..k+1,k], R[0..k+1,k] ]  (2k+5 doubles). */
+int kry_givens_update(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev,
+                      double* cs_dev, double* y_dev, int mailbox_off);
+/* out_dev[0..k) = R[:k,:k]^{-1} y[:k], R row-major with leading dim ldr
+ * (scipy.linalg.solve_triangular, linsys.py:946) */
+int kry_tri_solve(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const double* y_dev,
+                  double* out_dev);
+/* MINRES sliding QR (krypy/linsys.py:827-847).  st_dev: 16 doubles of state
+ * [G1c,G1s,G1valid,G2c,G2s,G2valid,y0,-, R0,R1,R2,ycoef, ...] (zero-initialised,
+ * st[6] = ||r0||); h3_dev: [H[k-1,k], H[k,k], H[k+1,k]] as left by
+ * kry_orth_fused (h_dev -> &h3[1]-k, nrm_dev -> &h3[2]); with shift != 0, on return
+ * h3[0] = H[k+1,k] and h3[1] = 0 for the next step (utils.py:1003).
+ * Mailbox at off: [ |y_next|, R0, R1, R2, ycoef, H[k-1,k], H[k,k], H[k+1,k] ]. */
+int kry_minres_recur(kry_ctx* ctx, int k, double* h3_dev, double* st_dev, int shift, int mailbox_off);
+/* z = (v - R0*W0 - R1*W1)/R2 ; W0 <- W1 ; W1 <- z ; yk += ycoef*z, scalars from
+ * st_dev[8..11] (krypy/linsys.py:844-846). w0/w1 are swapped by the caller. */
+int kry_minres_update(kry_ctx* ctx, int dtype, long long n, const void* v, void* w0, const void* w1,
+                      void* yk, const double* st_dev);
+
+/* ---- CG fused update (one streaming kernel) ------------------------------ */
+/* krypy/linsys.py:634-665 with a diagonal (Jacobi) or identity M:
+ *   alpha = rho / pAp_dev[0];  yk += alpha p;  r -= alpha Ap;
+ *   z = dinv .* r (dinv NULL: M is the identity, z is not written);
+ *   rho_new = <r, z>.
+ * mailbox[off..] = [rho_new, alpha, pAp].  The search-direction update
+ * p = z + beta p (linsys.py:627) stays a separate kry_axpby because the host may
+ * replace rho by the explicit residual first (linsys.py:681-683). */
+int kry_cg_update(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk,
+                  void* r, void* z, const void* dinv, double rho, const double* pAp_dev,
+                  int mailbox_off);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KRYPY_B200_H */

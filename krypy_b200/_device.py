@@ -1,0 +1,244 @@
+"""Device plumbing: context handle, torch tensors as device-array containers,
+thin typed wrappers over the C ABI (include/krypy_b200.h).
+
+PyTorch is used only to own device memory and expose the current CUDA stream;
+every N-sized arithmetic operation goes through libkrypy_b200.so.
+
+Internal layout: a block of k vectors of length N is a contiguous torch tensor
+of shape ``(k, N)`` ("vector-major"); the public API exposes ``(N, k)`` numpy
+arrays like the reference does.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import KRY_F32, KRY_F64, check
+
+_torch = None
+
+
+def torch():
+    global _torch
+    if _torch is None:
+        import torch as _t
+        _torch = _t
+    return _torch
+
+
+def np_to_torch_dtype(dt):
+    t = torch()
+    dt = np.dtype(dt)
+    if dt == np.float64:
+        return t.float64
+    if dt == np.float32:
+        return t.float32
+    raise NotImplementedError(
+        "krypy_b200: dtype %s is not supported by the device path (float32/float64 only; "
+        "complex arithmetic is not implemented and there is no CPU fallback)" % dt)
+
+
+def torch_to_np_dtype(dt):
+    t = torch()
+    if dt == t.float64:
+        return np.dtype(np.float64)
+    if dt == t.float32:
+        return np.dtype(np.float32)
+    raise NotImplementedError("unsupported torch dtype %s" % dt)
+
+
+def code(t):
+    return KRY_F64 if t.dtype == torch().float64 else KRY_F32
+
+
+def _p(t):
+    return None if t is None else t.data_ptr()
+
+
+class CsrDev(object):
+    """CSR matrix resident in HBM (int32 row pointers / column indices)."""
+
+    def __init__(self, rowptr, colidx, vals, shape):
+        self.rowptr, self.colidx, self.vals = rowptr, colidx, vals
+        self.shape = (int(shape[0]), int(shape[1]))
+        self.nnz = int(vals.shape[0])
+
+    @property
+    def dtype(self):
+        return self.vals.dtype
+
+    def nbytes(self):
+        return (self.rowptr.numel() + self.colidx.numel()) * 4 + self.vals.numel() * self.vals.element_size()
+
+
+class Context(object):
+    """One per (process, device): owns the kry_ctx handle and the pinned mailbox."""
+
+    _instances = {}
+
+    @classmethod
+    def get(cls, device=None):
+        t = torch()
+        if not t.cuda.is_available():
+            raise RuntimeError(
+                "krypy_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+        idx = t.cuda.current_device() if device is None else t.device(device).index
+        if idx is None:
+            idx = t.cuda.current_device()
+        inst = cls._instances.get(idx)
+        if inst is None:
+            inst = cls._instances[idx] = cls(idx)
+        return inst
+
+    def __init__(self, idx):
+        t = torch()
+        self.lib = lib = _lib.load()
+        self.index = idx
+        self.device = t.device("cuda", idx)
+        self.stream_handle = t.cuda.current_stream(self.device).cuda_stream
+        h = ctypes.c_void_p()
+        check(lib.kry_ctx_create(idx, ctypes.c_void_p(self.stream_handle), ctypes.byref(h)))
+        self.h = h
+        host = lib.kry_mailbox_host(h)
+        self.mailbox = np.ctypeslib.as_array(
+            ctypes.cast(host, ctypes.POINTER(ctypes.c_double)), shape=(_lib.KRY_MAILBOX_DOUBLES,))
+        info = (ctypes.c_longlong * 8)()
+        check(lib.kry_device_info(h, info))
+        self.sm_count, self.cc, self.l2_bytes = int(info[0]), int(info[1]), int(info[2])
+        self.orth_blocks = int(info[5])
+
+    # ---- stream / sync ------------------------------------------------
+    def use_current_stream(self):
+        s = torch().cuda.current_stream(self.device).cuda_stream
+        if s != self.stream_handle:
+            self.stream_handle = s
+            check(self.lib.kry_ctx_set_stream(self.h, ctypes.c_void_p(s)))
+
+    def sync(self):
+        check(self.lib.kry_sync(self.h))
+
+    def launch_count(self):
+        return int(self.lib.kry_launch_count(self.h))
+
+    def reset_launch_count(self):
+        self.lib.kry_reset_launch_count(self.h)
+
+    # ---- allocation / conversion ---------------------------------------
+    def empty(self, shape, dtype):
+        return torch().empty(shape, dtype=dtype, device=self.device)
+
+    def zeros(self, shape, dtype):
+        return torch().zeros(shape, dtype=dtype, device=self.device)
+
+    def scalars(self, n):
+        """n zeroed device doubles (small coefficients always live in fp64)."""
+        return torch().zeros(n, dtype=torch().float64, device=self.device)
+
+    def to_block(self, X, dtype):
+        """numpy/torch array (N,) or (N,k) -> contiguous device tensor (k, N)."""
+        t = torch()
+        if isinstance(X, t.Tensor):
+            if X.is_complex():
+                raise NotImplementedError("complex vectors are not supported by the device path")
+            Xt = X.detach().to(device=self.device, dtype=dtype)
+            Xt = Xt.reshape(1, -1) if Xt.dim() == 1 else Xt.t()
+            return Xt.contiguous().clone()   # inputs are never mutated (ownership)
+        X = np.asarray(X)
+        if np.iscomplexobj(X):
+            raise NotImplementedError("complex vectors are not supported by the device path")
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        Xh = np.ascontiguousarray(X.T, dtype=torch_to_np_dtype(dtype))
+        return t.from_numpy(Xh).to(self.device)
+
+    def to_numpy(self, Xd):
+        """device (k, N) -> numpy (N, k)."""
+        return np.ascontiguousarray(Xd.detach().cpu().numpy().T)
+
+    def upload_csr(self, A, dtype):
+        """scipy.sparse matrix (any format) -> CsrDev."""
+        import scipy.sparse as sp
+        t = torch()
+        A = sp.csr_matrix(A) if not sp.isspmatrix_csr(A) else A
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        if A.nnz >= 2 ** 31 - 1:
+            raise NotImplementedError("nnz >= 2^31 needs 64-bit row pointers (not built)")
+        npdt = torch_to_np_dtype(dtype)
+        rowptr = t.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int32)).to(self.device)
+        colidx = t.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).to(self.device)
+        vals = t.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)).to(self.device)
+        return CsrDev(rowptr, colidx, vals, A.shape)
+
+    # ---- operators -------------------------------------------------------
+    def spmv(self, A, x, y, w=None, dot_out=None):
+        check(self.lib.kry_spmv_csr(self.h, code(A.vals), A.shape[0], A.shape[1], A.nnz,
+                                    A.rowptr.data_ptr(), A.colidx.data_ptr(), A.vals.data_ptr(),
+                                    x.data_ptr(), _p(y), _p(w), _p(dot_out)))
+
+    def gemv(self, A, x, y):
+        check(self.lib.kry_gemv_dense(self.h, code(A), A.shape[0], A.shape[1], A.data_ptr(),
+                                      A.stride(0), x.data_ptr(), y.data_ptr()))
+
+    def diag_mul(self, d, x, y):
+        check(self.lib.kry_diag_mul(self.h, code(x), x.numel(), d.data_ptr(), x.data_ptr(), y.data_ptr()))
+
+    # ---- elementwise -------------------------------------------------------
+    def axpby(self, a, x, b, y, z):
+        check(self.lib.kry_axpby(self.h, code(x), x.numel(), float(a), x.data_ptr(), float(b), _p(y),
+                                 z.data_ptr()))
+
+    def axpy_dev(self, coef, sign, x, y):
+        check(self.lib.kry_axpy_dev(self.h, code(x), x.numel(), coef.data_ptr(), float(sign),
+                                    x.data_ptr(), y.data_ptr()))
+
+    def scale_dev(self, s, divide, mul, x, out):
+        check(self.lib.kry_scale_dev(self.h, code(x), x.numel(), s.data_ptr(), int(divide), float(mul),
+                                     x.data_ptr(), out.data_ptr()))
+
+    # ---- tall-skinny -----------------------------------------------------
+    def block_dot(self, V, nv, q, out, post=0, acc=None):
+        """out[j] = <V[j], q>, j < nv.  V: (>=nv, N) tensor (row stride = ld)."""
+        check(self.lib.kry_block_dot(self.h, code(q), q.numel(), _p(V), V.stride(0) if V is not None else 0,
+                                     int(nv), q.data_ptr(), out.data_ptr(), int(post), _p(acc)))
+
+    def block_axpy(self, V, nv, coef, sign, q):
+        check(self.lib.kry_block_axpy(self.h, code(q), q.numel(), V.data_ptr(), V.stride(0), int(nv),
+                                      coef.data_ptr(), float(sign), q.data_ptr()))
+
+    def block_combine(self, V, nv, coef, x0, out):
+        check(self.lib.kry_block_combine(self.h, code(out), out.numel(), _p(V),
+                                         V.stride(0) if V is not None else 0, int(nv), _p(coef), _p(x0),
+                                         out.data_ptr()))
+
+    def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
+                   pre_coef=None, h_ptr=None):
+        ld = Vdot.stride(0) if Vdot is not None else 0
+        hp = h_ptr if h_ptr is not None else _p(h)
+        check(self.lib.kry_orth_fused(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, int(j0), int(nv),
+                                      q.data_ptr(), int(passes), int(algo), _p(pre_vec), _p(pre_coef),
+                                      hp, _p(nrm), _p(vnext)))
+
+    def project(self, W, V, d, a, Q, R, iterations, c_first):
+        check(self.lib.kry_project(self.h, code(a), a.numel(), W.data_ptr(), W.stride(0), V.data_ptr(),
+                                   V.stride(0), int(d), a.data_ptr(), _p(Q), _p(R), int(iterations),
+                                   _p(c_first)))
+
+    # ---- small recurrences -------------------------------------------------
+    def givens_update(self, k, hcol, rcol, cs, y, off=0):
+        check(self.lib.kry_givens_update(self.h, int(k), hcol.data_ptr(), rcol.data_ptr(), cs.data_ptr(),
+                                         y.data_ptr(), int(off)))
+
+    def tri_solve(self, k, R, y, out):
+        check(self.lib.kry_tri_solve(self.h, int(k), R.data_ptr(), R.stride(0), y.data_ptr(), out.data_ptr()))
+
+    def minres_recur(self, k, h3, st, shift=1, off=0):
+        check(self.lib.kry_minres_recur(self.h, int(k), h3.data_ptr(), st.data_ptr(), int(shift), int(off)))
+
+    def minres_update(self, v, w0, w1, yk, st):
+        check(self.lib.kry_minres_update(self.h, code(v), v.numel(), v.data_ptr(), w0.data_ptr(),
+                                         w1.data_ptr(), yk.data_ptr(), st.data_ptr()))
+
+    def cg_update(self, Ap, p, yk, r, z, dinv, rho, pAp, off=0):
+        check(self.lib.kry_cg_update(self.h, code(p), p.numel(), Ap.data_ptr(), p.data_ptr(), yk.data_ptr(),
+                                     r.data_ptr(), _p(z), _p(dinv), float(rho), pAp.data_ptr(), int(off)))

@@ -1,0 +1,120 @@
+// Context, error reporting, pinned mailbox.
+#include <stdarg.h>
+#include "kry_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void kry_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int kry_orth_max_blocks(int dtype, int* out);   // kry_orth.cu
+int kry_proj_max_blocks(int dtype, int* out);   // kry_orth.cu
+
+extern "C" {
+
+int kry_version(void) { return KRY_ABI_VERSION; }
+
+const char* kry_last_error(void) { return g_err; }
+
+int kry_ctx_create(int device, void* stream, kry_ctx** out) {
+    KRY_REQUIRE(out != nullptr, "out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        kry_set_error("no CUDA device available (%s): krypy_b200 has no CPU fallback",
+                      cudaGetErrorString(e));
+        return KRY_ERR_CUDA;
+    }
+    KRY_REQUIRE(device >= 0 && device < ndev, "device index out of range");
+    KRY_CHECK_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    KRY_CHECK_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        kry_set_error("device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                      prop.major, prop.minor);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    kry_ctx* c = new kry_ctx();
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->stream = (cudaStream_t)stream;
+    c->sm_count = prop.multiProcessorCount;
+    c->cc = prop.major * 10 + prop.minor;
+    c->l2_bytes = prop.l2CacheSize;
+    c->smem_optin = (long long)prop.sharedMemPerBlockOptin;
+    c->coop = prop.cooperativeLaunch;
+    size_t pbytes = sizeof(double) * 2ull * KRY_MAX_SLOTS * KRY_MAX_PARTIAL_BLOCKS;
+    KRY_CHECK_CUDA(cudaMalloc(&c->d_partials, pbytes));
+    KRY_CHECK_CUDA(cudaMemset(c->d_partials, 0, pbytes));
+    KRY_CHECK_CUDA(cudaMalloc(&c->d_ticket, 64 * sizeof(unsigned int)));
+    KRY_CHECK_CUDA(cudaMemset(c->d_ticket, 0, 64 * sizeof(unsigned int)));
+    KRY_CHECK_CUDA(cudaHostAlloc(&c->h_mailbox, sizeof(double) * KRY_MAILBOX_DOUBLES,
+                                 cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(c->h_mailbox, 0, sizeof(double) * KRY_MAILBOX_DOUBLES);
+    KRY_CHECK_CUDA(cudaHostGetDevicePointer(&c->d_mailbox, c->h_mailbox, 0));
+    if (!c->coop) {
+        kry_set_error("device does not support cooperative launches");
+        return KRY_ERR_UNSUPPORTED;
+    }
+    int rc;
+    if ((rc = kry_orth_max_blocks(KRY_F64, &c->orth_blocks_f64))) return rc;
+    if ((rc = kry_orth_max_blocks(KRY_F32, &c->orth_blocks_f32))) return rc;
+    if ((rc = kry_proj_max_blocks(KRY_F64, &c->proj_blocks_f64))) return rc;
+    if ((rc = kry_proj_max_blocks(KRY_F32, &c->proj_blocks_f32))) return rc;
+    c->orth_blocks_f64 *= c->sm_count;
+    c->orth_blocks_f32 *= c->sm_count;
+    c->proj_blocks_f64 *= c->sm_count;
+    c->proj_blocks_f32 *= c->sm_count;
+    *out = c;
+    return KRY_OK;
+}
+
+int kry_ctx_destroy(kry_ctx* ctx) {
+    if (!ctx) return KRY_OK;
+    cudaSetDevice(ctx->device);
+    cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_ticket);
+    cudaFreeHost(ctx->h_mailbox);
+    delete ctx;
+    return KRY_OK;
+}
+
+int kry_ctx_set_stream(kry_ctx* ctx, void* stream) {
+    KRY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    ctx->stream = (cudaStream_t)stream;
+    return KRY_OK;
+}
+
+int kry_device_info(kry_ctx* ctx, long long info[8]) {
+    KRY_REQUIRE(ctx != nullptr && info != nullptr, "NULL argument");
+    info[0] = ctx->sm_count;
+    info[1] = ctx->cc;
+    info[2] = ctx->l2_bytes;
+    info[3] = ctx->smem_optin;
+    info[4] = ctx->coop;
+    info[5] = ctx->orth_blocks_f64;
+    info[6] = ctx->proj_blocks_f64;
+    info[7] = 0;
+    return KRY_OK;
+}
+
+double* kry_mailbox_host(kry_ctx* ctx) { return ctx ? ctx->h_mailbox : nullptr; }
+double* kry_mailbox_dev(kry_ctx* ctx) { return ctx ? ctx->d_mailbox : nullptr; }
+
+int kry_sync(kry_ctx* ctx) {
+    KRY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    KRY_CHECK_CUDA(cudaStreamSynchronize(ctx->stream));
+    return KRY_OK;
+}
+
+long long kry_launch_count(kry_ctx* ctx) { return ctx ? ctx->launches : -1; }
+void kry_reset_launch_count(kry_ctx* ctx) {
+    if (ctx) ctx->launches = 0;
+}
+
+}  // extern "C"

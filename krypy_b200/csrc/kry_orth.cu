@@ -1,0 +1,583 @@
+// Fused Gram-Schmidt step and fused oblique (deflation) projection: ONE
+// cooperative persistent kernel each.  HBM-bound tall-skinny sweeps:
+//   phase A  c = Vdot^H q      (register tile of JT basis vectors per pass over q,
+//                               warp-shuffle + shared-memory CTA reduction,
+//                               per-CTA partials, grid.sync, fixed-order final sum
+//                               recomputed identically by every CTA)
+//   phase B  q -= Vsub c       (+ ||q||^2 partials in the epilogue)
+//   phase C  vnext = q / ||q||
+// Every thread owns the same q elements in every phase (identical grid-stride
+// map), so the only grid-wide dependencies are the reductions themselves.
+// Reductions are deterministic for a fixed grid size.
+#include "kry_common.cuh"
+
+#define KRY_ENTER(ctx)                                                         \
+    KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+#define ORTH_JT 16
+
+// value as it reads back after being stored as T (identity for double)
+template <typename T> __device__ __forceinline__ double round_as(double v) { return (double)(T)v; }
+
+template <typename T>
+struct OrthArgs {
+    long long n;
+    const T* Vdot;
+    const T* Vsub;
+    long long ldv;
+    int j0, nv, passes, algo;
+    T* q;
+    const T* pre_vec;
+    const double* pre_coef;
+    double* h;
+    double* nrm;
+    T* vnext;
+    double* partials;   // [2][KRY_MAX_SLOTS][KRY_MAX_PARTIAL_BLOCKS]
+};
+
+__device__ __forceinline__ double* partial_slot(double* partials, int buf, int slot) {
+    return partials + ((size_t)buf * KRY_MAX_SLOTS + (size_t)slot) * KRY_MAX_PARTIAL_BLOCKS;
+}
+
+// fixed-order sum of one slot's per-CTA partials; identical in every CTA
+__device__ __forceinline__ double reduce_slot(double* partials, int buf, int slot, double* sm) {
+    const double* p = partial_slot(partials, buf, slot);
+    double v = 0.0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v += __ldcg(p + b);
+    return kry_block_sum(v, sm);
+}
+
+// c[slot] for slots [0, cnt): warps split the slots, lanes stride over CTAs
+__device__ __forceinline__ void reduce_slots(double* partials, int buf, int cnt, double* c_s) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int s = w; s < cnt; s += nw) {
+        const double* p = partial_slot(partials, buf, s);
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(p + b);
+        v = kry_warp_sum(v);
+        if (lane == 0) c_s[s] = v;
+    }
+    __syncthreads();
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[32];
+    __shared__ double c_s[KRY_MAX_SLOTS];
+    const long long n = a.n, ldv = a.ldv;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tail0 = nvec * VEC + threadIdx.x;   // scalar tail handled by CTA 0
+    const bool tail_cta = (blockIdx.x == 0);
+    T* q = a.q;
+    int buf = 0;
+    const int cnt = a.nv - a.j0;
+    bool pre_pending = (a.pre_vec != nullptr);
+    const double pre_c = pre_pending ? a.pre_coef[0] : 0.0;
+    double nrm2_part = 0.0;
+
+    if (a.algo == KRY_ORTH_CGS) {
+        for (int pass = 0; pass < a.passes; ++pass) {
+            // ---- phase A: block dots ----
+            for (int jb = 0; jb < cnt || (jb == 0 && pre_pending); jb += ORTH_JT) {
+                double acc[ORTH_JT];
+#pragma unroll
+                for (int t = 0; t < ORTH_JT; ++t) acc[t] = 0.0;
+                for (long long i = i0; i < nvec; i += stride) {
+                    double qv[VEC];
+                    VecIO<T, VEC>::loadrw(q, i, qv);
+                    if (pre_pending) {
+                        double pv[VEC];
+                        VecIO<T, VEC>::load(a.pre_vec, i, pv);
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, pv[u], qv[u]);
+                        VecIO<T, VEC>::store(q, i, qv);
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);   // value as stored
+                    }
+                    if (cnt > 0) {
+#pragma unroll
+                        for (int tb = 0; tb < ORTH_JT; tb += 8) {
+                            if (jb + tb < cnt) {
+                                double vv[8][VEC];
+#pragma unroll
+                                for (int t = 0; t < 8; ++t) {
+                                    int j = jb + tb + t;
+                                    j = j < cnt ? j : cnt - 1;
+                                    VecIO<T, VEC>::load(a.Vdot + (long long)(a.j0 + j) * ldv, i, vv[t]);
+                                }
+#pragma unroll
+                                for (int t = 0; t < 8; ++t)
+#pragma unroll
+                                    for (int u = 0; u < VEC; ++u) acc[tb + t] = fma(vv[t][u], qv[u], acc[tb + t]);
+                            }
+                        }
+                    }
+                }
+                if (tail_cta) {
+                    for (long long i = tail0; i < n; i += blockDim.x) {
+                        double qe = (double)q[i];
+                        if (pre_pending) {
+                            qe = fma(-pre_c, (double)a.pre_vec[i], qe);
+                            q[i] = (T)qe;
+                            qe = (double)q[i];
+                        }
+#pragma unroll
+                        for (int t = 0; t < ORTH_JT; ++t)
+                            if (jb + t < cnt)
+                                acc[t] = fma((double)a.Vdot[(long long)(a.j0 + jb + t) * ldv + i], qe, acc[t]);
+                    }
+                }
+                pre_pending = false;
+#pragma unroll
+                for (int t = 0; t < ORTH_JT; ++t) {
+                    if (jb + t < cnt) {   // uniform across the CTA
+                        double s = kry_block_sum(acc[t], sm);
+                        if (threadIdx.x == 0) partial_slot(a.partials, buf, jb + t)[blockIdx.x] = s;
+                    }
+                }
+            }
+            grid.sync();
+            reduce_slots(a.partials, buf, cnt, c_s);
+            if (blockIdx.x == 0)
+                for (int s = threadIdx.x; s < cnt; s += blockDim.x) a.h[a.j0 + s] += c_s[s];
+            buf ^= 1;
+            // ---- phase B: q -= Vsub c ----
+            const bool want_nrm = (a.nrm != nullptr) && (pass == a.passes - 1);
+            for (long long i = i0; i < nvec; i += stride) {
+                double qv[VEC];
+                VecIO<T, VEC>::loadrw(q, i, qv);
+                for (int jb = 0; jb < cnt; jb += 8) {
+                    double vv[8][VEC];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) {
+                        int j = jb + t < cnt ? jb + t : cnt - 1;
+                        VecIO<T, VEC>::load(a.Vsub + (long long)(a.j0 + j) * ldv, i, vv[t]);
+                    }
+#pragma unroll
+                    for (int t = 0; t < 8; ++t)
+                        if (jb + t < cnt) {
+                            const double c = c_s[jb + t];
+#pragma unroll
+                            for (int u = 0; u < VEC; ++u) qv[u] = fma(-c, vv[t][u], qv[u]);
+                        }
+                }
+                VecIO<T, VEC>::store(q, i, qv);
+                if (want_nrm) {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) {
+                        const double r = round_as<T>(qv[u]);
+                        nrm2_part = fma(r, r, nrm2_part);
+                    }
+                }
+            }
+            if (tail_cta) {
+                for (long long i = tail0; i < n; i += blockDim.x) {
+                    double qe = (double)q[i];
+                    for (int j = 0; j < cnt; ++j)
+                        qe = fma(-c_s[j], (double)a.Vsub[(long long)(a.j0 + j) * ldv + i], qe);
+                    q[i] = (T)qe;
+                    qe = (double)q[i];
+                    if (want_nrm) nrm2_part = fma(qe, qe, nrm2_part);
+                }
+            }
+            __syncthreads();   // c_s is rewritten by the next pass
+        }
+    } else {
+        // ---- exact modified Gram-Schmidt: one dependent reduction per basis vector ----
+        double c_prev = 0.0;
+        int j_prev = -1;
+        for (int pass = 0; pass < a.passes; ++pass) {
+            for (int j = a.j0; j < a.nv; ++j) {
+                double acc = 0.0;
+                const T* vj = a.Vdot + (long long)j * ldv;
+                const T* vp = j_prev >= 0 ? a.Vsub + (long long)j_prev * ldv : nullptr;
+                const bool modify = (j_prev >= 0) || pre_pending;
+                for (long long i = i0; i < nvec; i += stride) {
+                    double qv[VEC], vv[VEC];
+                    VecIO<T, VEC>::loadrw(q, i, qv);
+                    VecIO<T, VEC>::load(vj, i, vv);
+                    if (pre_pending) {
+                        double pv[VEC];
+                        VecIO<T, VEC>::load(a.pre_vec, i, pv);
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, pv[u], qv[u]);
+                    }
+                    if (vp) {
+                        double pv[VEC];
+                        VecIO<T, VEC>::load(vp, i, pv);
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) qv[u] = fma(-c_prev, pv[u], qv[u]);
+                    }
+                    if (modify) {
+                        VecIO<T, VEC>::store(q, i, qv);
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);
+                    }
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) acc = fma(vv[u], qv[u], acc);
+                }
+                if (tail_cta) {
+                    for (long long i = tail0; i < n; i += blockDim.x) {
+                        double qe = (double)q[i];
+                        if (pre_pending) qe = fma(-pre_c, (double)a.pre_vec[i], qe);
+                        if (vp) qe = fma(-c_prev, (double)vp[i], qe);
+                        if (modify) {
+                            q[i] = (T)qe;
+                            qe = (double)q[i];
+                        }
+                        acc = fma((double)vj[i], qe, acc);
+                    }
+                }
+                pre_pending = false;
+                double s = kry_block_sum(acc, sm);
+                if (threadIdx.x == 0) partial_slot(a.partials, buf, 0)[blockIdx.x] = s;
+                grid.sync();
+                c_prev = reduce_slot(a.partials, buf, 0, sm);
+                j_prev = j;
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.h[j] += c_prev;
+                buf ^= 1;
+            }
+        }
+        // flush the pending subtraction (and a lone pre-subtraction when nv == j0)
+        const T* vp = j_prev >= 0 ? a.Vsub + (long long)j_prev * ldv : nullptr;
+        const bool want_nrm = (a.nrm != nullptr);
+        if (vp || pre_pending || want_nrm) {
+            for (long long i = i0; i < nvec; i += stride) {
+                double qv[VEC];
+                VecIO<T, VEC>::loadrw(q, i, qv);
+                if (pre_pending) {
+                    double pv[VEC];
+                    VecIO<T, VEC>::load(a.pre_vec, i, pv);
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, pv[u], qv[u]);
+                }
+                if (vp) {
+                    double pv[VEC];
+                    VecIO<T, VEC>::load(vp, i, pv);
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) qv[u] = fma(-c_prev, pv[u], qv[u]);
+                }
+                if (vp || pre_pending) {
+                    VecIO<T, VEC>::store(q, i, qv);
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);
+                }
+                if (want_nrm) {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) nrm2_part = fma(qv[u], qv[u], nrm2_part);
+                }
+            }
+            if (tail_cta) {
+                for (long long i = tail0; i < n; i += blockDim.x) {
+                    double qe = (double)q[i];
+                    if (pre_pending) qe = fma(-pre_c, (double)a.pre_vec[i], qe);
+                    if (vp) qe = fma(-c_prev, (double)vp[i], qe);
+                    if (vp || pre_pending) {
+                        q[i] = (T)qe;
+                        qe = (double)q[i];
+                    }
+                    if (want_nrm) nrm2_part = fma(qe, qe, nrm2_part);
+                }
+            }
+        }
+    }
+
+    // ---- norm and phase C ----
+    if (a.nrm != nullptr) {
+        double s = kry_block_sum(nrm2_part, sm);
+        if (threadIdx.x == 0) partial_slot(a.partials, buf, 0)[blockIdx.x] = s;
+        grid.sync();
+        const double nrm = sqrt(reduce_slot(a.partials, buf, 0, sm));
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.nrm[0] = nrm;
+        if (a.vnext != nullptr) {
+            for (long long i = i0; i < nvec; i += stride) {
+                double qv[VEC];
+                VecIO<T, VEC>::loadrw(q, i, qv);
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) qv[u] = nrm > 0.0 ? qv[u] / nrm : 0.0;
+                VecIO<T, VEC>::store(a.vnext, i, qv);
+            }
+            if (tail_cta)
+                for (long long i = tail0; i < n; i += blockDim.x)
+                    a.vnext[i] = (T)(nrm > 0.0 ? (double)q[i] / nrm : 0.0);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// oblique projection  a <- (I - V R^-1 Q^H W^H)^iterations a
+// ---------------------------------------------------------------------------
+template <typename T>
+struct ProjArgs {
+    long long n;
+    const T* W;
+    long long ldw;
+    const T* V;
+    long long ldv;
+    int d, iterations;
+    T* a;
+    const double* Q;
+    const double* R;
+    double* c_first;
+    double* partials;
+};
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2) proj_kernel(ProjArgs<T> p) {
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double sm[32];
+    __shared__ double c_s[KRY_MAX_SLOTS];
+    __shared__ double t_s[KRY_MAX_SLOTS];
+    const long long n = p.n;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long tail0 = nvec * VEC + threadIdx.x;
+    const bool tail_cta = (blockIdx.x == 0);
+    const int d = p.d;
+    T* av = p.a;
+    int buf = 0;
+    for (int iter = 0; iter < p.iterations; ++iter) {
+        for (int jb = 0; jb < d; jb += ORTH_JT) {
+            double acc[ORTH_JT];
+#pragma unroll
+            for (int t = 0; t < ORTH_JT; ++t) acc[t] = 0.0;
+            for (long long i = i0; i < nvec; i += stride) {
+                double qv[VEC];
+                VecIO<T, VEC>::loadrw(av, i, qv);
+#pragma unroll
+                for (int tb = 0; tb < ORTH_JT; tb += 8) {
+                    if (jb + tb < d) {
+                        double vv[8][VEC];
+#pragma unroll
+                        for (int t = 0; t < 8; ++t) {
+                            int j = jb + tb + t;
+                            j = j < d ? j : d - 1;
+                            VecIO<T, VEC>::load(p.W + (long long)j * p.ldw, i, vv[t]);
+                        }
+#pragma unroll
+                        for (int t = 0; t < 8; ++t)
+#pragma unroll
+                            for (int u = 0; u < VEC; ++u) acc[tb + t] = fma(vv[t][u], qv[u], acc[tb + t]);
+                    }
+                }
+            }
+            if (tail_cta) {
+                for (long long i = tail0; i < n; i += blockDim.x) {
+                    const double qe = (double)av[i];
+#pragma unroll
+                    for (int t = 0; t < ORTH_JT; ++t)
+                        if (jb + t < d) acc[t] = fma((double)p.W[(long long)(jb + t) * p.ldw + i], qe, acc[t]);
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < ORTH_JT; ++t) {
+                if (jb + t < d) {
+                    double s = kry_block_sum(acc[t], sm);
+                    if (threadIdx.x == 0) partial_slot(p.partials, buf, jb + t)[blockIdx.x] = s;
+                }
+            }
+        }
+        grid.sync();
+        reduce_slots(p.partials, buf, d, c_s);
+        buf ^= 1;
+        if (iter == 0 && p.c_first && blockIdx.x == 0)
+            for (int s = threadIdx.x; s < d; s += blockDim.x) p.c_first[s] = c_s[s];
+        // x = R^{-1} Q^H c   (utils.py:547-548), every CTA redundantly and identically
+        if (p.Q != nullptr) {
+            for (int i = threadIdx.x; i < d; i += blockDim.x) {
+                double t = 0.0;
+                for (int j = 0; j < d; ++j) t = fma(__ldg(p.Q + (long long)j * d + i), c_s[j], t);
+                t_s[i] = t;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                for (int j = d - 1; j >= 0; --j) {   // column-oriented back substitution
+                    const double xj = t_s[j] / __ldg(p.R + (long long)j * d + j);
+                    t_s[j] = xj;
+                    for (int i = 0; i < j; ++i) t_s[i] = fma(-xj, __ldg(p.R + (long long)i * d + j), t_s[i]);
+                }
+            }
+            __syncthreads();
+        } else {
+            for (int i = threadIdx.x; i < d; i += blockDim.x) t_s[i] = c_s[i];
+            __syncthreads();
+        }
+        // a -= V x
+        for (long long i = i0; i < nvec; i += stride) {
+            double qv[VEC];
+            VecIO<T, VEC>::loadrw(av, i, qv);
+            // reference forms Pa = V.dot(x) first and then subtracts (utils.py:549, 621)
+            double pa[VEC];
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) pa[u] = 0.0;
+            for (int jb = 0; jb < d; jb += 8) {
+                double vv[8][VEC];
+#pragma unroll
+                for (int t = 0; t < 8; ++t) {
+                    int j = jb + t < d ? jb + t : d - 1;
+                    VecIO<T, VEC>::load(p.V + (long long)j * p.ldv, i, vv[t]);
+                }
+#pragma unroll
+                for (int t = 0; t < 8; ++t)
+                    if (jb + t < d) {
+                        const double c = t_s[jb + t];
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) pa[u] = fma(c, vv[t][u], pa[u]);
+                    }
+            }
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) qv[u] -= pa[u];
+            VecIO<T, VEC>::store(av, i, qv);
+        }
+        if (tail_cta) {
+            for (long long i = tail0; i < n; i += blockDim.x) {
+                double pa = 0.0;
+                for (int j = 0; j < d; ++j) pa = fma(t_s[j], (double)p.V[(long long)j * p.ldv + i], pa);
+                av[i] = (T)((double)av[i] - pa);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+template <typename K>
+static int max_blocks_of(K kern, int* out) {
+    int nb = 0;
+    KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, KRY_THREADS, 0));
+    *out = nb;
+    return KRY_OK;
+}
+
+int kry_orth_max_blocks(int dtype, int* out) {
+    int a = 0, b = 0, rc;
+    if (dtype == KRY_F64) {
+        if ((rc = max_blocks_of(orth_kernel<double, 2>, &a))) return rc;
+        if ((rc = max_blocks_of(orth_kernel<double, 1>, &b))) return rc;
+    } else {
+        if ((rc = max_blocks_of(orth_kernel<float, 4>, &a))) return rc;
+        if ((rc = max_blocks_of(orth_kernel<float, 1>, &b))) return rc;
+    }
+    *out = a < b ? a : b;
+    KRY_REQUIRE(*out >= 1, "orth kernel does not fit");
+    return KRY_OK;
+}
+
+int kry_proj_max_blocks(int dtype, int* out) {
+    int a = 0, b = 0, rc;
+    if (dtype == KRY_F64) {
+        if ((rc = max_blocks_of(proj_kernel<double, 2>, &a))) return rc;
+        if ((rc = max_blocks_of(proj_kernel<double, 1>, &b))) return rc;
+    } else {
+        if ((rc = max_blocks_of(proj_kernel<float, 4>, &a))) return rc;
+        if ((rc = max_blocks_of(proj_kernel<float, 1>, &b))) return rc;
+    }
+    *out = a < b ? a : b;
+    KRY_REQUIRE(*out >= 1, "projection kernel does not fit");
+    return KRY_OK;
+}
+
+static int coop_grid(long long work_items, int max_blocks) {
+    long long need = (work_items + KRY_THREADS - 1) / KRY_THREADS;
+    if (need < 1) need = 1;
+    long long cap = max_blocks < KRY_MAX_PARTIAL_BLOCKS ? max_blocks : KRY_MAX_PARTIAL_BLOCKS;
+    return (int)(need < cap ? need : cap);
+}
+
+template <typename T>
+static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
+    const int W = VecWidth<T>::value;
+    bool al = kry_aligned16(a.Vdot) && kry_aligned16(a.Vsub) && kry_aligned16(a.q) && (a.ldv % W == 0) &&
+              (!a.pre_vec || kry_aligned16(a.pre_vec)) && (!a.vnext || kry_aligned16(a.vnext));
+    void* args[] = {&a};
+    if (al) {
+        int g = coop_grid(a.n / W, max_blocks);
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)orth_kernel<T, W>, dim3(g), dim3(KRY_THREADS), args, 0,
+                                                   ctx->stream));
+    } else {
+        int g = coop_grid(a.n, max_blocks);
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)orth_kernel<T, 1>, dim3(g), dim3(KRY_THREADS), args, 0,
+                                                   ctx->stream));
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+template <typename T>
+static int proj_launch(kry_ctx* ctx, ProjArgs<T>& p, int max_blocks) {
+    const int W = VecWidth<T>::value;
+    bool al = kry_aligned16(p.W) && kry_aligned16(p.V) && kry_aligned16(p.a) && (p.ldw % W == 0) && (p.ldv % W == 0);
+    void* args[] = {&p};
+    if (al) {
+        int g = coop_grid(p.n / W, max_blocks);
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)proj_kernel<T, W>, dim3(g), dim3(KRY_THREADS), args, 0,
+                                                   ctx->stream));
+    } else {
+        int g = coop_grid(p.n, max_blocks);
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)proj_kernel<T, 1>, dim3(g), dim3(KRY_THREADS), args, 0,
+                                                   ctx->stream));
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+extern "C" {
+
+int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub, long long ldv, int j0,
+                   int nv, void* q, int passes, int algo, const void* pre_vec, const double* pre_coef_dev,
+                   double* h_dev, double* nrm_dev, void* vnext) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && q, "bad arguments");
+    KRY_REQUIRE(j0 >= 0 && nv >= j0, "bad basis range");
+    KRY_REQUIRE(nv == j0 || (Vdot && Vsub && h_dev), "NULL basis / h");
+    KRY_REQUIRE(passes == 1 || passes == 2, "passes must be 1 or 2");
+    KRY_REQUIRE(algo == KRY_ORTH_CGS || algo == KRY_ORTH_MGS, "unknown algo");
+    KRY_REQUIRE(!pre_vec || pre_coef_dev, "pre_vec without pre_coef_dev");
+    KRY_REQUIRE(!vnext || nrm_dev, "vnext requires nrm_dev");
+    KRY_REQUIRE(algo != KRY_ORTH_CGS || nv - j0 <= KRY_MAX_SLOTS, "CGS: too many vectors in one call");
+    if (!Vdot) Vdot = q;   // never dereferenced when nv == j0; keeps alignment checks simple
+    if (!Vsub) Vsub = q;
+    if (dtype == KRY_F64) {
+        OrthArgs<double> a = {n, (const double*)Vdot, (const double*)Vsub, ldv, j0, nv, passes, algo, (double*)q,
+                              (const double*)pre_vec, pre_coef_dev, h_dev, nrm_dev, (double*)vnext, ctx->d_partials};
+        return orth_launch<double>(ctx, a, ctx->orth_blocks_f64);
+    }
+    if (dtype == KRY_F32) {
+        OrthArgs<float> a = {n, (const float*)Vdot, (const float*)Vsub, ldv, j0, nv, passes, algo, (float*)q,
+                             (const float*)pre_vec, pre_coef_dev, h_dev, nrm_dev, (float*)vnext, ctx->d_partials};
+        return orth_launch<float>(ctx, a, ctx->orth_blocks_f32);
+    }
+    kry_set_error("kry_orth_fused: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_project(kry_ctx* ctx, int dtype, long long n, const void* W, long long ldw, const void* V, long long ldv,
+                int d, void* a, const double* Q_dev, const double* R_dev, int iterations, double* c_first_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && a && d >= 0 && iterations >= 1, "bad arguments");
+    if (d == 0) return KRY_OK;
+    KRY_REQUIRE(d <= KRY_MAX_SLOTS, "too many deflation vectors for one call");
+    KRY_REQUIRE(W && V, "NULL basis");
+    KRY_REQUIRE((Q_dev == nullptr) == (R_dev == nullptr), "Q and R must be given together");
+    if (dtype == KRY_F64) {
+        ProjArgs<double> p = {n, (const double*)W, ldw, (const double*)V, ldv, d, iterations, (double*)a,
+                              Q_dev, R_dev, c_first_dev, ctx->d_partials};
+        return proj_launch<double>(ctx, p, ctx->proj_blocks_f64);
+    }
+    if (dtype == KRY_F32) {
+        ProjArgs<float> p = {n, (const float*)W, ldw, (const float*)V, ldv, d, iterations, (float*)a,
+                             Q_dev, R_dev, c_first_dev, ctx->d_partials};
+        return proj_launch<float>(ctx, p, ctx->proj_blocks_f32);
+    }
+    kry_set_error("kry_project: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

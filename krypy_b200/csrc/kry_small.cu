@@ -1,0 +1,157 @@
+// Latency-bound device recurrences: GMRES Givens/Hessenberg update, triangular
+// solve, MINRES sliding QR.  One small CTA each; inputs are staged into shared
+// memory in parallel, one thread runs the (inherently serial) recurrence, the
+// results go to device state and to the pinned host mailbox in parallel.
+#include "kry_common.cuh"
+
+#define KRY_ENTER(ctx)                                                         \
+    KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+// BLAS drotg (reference BLAS 3.10 / OpenBLAS >= 0.3.20 algorithm), returns c, s
+// with r = sigma*hypot(a,b), sigma = sign of the larger-magnitude input.
+// krypy/utils.py:421-424 takes (c, s) from scipy.linalg.blas.drotg.
+__device__ __forceinline__ void kry_drotg(double a, double b, double& c, double& s) {
+    const double safmin = 2.2250738585072014e-308, safmax = 4.4942328371557898e+307;
+    const double anorm = fabs(a), bnorm = fabs(b);
+    if (bnorm == 0.0) {
+        c = 1.0;
+        s = 0.0;
+    } else if (anorm == 0.0) {
+        c = 0.0;
+        s = 1.0;
+    } else {
+        const double scl = fmin(safmax, fmax(safmin, fmax(anorm, bnorm)));
+        const double sigma = (anorm > bnorm) ? copysign(1.0, a) : copysign(1.0, b);
+        const double as = a / scl, bs = b / scl;
+        const double r = sigma * (scl * sqrt(__dadd_rn(__dmul_rn(as, as), __dmul_rn(bs, bs))));
+        c = a / r;
+        s = b / r;
+    }
+}
+
+// G = [[c, s], [-s, c]] applied to (x0, x1): numpy.dot(G, x), utils.py:434-436
+__device__ __forceinline__ void kry_rot(double c, double s, double& x0, double& x1) {
+    const double t0 = __dadd_rn(__dmul_rn(c, x0), __dmul_rn(s, x1));
+    const double t1 = __dadd_rn(__dmul_rn(-s, x0), __dmul_rn(c, x1));
+    x0 = t0;
+    x1 = t1;
+}
+
+__global__ void __launch_bounds__(128) givens_kernel(int k, double* hcol, double* rcol, double* cs, double* y,
+                                                     double* mailbox) {
+    extern __shared__ double sh[];
+    double* r = sh;              // k+2
+    double* rot = sh + (k + 2);  // 2k
+    for (int i = threadIdx.x; i < k + 2; i += blockDim.x) r[i] = hcol[i];
+    for (int i = threadIdx.x; i < 2 * k; i += blockDim.x) rot[i] = cs[i];
+    __syncthreads();
+    // raw Hessenberg column goes to the host (invariant-subspace test, H attribute)
+    for (int i = threadIdx.x; i < k + 2; i += blockDim.x) {
+        mailbox[1 + i] = r[i];
+        hcol[i] = 0.0;   // h accumulates with += (reorthogonalisation): leave it zeroed
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < k; ++i) kry_rot(rot[2 * i], rot[2 * i + 1], r[i], r[i + 1]);   // linsys.py:985-986
+        double c, s;
+        kry_drotg(r[k], r[k + 1], c, s);                                                  // linsys.py:989
+        cs[2 * k] = c;
+        cs[2 * k + 1] = s;
+        kry_rot(c, s, r[k], r[k + 1]);                                                    // linsys.py:990
+        double y0 = y[k], y1 = y[k + 1];
+        kry_rot(c, s, y0, y1);                                                            // linsys.py:991
+        y[k] = y0;
+        y[k + 1] = y1;
+        mailbox[0] = fabs(y1);                                                            // linsys.py:993
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < k + 2; i += blockDim.x) {
+        rcol[i] = r[i];
+        mailbox[k + 3 + i] = r[i];
+    }
+}
+
+__global__ void __launch_bounds__(128) tri_solve_kernel(int k, const double* R, long long ldr, const double* y,
+                                                        double* out) {
+    extern __shared__ double sh[];
+    double* x = sh;  // k
+    for (int i = threadIdx.x; i < k; i += blockDim.x) x[i] = y[i];
+    __syncthreads();
+    // column-oriented back substitution (LAPACK trtrs order); the column update is parallel
+    for (int j = k - 1; j >= 0; --j) {
+        __shared__ double xj;
+        if (threadIdx.x == 0) {
+            xj = x[j] / R[(long long)j * ldr + j];
+            x[j] = xj;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < j; i += blockDim.x) x[i] = fma(-xj, R[(long long)i * ldr + j], x[i]);
+        __syncthreads();
+    }
+    for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = x[i];
+}
+
+// state: [0]G1c [1]G1s [2]G1valid [3]G2c [4]G2s [5]G2valid [6]y0 [7]unused
+//        [8]R0 [9]R1 [10]R2 [11]ycoef
+__global__ void minres_recur_kernel(int k, double* h3, double* st, int shift, double* mailbox) {
+    if (threadIdx.x != 0) return;
+    double R0 = 0.0, R1 = h3[0], R2, R3;                // linsys.py:827-828 (H[k-1,k]; 0 for k == 0)
+    if (k == 0) R1 = 0.0;
+    if (st[2] != 0.0) kry_rot(st[0], st[1], R0, R1);    // :829-830
+    R2 = h3[1];                                         // :833
+    R3 = h3[2];
+    if (st[5] != 0.0) kry_rot(st[3], st[4], R1, R2);    // :834-835
+    st[0] = st[3]; st[1] = st[4]; st[2] = st[5];        // :836
+    double c, s;
+    kry_drotg(R2, R3, c, s);                            // :838
+    st[3] = c; st[4] = s; st[5] = 1.0;
+    R2 = __dadd_rn(__dmul_rn(c, R2), __dmul_rn(s, R3)); // :839  r = c*a + s*b
+    double y0 = st[6], y1 = 0.0;
+    kry_rot(c, s, y0, y1);                              // :841
+    st[8] = R0; st[9] = R1; st[10] = R2; st[11] = y0;   // :844, :846
+    st[6] = y1;                                         // :847
+    mailbox[0] = fabs(y1);                              // :849
+    mailbox[1] = R0; mailbox[2] = R1; mailbox[3] = R2; mailbox[4] = y0;
+    mailbox[5] = h3[0]; mailbox[6] = h3[1]; mailbox[7] = h3[2];
+    if (shift) {
+        h3[0] = h3[2];   // next step's H[k, k+1] = H[k+1, k]   (utils.py:1003)
+        h3[1] = 0.0;     // alpha accumulates with +=
+    }
+}
+
+extern "C" {
+
+int kry_givens_update(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev, double* cs_dev, double* y_dev,
+                      int mailbox_off) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(k >= 0 && hcol_dev && rcol_dev && cs_dev && y_dev, "bad arguments");
+    KRY_REQUIRE(k <= 2000, "k too large for the single-CTA Givens update (use restarts)");
+    KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 2 * k + 5 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
+    size_t smem = sizeof(double) * (size_t)(3 * k + 2);
+    givens_kernel<<<1, 128, smem, ctx->stream>>>(k, hcol_dev, rcol_dev, cs_dev, y_dev, ctx->d_mailbox + mailbox_off);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_tri_solve(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const double* y_dev, double* out_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(k >= 0 && ldr >= k, "bad arguments");
+    if (k == 0) return KRY_OK;
+    KRY_REQUIRE(R_dev && y_dev && out_dev, "NULL argument");
+    KRY_REQUIRE(k <= 6000, "k too large");
+    tri_solve_kernel<<<1, 128, sizeof(double) * (size_t)k, ctx->stream>>>(k, R_dev, ldr, y_dev, out_dev);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_minres_recur(kry_ctx* ctx, int k, double* h3_dev, double* st_dev, int shift, int mailbox_off) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(k >= 0 && h3_dev && st_dev, "bad arguments");
+    KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 8 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
+    minres_recur_kernel<<<1, 32, 0, ctx->stream>>>(k, h3_dev, st_dev, shift, ctx->d_mailbox + mailbox_off);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+}  // extern "C"

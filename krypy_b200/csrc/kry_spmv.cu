@@ -1,0 +1,315 @@
+// CSR SpMV for sm_100a.
+//
+// Short-row matrices (stencils: 5/7 nnz per row) use a persistent kernel in
+// which one elected thread stages each 256-row block's contiguous vals[] and
+// colidx[] ranges into shared memory with 1-D TMA bulk copies
+// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx, SASS UBLKCP)
+// through a STAGES-deep ring, so tens of KB per SM are in flight without
+// holding registers.  Consumers then run thread-per-row out of shared memory:
+// for banded matrices the x gathers of neighbouring threads are contiguous
+// (coalesced ld.global.nc), and each row is summed sequentially left to right
+// with separately rounded multiply and add -- the same order and rounding as
+// scipy's csr_matvec, so y is bit-identical to the reference's SpMV in fp64.
+//
+// Long-row matrices (or unaligned arrays) use a warp-per-row kernel with
+// coalesced direct loads and a shuffle reduction.
+#include "kry_common.cuh"
+
+#define KRY_ENTER(ctx)                                                         \
+    KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+#define SPMV_R 256   // rows per tile == threads per CTA
+
+// ---- mbarrier / bulk-copy PTX ------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    const uint32_t addr = smem_u32(bar);
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+// 1-D bulk async copy global -> shared, completion signalled on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(dst_smem)),
+        "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <typename T, int CPR>
+struct SpmvCfg {
+    static const int CAP = SPMV_R * CPR + 8;                       // entries per stage (multiple of 4)
+    static const int STAGE_BYTES = CAP * (int)(sizeof(T) + sizeof(int));
+    static const int STAGES = (CPR <= 8) ? 4 : 2;
+    static const int SMEM_BYTES = 128 + STAGES * STAGE_BYTES;
+};
+
+// finish a CTA-partial dot: write partial, last CTA reduces in fixed order
+__device__ __forceinline__ void finish_dot(double acc, double* partials, unsigned int* ticket, double* dot_out,
+                                           double* sm, bool* last_flag) {
+    double s = kry_block_sum(acc, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        *last_flag = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (*last_flag) {
+        __threadfence();
+        double v = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v += __ldcg(partials + b);
+        double r = kry_block_sum(v, sm);
+        if (threadIdx.x == 0) {
+            dot_out[0] = r;
+            *ticket = 0u;
+        }
+    }
+}
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void consumer_bar_sync() {   // named barrier 1 over the 256 consumer threads
+    asm volatile("bar.sync 1, %0;" ::"n"(SPMV_R) : "memory");
+}
+
+#define SPMV_THREADS (SPMV_R + 32)   // 8 consumer warps (thread per row) + 1 producer warp
+
+template <typename T, int CPR, bool DOT>
+__global__ void __launch_bounds__(SPMV_THREADS)
+spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowptr,
+                   const int* __restrict__ colidx, const T* __restrict__ vals, const T* __restrict__ x, T* y,
+                   const T* __restrict__ w, double* partials, unsigned int* ticket, double* dot_out) {
+    typedef SpmvCfg<T, CPR> Cfg;
+    const int STAGES = Cfg::STAGES;
+    const int CAP = Cfg::CAP;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double red_sm[32];
+    __shared__ bool last_flag;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem);        // [STAGES] producer -> consumers (tx bytes)
+    uint64_t* empty = full + STAGES;                            // [STAGES] consumers -> producer
+    unsigned char* stage_base = smem + 128;
+
+    const int tid = threadIdx.x;
+    const long long ntiles = (nrows + SPMV_R - 1) / SPMV_R;
+    const long long G = gridDim.x;
+    const long long nmine = ((long long)blockIdx.x < ntiles) ? (ntiles - blockIdx.x + G - 1) / G : 0;
+    const int nnz_al = (int)(nnz & ~3LL);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], SPMV_R / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    double dot_acc = 0.0;
+    if (tid >= SPMV_R) {
+        // ---------------- producer warp: one elected lane drives the TMA ring ----------------
+        if (tid == SPMV_R) {
+            for (long long it = 0; it < nmine; ++it) {
+                const int st = (int)(it % STAGES);
+                if (it >= STAGES) mbar_wait(&empty[st], (uint32_t)(((it / STAGES) - 1) & 1));
+                const long long t = blockIdx.x + it * G;
+                const long long r0 = t * SPMV_R;
+                const long long r1 = (r0 + SPMV_R < nrows) ? r0 + SPMV_R : nrows;
+                const int s = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
+                const int s_al = s & ~3;
+                const int e_al = (e + 3) & ~3;
+                const int e_bulk = e_al < nnz_al ? e_al : nnz_al;
+                const int cnt = e_bulk - s_al;
+                T* sv = reinterpret_cast<T*>(stage_base + (size_t)st * Cfg::STAGE_BYTES);
+                int* sc = reinterpret_cast<int*>(stage_base + (size_t)st * Cfg::STAGE_BYTES + (size_t)CAP * sizeof(T));
+                if (e_al - s_al <= CAP && cnt > 0) {
+                    mbar_expect_tx(&full[st], (uint32_t)cnt * (uint32_t)(sizeof(T) + sizeof(int)));
+                    bulk_g2s(sv, vals + s_al, (uint32_t)cnt * (uint32_t)sizeof(T), &full[st]);
+                    bulk_g2s(sc, colidx + s_al, (uint32_t)cnt * (uint32_t)sizeof(int), &full[st]);
+                } else {
+                    mbar_expect_tx(&full[st], 0u);  // nothing staged: complete the phase at once
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers: thread per row out of shared memory ----------------
+        for (long long it = 0; it < nmine; ++it) {
+            const long long t = blockIdx.x + it * G;
+            const int st = (int)(it % STAGES);
+            const uint32_t parity = (uint32_t)((it / STAGES) & 1);
+            const long long r0 = t * SPMV_R;
+            const long long r1 = (r0 + SPMV_R < nrows) ? r0 + SPMV_R : nrows;
+            const int s = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
+            const int s_al = s & ~3;
+            const int e_al = (e + 3) & ~3;
+            const bool staged = (e_al - s_al) <= CAP;
+            const long long row = r0 + tid;
+            int a = 0, b = 0;
+            if (row < r1) {
+                a = __ldg(rowptr + row);
+                b = __ldg(rowptr + row + 1);
+            }
+            T* sv = reinterpret_cast<T*>(stage_base + (size_t)st * Cfg::STAGE_BYTES);
+            int* sc = reinterpret_cast<int*>(stage_base + (size_t)st * Cfg::STAGE_BYTES + (size_t)CAP * sizeof(T));
+            double sum = 0.0;
+            mbar_wait(&full[st], parity);
+            if (staged) {
+                const int e_bulk = e_al < nnz_al ? e_al : nnz_al;
+                if (e > e_bulk) {
+                    // the last (<4) entries of the matrix are not 16-byte coverable: plain copy
+                    for (int jj = e_bulk + tid; jj < e; jj += SPMV_R) {
+                        sv[jj - s_al] = vals[jj];
+                        sc[jj - s_al] = colidx[jj];
+                    }
+                    consumer_bar_sync();
+                }
+                int jj = a - s_al;
+                const int end = b - s_al;
+                for (; jj + 4 <= end; jj += 4) {
+                    const int c0 = sc[jj], c1 = sc[jj + 1], c2 = sc[jj + 2], c3 = sc[jj + 3];
+                    const double x0 = (double)__ldg(x + c0), x1 = (double)__ldg(x + c1);
+                    const double x2 = (double)__ldg(x + c2), x3 = (double)__ldg(x + c3);
+                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj], x0));
+                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 1], x1));
+                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 2], x2));
+                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 3], x3));
+                }
+                for (; jj < end; ++jj)
+                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj], (double)__ldg(x + sc[jj])));
+            } else {
+                for (int jj = a; jj < b; ++jj)
+                    sum = __dadd_rn(sum, __dmul_rn((double)__ldg(vals + jj), (double)__ldg(x + __ldg(colidx + jj))));
+            }
+            if (row < r1) {
+                if (y) y[row] = (T)sum;
+                if (DOT) dot_acc = fma((double)__ldg(w + row), (double)(T)sum, dot_acc);
+            }
+            // this warp is done with slot st: let the producer refill it
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+        }
+    }
+    if (DOT) finish_dot(dot_acc, partials, ticket, dot_out, red_sm, &last_flag);
+}
+
+template <typename T, bool DOT>
+__global__ void __launch_bounds__(KRY_THREADS)
+spmv_warp_kernel(long long nrows, const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                 const T* __restrict__ vals, const T* __restrict__ x, T* y, const T* __restrict__ w,
+                 double* partials, unsigned int* ticket, double* dot_out) {
+    __shared__ double red_sm[32];
+    __shared__ bool last_flag;
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
+    double dot_acc = 0.0;
+    for (long long r = warp; r < nrows; r += nwarps) {
+        const int a = __ldg(rowptr + r), b = __ldg(rowptr + r + 1);
+        double acc = 0.0;
+        for (int jj = a + lane; jj < b; jj += 32)
+            acc = fma((double)__ldg(vals + jj), (double)__ldg(x + __ldg(colidx + jj)), acc);
+        acc = kry_warp_sum(acc);
+        if (lane == 0) {
+            if (y) y[r] = (T)acc;
+            if (DOT) dot_acc = fma((double)__ldg(w + r), (double)(T)acc, dot_acc);
+        }
+    }
+    if (DOT) finish_dot(dot_acc, partials, ticket, dot_out, red_sm, &last_flag);
+}
+
+template <typename T, int CPR, bool DOT>
+static int launch_staged(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
+                         const T* vals, const T* x, T* y, const T* w, double* dot_out) {
+    typedef SpmvCfg<T, CPR> Cfg;
+    auto kern = spmv_staged_kernel<T, CPR, DOT>;
+    static thread_local int occ[16] = {0};
+    int& o = occ[ctx->device & 15];
+    if (o == 0) {
+        KRY_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        int nb = 0;
+        KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, SPMV_THREADS, Cfg::SMEM_BYTES));
+        KRY_REQUIRE(nb >= 1, "staged SpMV kernel does not fit on an SM");
+        o = nb;
+    }
+    long long ntiles = (nrows + SPMV_R - 1) / SPMV_R;
+    long long cap = (long long)ctx->sm_count * o;
+    if (cap > KRY_MAX_PARTIAL_BLOCKS) cap = KRY_MAX_PARTIAL_BLOCKS;
+    int g = (int)(ntiles < cap ? ntiles : cap);
+    if (g < 1) g = 1;
+    kern<<<g, SPMV_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(nrows, nnz, rowptr, colidx, vals, x, y, w,
+                                                      ctx->d_partials, ctx->d_ticket + 1, dot_out);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+template <typename T, bool DOT>
+static int spmv_dispatch(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
+                         const T* vals, const T* x, T* y, const T* w, double* dot_out) {
+    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    const bool al = kry_aligned16(vals) && kry_aligned16(colidx);
+    if (al && avg <= 7.5) return launch_staged<T, 8, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    if (al && avg <= 15.0) return launch_staged<T, 16, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    if (al && avg <= 30.0) return launch_staged<T, 32, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    long long need = (nrows * 32 + KRY_THREADS - 1) / KRY_THREADS;
+    long long cap = (long long)ctx->sm_count * 8;
+    int g = (int)(need < cap ? need : cap);
+    if (g < 1) g = 1;
+    spmv_warp_kernel<T, DOT><<<g, KRY_THREADS, 0, ctx->stream>>>(nrows, rowptr, colidx, vals, x, y, w,
+                                                                 ctx->d_partials, ctx->d_ticket + 1, dot_out);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+extern "C" int kry_spmv_csr(kry_ctx* ctx, int dtype, long long nrows, long long ncols, long long nnz,
+                            const int* rowptr, const int* colidx, const void* vals, const void* x, void* y,
+                            const void* w_dev, double* dot_out_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(nrows >= 0 && ncols >= 0 && nnz >= 0, "negative size");
+    KRY_REQUIRE(nnz < 2147483647LL, "nnz must fit int32 row pointers");
+    KRY_REQUIRE(rowptr && x, "NULL argument");
+    KRY_REQUIRE(nnz == 0 || (colidx && vals), "NULL matrix arrays");
+    KRY_REQUIRE(y || w_dev, "neither y nor a dot epilogue requested");
+    KRY_REQUIRE(!w_dev || dot_out_dev, "w given without dot_out");
+    if (nrows == 0) return KRY_OK;
+    if (dtype == KRY_F64) {
+        if (w_dev)
+            return spmv_dispatch<double, true>(ctx, nrows, nnz, rowptr, colidx, (const double*)vals,
+                                               (const double*)x, (double*)y, (const double*)w_dev, dot_out_dev);
+        return spmv_dispatch<double, false>(ctx, nrows, nnz, rowptr, colidx, (const double*)vals, (const double*)x,
+                                            (double*)y, nullptr, nullptr);
+    }
+    if (dtype == KRY_F32) {
+        if (w_dev)
+            return spmv_dispatch<float, true>(ctx, nrows, nnz, rowptr, colidx, (const float*)vals, (const float*)x,
+                                              (float*)y, (const float*)w_dev, dot_out_dev);
+        return spmv_dispatch<float, false>(ctx, nrows, nnz, rowptr, colidx, (const float*)vals, (const float*)x,
+                                           (float*)y, nullptr, nullptr);
+    }
+    kry_set_error("kry_spmv_csr: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}

@@ -1,0 +1,189 @@
+// Fused N-sized solver updates: CG (x, r, z, rho in one sweep) and MINRES
+// (z, W shift, y in one sweep).  HBM-bound streaming kernels.
+#include "kry_common.cuh"
+
+#define KRY_ENTER(ctx)                                                         \
+    KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+template <typename T> __device__ __forceinline__ double round_as(double v) { return (double)(T)v; }
+
+// krypy/linsys.py:634 (alpha), :655 (yk += alpha p), :658 (Mlrk -= alpha Ap),
+// :661 (MMlrk = M Mlrk, diagonal M), :664-665 (rho = <Mlrk, MMlrk>)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2)
+cg_update_kernel(long long n, const T* __restrict__ Ap, const T* __restrict__ p, T* yk, T* r, T* z,
+                 const T* __restrict__ dinv, double rho, const double* pAp, double* partials,
+                 unsigned int* ticket, double* mailbox) {
+    __shared__ double sm[32];
+    __shared__ bool last;
+    const double pap = pAp[0];
+    const double alpha = rho / pap;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double acc = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        double pv[VEC], av[VEC], yv[VEC], rv[VEC], zv[VEC];
+        VecIO<T, VEC>::load(p, i, pv);
+        VecIO<T, VEC>::load(Ap, i, av);
+        VecIO<T, VEC>::loadrw(yk, i, yv);
+        VecIO<T, VEC>::loadrw(r, i, rv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            yv[u] = fma(alpha, pv[u], yv[u]);
+            rv[u] = round_as<T>(fma(-alpha, av[u], rv[u]));
+        }
+        VecIO<T, VEC>::store(yk, i, yv);
+        VecIO<T, VEC>::store(r, i, rv);
+        if (dinv) {
+            double dv[VEC];
+            VecIO<T, VEC>::load(dinv, i, dv);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) zv[u] = round_as<T>(dv[u] * rv[u]);
+            VecIO<T, VEC>::store(z, i, zv);
+        } else {
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) zv[u] = rv[u];
+        }
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) acc = fma(rv[u], zv[u], acc);
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
+            yk[i] = (T)fma(alpha, (double)p[i], (double)yk[i]);
+            double rv = round_as<T>(fma(-alpha, (double)Ap[i], (double)r[i]));
+            r[i] = (T)rv;
+            double zv = rv;
+            if (dinv) {
+                zv = round_as<T>((double)dinv[i] * rv);
+                z[i] = (T)zv;
+            }
+            acc = fma(rv, zv, acc);
+        }
+    }
+    double s = kry_block_sum(acc, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double v = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v += __ldcg(partials + b);
+        double rr = kry_block_sum(v, sm);
+        if (threadIdx.x == 0) {
+            mailbox[0] = rr;
+            mailbox[1] = alpha;
+            mailbox[2] = pap;
+            *ticket = 0u;
+        }
+    }
+}
+
+// krypy/linsys.py:844-846
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2)
+minres_update_kernel(long long n, const T* __restrict__ v, T* w0, const T* __restrict__ w1, T* yk,
+                     const double* st) {
+    const double R0 = st[8], R1 = st[9], R2 = st[10], yc = st[11];
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        double vv[VEC], a0[VEC], a1[VEC], yv[VEC], zv[VEC];
+        VecIO<T, VEC>::load(v, i, vv);
+        VecIO<T, VEC>::loadrw(w0, i, a0);
+        VecIO<T, VEC>::load(w1, i, a1);
+        VecIO<T, VEC>::loadrw(yk, i, yv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            zv[u] = round_as<T>(fma(-R1, a1[u], fma(-R0, a0[u], vv[u])) / R2);
+            yv[u] = fma(yc, zv[u], yv[u]);
+        }
+        VecIO<T, VEC>::store(w0, i, zv);
+        VecIO<T, VEC>::store(yk, i, yv);
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
+            double zv = round_as<T>(fma(-R1, (double)w1[i], fma(-R0, (double)w0[i], (double)v[i])) / R2);
+            w0[i] = (T)zv;
+            yk[i] = (T)fma(yc, zv, (double)yk[i]);
+        }
+    }
+}
+
+static inline int upd_grid(const kry_ctx* ctx, long long nvec) {
+    long long need = (nvec + KRY_THREADS - 1) / KRY_THREADS;
+    long long cap = (long long)ctx->sm_count * 4;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+extern "C" {
+
+int kry_cg_update(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk, void* r, void* z,
+                  const void* dinv, double rho, const double* pAp_dev, int mailbox_off) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && Ap && p && yk && r && pAp_dev, "bad arguments");
+    KRY_REQUIRE(!dinv || z, "dinv given without z");
+    KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 3 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
+    bool al = kry_aligned16(Ap) && kry_aligned16(p) && kry_aligned16(yk) && kry_aligned16(r) &&
+              (!z || kry_aligned16(z)) && (!dinv || kry_aligned16(dinv));
+    double* mb = ctx->d_mailbox + mailbox_off;
+    if (dtype == KRY_F64) {
+        if (al)
+            cg_update_kernel<double, 2><<<upd_grid(ctx, n / 2), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const double*)Ap, (const double*)p, (double*)yk, (double*)r, (double*)z, (const double*)dinv, rho,
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+        else
+            cg_update_kernel<double, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const double*)Ap, (const double*)p, (double*)yk, (double*)r, (double*)z, (const double*)dinv, rho,
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+    } else if (dtype == KRY_F32) {
+        if (al)
+            cg_update_kernel<float, 4><<<upd_grid(ctx, n / 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const float*)Ap, (const float*)p, (float*)yk, (float*)r, (float*)z, (const float*)dinv, rho,
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+        else
+            cg_update_kernel<float, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const float*)Ap, (const float*)p, (float*)yk, (float*)r, (float*)z, (const float*)dinv, rho,
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+    } else {
+        kry_set_error("kry_cg_update: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_minres_update(kry_ctx* ctx, int dtype, long long n, const void* v, void* w0, const void* w1, void* yk,
+                      const double* st_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && v && w0 && w1 && yk && st_dev, "bad arguments");
+    bool al = kry_aligned16(v) && kry_aligned16(w0) && kry_aligned16(w1) && kry_aligned16(yk);
+    if (dtype == KRY_F64) {
+        if (al)
+            minres_update_kernel<double, 2><<<upd_grid(ctx, n / 2), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const double*)v, (double*)w0, (const double*)w1, (double*)yk, st_dev);
+        else
+            minres_update_kernel<double, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const double*)v, (double*)w0, (const double*)w1, (double*)yk, st_dev);
+    } else if (dtype == KRY_F32) {
+        if (al)
+            minres_update_kernel<float, 4><<<upd_grid(ctx, n / 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const float*)v, (float*)w0, (const float*)w1, (float*)yk, st_dev);
+        else
+            minres_update_kernel<float, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const float*)v, (float*)w0, (const float*)w1, (float*)yk, st_dev);
+    } else {
+        kry_set_error("kry_minres_update: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,739 @@
+"""Host-side mirror of ``krypy.linsys``: the
+same classes, constructor arguments, attributes and exceptions as the reference;
+the iteration itself runs on the B200 through libkrypy_b200.so.
+
+Convergence control stays on the host (one pinned-mailbox read per iteration);
+operator applies, Gram-Schmidt, Givens/Hessenberg updates, solution updates and
+residual norms are device kernels.
+"""
+import warnings
+
+import numpy
+
+from . import _device, utils
+from .utils import _ctx, _is_dev
+
+__all__ = ["LinearSystem", "Cg", "Minres", "Gmres", "RestartedGmres", "TimedLinearSystem",
+           "ConvertedTimedLinearSystem"]
+
+
+def _host_vec(x):
+    """numpy view (N,1) of a public vector argument, or None."""
+    if x is None:
+        return None
+    if _is_dev(x):
+        x = x.detach().cpu().numpy()
+    x = numpy.asarray(x)
+    return x.reshape(x.shape[0], -1)
+
+
+class _LazyVec(object):
+    """Descriptor: numpy (N,1) view of a device block attribute, materialised on access."""
+
+    def __init__(self, name):
+        self.dev = "_" + name + "_dev"
+        self.cache = "_" + name + "_np"
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        c = obj.__dict__.get(self.cache)
+        if c is not None:
+            return c
+        d = obj.__dict__.get(self.dev)
+        if d is None:
+            return None
+        c = _ctx().to_numpy(d).astype(obj.dtype, copy=False)
+        obj.__dict__[self.cache] = c
+        return c
+
+    def __set__(self, obj, value):
+        if value is None:
+            obj.__dict__[self.dev] = None
+            obj.__dict__[self.cache] = None
+        elif _is_dev(value):
+            obj.__dict__[self.dev] = value
+            obj.__dict__[self.cache] = None
+        else:
+            value = numpy.asarray(value)
+            obj.__dict__[self.cache] = value
+            obj.__dict__[self.dev] = None
+
+
+class LinearSystem(object):
+    """krypy/linsys.py:11-201.  ``dtype`` (new, optional): storage/compute dtype
+    of the device path; the default follows the reference's promotion rule
+    (>= float64); ``dtype=numpy.float32`` opts into fp32 storage."""
+
+    def __init__(self, A, b, M=None, Minv=None, Ml=None, Mr=None, ip_B=None, normal=None,
+                 self_adjoint=False, positive_definite=False, exact_solution=None, dtype=None):
+        self.N = N = len(b)
+        shape = (N, N)
+        self.A = utils.get_linearoperator(shape, A)
+        self.M = utils.get_linearoperator(shape, M)
+        self.Minv = utils.get_linearoperator(shape, Minv)
+        self.Ml = utils.get_linearoperator(shape, Ml)
+        self.Mr = utils.get_linearoperator(shape, Mr)
+        self.MlAMr = self.Ml * self.A * self.Mr
+        try:
+            self.ip_B = utils.get_linearoperator(shape, ip_B)
+        except TypeError:
+            self.ip_B = ip_B
+
+        b_dev_in = _is_dev(b)
+        if b_dev_in:
+            self.flat_vecs = b.dim() == 1
+            b_np = None
+        else:
+            self.flat_vecs, (b_np, exact_solution) = utils.shape_vecs(numpy.asarray(b), exact_solution)
+        if _is_dev(exact_solution):
+            exact_solution = _host_vec(exact_solution)
+        self.exact_solution = exact_solution
+
+        self.self_adjoint = self_adjoint
+        if self_adjoint:
+            if normal is not None and not normal:
+                warnings.warn("Setting normal=True because self_adjoint=True is provided.")
+            normal = True
+        if normal is None:
+            normal = False
+        self.normal = normal
+        self.positive_definite = positive_definite
+        if self_adjoint and not normal:
+            raise utils.ArgumentError("self-adjointness implies normality")
+
+        # common dtype (linsys.py:115-117); the identities contribute float64
+        bdt = _device.torch_to_np_dtype(b.dtype) if b_dev_in else b_np.dtype
+        self.dtype = utils._common_type(
+            [utils.find_common_dtype(self.A, self.M, self.Ml, self.Mr, self.ip_B), bdt])
+        if dtype is not None:
+            self.dtype = numpy.dtype(dtype)
+        self._td = utils._compute_dtype(self.dtype)
+
+        ctx = _ctx()
+        self._b_dev = ctx.to_block(b if b_dev_in else b_np, self._td)
+        self._b_np = b_np
+        self._exact_dev = None if exact_solution is None else ctx.to_block(exact_solution, self._td)
+        # ||M Ml b||_{M^-1}  (linsys.py:120-122)
+        self._Mlb_dev = self.Ml._apply_dev(self._b_dev)
+        self._MMlb_dev = self.M._apply_dev(self._Mlb_dev)
+        self.MMlb_norm = _norm_dev(self._Mlb_dev, self._MMlb_dev, self.ip_B)
+
+    b = _LazyVec("b")
+    Mlb = _LazyVec("Mlb")
+    MMlb = _LazyVec("MMlb")
+
+    # -- device residual -------------------------------------------------------
+    def _get_residual_dev(self, zd, compute_norm=False):
+        """(M Ml (b - A z), Ml (b - A z)[, norm]) on device blocks (linsys.py:130-161)."""
+        if zd is None:
+            if compute_norm:
+                return self._MMlb_dev, self._Mlb_dev, self.MMlb_norm
+            return self._MMlb_dev, self._Mlb_dev
+        ctx = _ctx()
+        Az = self.A._apply_dev(zd)
+        r = ctx.empty(zd.shape, zd.dtype)
+        ctx.axpby(1.0, self._b_dev[0], -1.0, Az[0], r[0])           # b - A z
+        Mlr = self.Ml._apply_dev(r)
+        MMlr = self.M._apply_dev(Mlr)
+        if compute_norm:
+            return MMlr, Mlr, _norm_dev(Mlr, MMlr, self.ip_B)
+        return MMlr, Mlr
+
+    def get_residual(self, z, compute_norm=False):
+        """krypy/linsys.py:130-161 for a numpy ``(N,1)`` z."""
+        if z is None:
+            if compute_norm:
+                return self.MMlb, self.Mlb, self.MMlb_norm
+            return self.MMlb, self.Mlb
+        ctx = _ctx()
+        zd = z if _is_dev(z) else ctx.to_block(numpy.asarray(z), self._td)
+        res = self._get_residual_dev(zd, compute_norm)
+        out = (ctx.to_numpy(res[0]), ctx.to_numpy(res[1]))
+        return out + ((res[2],) if compute_norm else ())
+
+    def get_ip_Minv_B(self):
+        """krypy/linsys.py:163-176."""
+        if not isinstance(self.M, utils.IdentityLinearOperator):
+            if isinstance(self.Minv, utils.IdentityLinearOperator):
+                raise utils.ArgumentError(
+                    "Minv has to be provided for the evaluation of the inner "
+                    "product that is implicitly defined by M.")
+            if isinstance(self.ip_B, utils.LinearOperator):
+                return self.Minv * self.ip_B
+            else:
+                return lambda x, y: self.ip_B(x, self.Minv * y)
+        return self.ip_B
+
+    def __repr__(self):
+        ret = "LinearSystem {\n"
+
+        def add(k):
+            op = getattr(self, k)
+            if op is not None and not isinstance(op, utils.IdentityLinearOperator):
+                return "  " + k + ": " + op.__repr__() + "\n"
+            return ""
+
+        for k in ["A", "b", "M", "Minv", "Ml", "Mr", "ip_B", "normal", "self_adjoint",
+                  "positive_definite", "exact_solution"]:
+            ret += add(k)
+        return ret + "}"
+
+
+def _norm_dev(xd, yd, ip_B):
+    """sqrt(<x, y>_B) of single-vector device blocks; one host synchronisation."""
+    ctx = _ctx()
+    tmp = ctx.scalars(1)
+    utils._ip_coef(xd, xd if yd is None else yd, ip_B, tmp, post=1)
+    return numpy.float64(tmp[0].item())
+
+
+class TimedLinearSystem(LinearSystem):
+    """krypy/linsys.py:204-252."""
+
+    def __init__(self, A, b, M=None, Minv=None, Ml=None, Mr=None, ip_B=None, normal=None,
+                 self_adjoint=False, positive_definite=False, exact_solution=None, dtype=None):
+        self.timings = utils.Timings()
+        N = len(b)
+        shape = (N, N)
+        try:
+            _ip_B = utils.get_linearoperator(shape, ip_B, timer=self.timings["ip_B"])
+        except TypeError:
+            def _ip_B(X, Y):
+                (_, m) = X.shape
+                (_, n) = Y.shape
+                if m == 0 or n == 0:
+                    return ip_B(X, Y)
+                with self.timings["ip_B"]:
+                    ret = ip_B(X, Y)
+                self.timings["ip_B"][-1] /= m * n
+                return ret
+        super(TimedLinearSystem, self).__init__(
+            A=utils.get_linearoperator(shape, A, self.timings["A"]), b=b,
+            M=utils.get_linearoperator(shape, M, self.timings["M"]),
+            Minv=utils.get_linearoperator(shape, Minv, self.timings["Minv"]),
+            Ml=utils.get_linearoperator(shape, Ml, self.timings["Ml"]),
+            Mr=utils.get_linearoperator(shape, Mr, self.timings["Mr"]),
+            ip_B=_ip_B, normal=normal, self_adjoint=self_adjoint,
+            positive_definite=positive_definite, exact_solution=exact_solution, dtype=dtype)
+
+
+class ConvertedTimedLinearSystem(TimedLinearSystem):
+    """krypy/linsys.py:255-274."""
+
+    def __init__(self, linear_system):
+        kwargs = {k: getattr(linear_system, k) for k in
+                  ["A", "b", "M", "Minv", "Ml", "Mr", "ip_B", "normal", "self_adjoint",
+                   "positive_definite", "exact_solution"]}
+        super(ConvertedTimedLinearSystem, self).__init__(**kwargs)
+
+
+class _KrylovSolver(object):
+    """krypy/linsys.py:277-517."""
+
+    x0 = _LazyVec("x0")
+    xk = _LazyVec("xk")
+    MMlr0 = _LazyVec("MMlr0")
+    Mlr0 = _LazyVec("Mlr0")
+
+    def __init__(self, linear_system, x0=None, tol=1e-5, maxiter=None, explicit_residual=False,
+                 store_arnoldi=False, dtype=None):
+        if not isinstance(linear_system, LinearSystem):
+            raise utils.ArgumentError("linear_system is not an instance of LinearSystem")
+        self.linear_system = ls = linear_system
+        self._ctx = ctx = _ctx()
+        ctx.use_current_stream()
+        N = ls.N
+        self.maxiter = N if maxiter is None else maxiter
+        self.explicit_residual = explicit_residual
+        self.store_arnoldi = store_arnoldi
+        self.tol = tol
+
+        # dtype (linsys.py:370-372); a missing x0 does not promote (zeros in ls.dtype)
+        x0dt = None
+        if x0 is not None:
+            x0dt = _device.torch_to_np_dtype(x0.dtype) if _is_dev(x0) else numpy.asarray(x0).dtype
+        self.dtype = utils._common_type([ls.dtype, x0dt, dtype])
+        self._td = utils._compute_dtype(self.dtype)
+        if self._td != ls._td:
+            raise NotImplementedError(
+                "solver dtype %s differs from the linear system's device dtype %s" % (self.dtype, ls.dtype))
+
+        if x0 is None:
+            self.flat_vecs = True
+            x0d = None
+        else:
+            self.flat_vecs = (x0.dim() == 1) if _is_dev(x0) else (numpy.asarray(x0).ndim == 1)
+            x0d = ctx.to_block(x0, self._td)
+            if x0d.shape[1] != N:
+                raise utils.ArgumentError("x0 has the wrong length")
+        x0d = self._get_initial_guess(x0d)
+
+        # initial residual (linsys.py:359)
+        self.MMlr0, self.Mlr0, self.MMlr0_norm = self._get_initial_residual(x0d)
+        if x0d is None:
+            x0d = ctx.zeros((1, N), self._td)
+        self.x0 = x0d
+        self.xk = None
+        self.MlAMr = ls.MlAMr
+        self.iter = 0
+        self.resnorms = []
+        if ls.MMlb_norm == 0:                                   # linsys.py:385-387
+            self.xk = self.x0 = ctx.zeros((1, N), self._td)
+            self.resnorms.append(0.0)
+        else:
+            self.resnorms.append(self.MMlr0_norm / ls.MMlb_norm)
+        if ls.exact_solution is not None:                       # linsys.py:393-402
+            self.errnorms = []
+            self.errnorms.append(self._errnorm(self._get_xk(None)))
+        self._solve()
+        self._finalize()
+
+    # -- hooks -----------------------------------------------------------------
+    def _get_initial_guess(self, x0):
+        return x0
+
+    def _get_initial_residual(self, x0):
+        return self.linear_system._get_residual_dev(x0, compute_norm=True)
+
+    def _errnorm(self, xkd):
+        ctx = self._ctx
+        ls = self.linear_system
+        e = ctx.empty(xkd.shape, xkd.dtype)
+        ctx.axpby(1.0, ls._exact_dev[0], -1.0, xkd[0], e[0])
+        return _norm_dev(e, None, ls.ip_B)
+
+    def _get_xk(self, yk):
+        """krypy/linsys.py:423-428 on device blocks."""
+        x0d = self.__dict__["_x0_dev"]
+        if yk is not None:
+            ctx = self._ctx
+            Mry = self.linear_system.Mr._apply_dev(yk)
+            out = ctx.empty(x0d.shape, x0d.dtype)
+            ctx.axpby(1.0, x0d[0], 1.0, Mry[0], out[0])
+            return out
+        return x0d
+
+    def _finalize_iteration(self, yk, resnorm):
+        """krypy/linsys.py:430-493."""
+        ls = self.linear_system
+        self.xk = None
+        if ls.exact_solution is not None:
+            self.xk = self._get_xk(yk)
+            self.errnorms.append(self._errnorm(self.__dict__["_xk_dev"]))
+        rkn = None
+        if (self.explicit_residual or resnorm / ls.MMlb_norm <= self.tol
+                or self.iter + 1 == self.maxiter):
+            if self.__dict__.get("_xk_dev") is None:
+                self.xk = self._get_xk(yk)
+            _, _, rkn = ls._get_residual_dev(self.__dict__["_xk_dev"], compute_norm=True)
+            self.resnorms.append(rkn / ls.MMlb_norm)
+            if self.resnorms[-1] > self.tol:
+                if self.iter + 1 == self.maxiter:
+                    self._finalize()
+                    raise utils.ConvergenceError(
+                        ("No convergence in last iteration "
+                         "(maxiter: %s, residual: %s)." % (self.maxiter, self.resnorms[-1])), self)
+                elif not self.explicit_residual and resnorm / ls.MMlb_norm <= self.tol:
+                    warnings.warn(
+                        "updated residual is below tolerance, explicit residual is NOT! "
+                        "(upd=%s <= tol=%s < exp=%s)" % (resnorm, self.tol, self.resnorms[-1]))
+        else:
+            self.resnorms.append(resnorm / ls.MMlb_norm)
+        return rkn
+
+    def _finalize(self):
+        pass
+
+    @staticmethod
+    def operations(nsteps):
+        raise NotImplementedError("operations() has to be overridden by the derived solver class.")
+
+    def _solve(self):
+        raise NotImplementedError("_solve has to be overridden by the derived solver class.")
+
+    def _repr(self, name, extra=()):
+        s = "krypy %s object\n" % name
+        s += "    MMlr0 = [{}, ..., {}]\n".format(self.MMlr0[0], self.MMlr0[-1])
+        s += "    MMlr0_norm = {}\n".format(self.MMlr0_norm)
+        s += "    MlAMr: {} x {} matrix\n".format(*self.MlAMr.shape)
+        s += "    Mlr0: [{}, ..., {}]\n".format(self.Mlr0[0], self.Mlr0[-1])
+        for line in extra:
+            s += line
+        s += "    flat_vecs: {}\n".format(self.flat_vecs)
+        s += "    store_arnoldi: {}\n".format(self.store_arnoldi)
+        if hasattr(self, "ortho"):
+            s += "    ortho: {}\n".format(self.ortho)
+        s += "    tol: {}\n".format(self.tol)
+        s += "    maxiter: {}\n".format(self.maxiter)
+        s += "    iter: {}\n".format(self.iter)
+        s += "    explicit residual: {}\n".format(self.explicit_residual)
+        s += "    resnorms: [{}, ..., {}]\n".format(self.resnorms[0], self.resnorms[-1])
+        s += "    x0: [{}, ..., {}]\n".format(self.x0[0], self.x0[-1])
+        s += "    xk: [{}, ..., {}]".format(self.xk[0], self.xk[-1])
+        return s
+
+
+def _diag_of(op):
+    return op if isinstance(op, utils.DiagonalLinearOperator) else None
+
+
+class Cg(_KrylovSolver):
+    """Preconditioned CG (krypy/linsys.py:520-708).
+
+    Device iteration (Euclidean inner product, identity or diagonal ``M``):
+    ``p = z + beta p`` (kry_axpby), ``Ap = A p`` with ``<p,Ap>`` fused into the
+    SpMV epilogue (kry_spmv_csr), and ONE fused sweep for ``x, r, z, rho``
+    (kry_cg_update); the host reads ``rho`` from the pinned mailbox."""
+
+    def __init__(self, linear_system, **kwargs):
+        if not linear_system.self_adjoint or not linear_system.positive_definite:
+            warnings.warn("Cg applied to a non-self-adjoint or non-definite "
+                          "linear system. Consider using Minres or Gmres.")
+        super(Cg, self).__init__(linear_system, **kwargs)
+
+    def __repr__(self):
+        return self._repr("CG")
+
+    Mlrk = _LazyVec("Mlrk")
+    MMlrk = _LazyVec("MMlrk")
+
+    def _apply_op_dot(self, p, Ap, pAp):
+        """Ap = MlAMr p and pAp[0] = <p, Ap>_B (linsys.py:631-634)."""
+        ctx = self._ctx
+        ls = self.linear_system
+        op = self.MlAMr
+        euclid = utils._is_identity_ip(ls.ip_B)
+        if euclid and type(op) is utils.MatrixLinearOperator:
+            A = op._dev(p.dtype)
+            if isinstance(A, _device.CsrDev):
+                ctx.spmv(A, p[0], Ap[0], w=p[0], dot_out=pAp)      # fused <p,Ap> epilogue
+                return
+        op._apply_dev(p, out=Ap)
+        utils._ip_coef(p, Ap, ls.ip_B, pAp)
+
+    def _solve(self):
+        """krypy/linsys.py:593-689."""
+        ctx = self._ctx
+        ls = self.linear_system
+        N = ls.N
+        td = self._td
+        yk = ctx.zeros((1, N), td)
+        self.rhos = rhos = [self.MMlr0_norm ** 2]
+        Mlr0d, MMlr0d = self.__dict__["_Mlr0_dev"], self.__dict__["_MMlr0_dev"]
+        r = Mlr0d.clone()                          # Mlrk
+        M_is_id = isinstance(ls.M, utils.IdentityLinearOperator)
+        Mdiag = _diag_of(ls.M)
+        euclid = utils._is_identity_ip(ls.ip_B)
+        fast = euclid and (M_is_id or Mdiag is not None)
+        z = r if M_is_id else MMlr0d.clone()       # MMlrk (aliases Mlrk when M is the identity)
+        dinv = Mdiag._dev(td) if (fast and Mdiag is not None) else None
+        p = MMlr0d.clone()
+        Ap = ctx.empty((1, N), td)
+        pAp = ctx.scalars(1)
+        tmp = ctx.scalars(1)
+        self.iter = 0
+        store = self.store_arnoldi
+        if store:
+            ld = (N + 31) // 32 * 32
+            self._Vs = ctx.zeros((self.maxiter + 1, ld), td)
+            self._Vd = self._Vs[:, :N]
+            self._Pd = None
+            if self.MMlr0_norm > 0:
+                tmp.fill_(float(self.MMlr0_norm))
+                ctx.scale_dev(tmp, 1, 1.0, MMlr0d[0], self._Vd[0])
+            if not M_is_id:
+                self._Ps = ctx.zeros((self.maxiter + 1, ld), td)
+                self._Pd = self._Ps[:, :N]
+                if self.MMlr0_norm > 0:
+                    ctx.scale_dev(tmp, 1, 1.0, Mlr0d[0], self._Pd[0])
+            self.H = numpy.zeros((self.maxiter + 1, self.maxiter))
+            alpha_old = 0
+        mb = ctx.mailbox
+
+        while self.resnorms[-1] > self.tol and self.iter < self.maxiter:
+            k = self.iter
+            if k > 0:
+                ctx.axpby(1.0, z[0], rhos[-1] / rhos[-2], p[0], p[0])       # linsys.py:627
+                if store:
+                    omega = rhos[-1] / rhos[-2]
+            self._apply_op_dot(p, Ap, pAp)                                 # linsys.py:631-634
+            if fast:
+                ctx.cg_update(Ap[0], p[0], yk[0], r[0], z[0] if dinv is not None else None, dinv,
+                              rhos[-1], pAp, 0)                            # linsys.py:655-665
+                ctx.sync()
+                rho_new, alpha = float(mb[0]), float(mb[1])
+                if not numpy.isfinite(rho_new) or rho_new < 0:
+                    rho_new = abs(rho_new)
+                MMlrk_norm = numpy.sqrt(rho_new)
+            else:
+                ctx.cg_update(Ap[0], p[0], yk[0], r[0], None, None, rhos[-1], pAp, 0)
+                zz = ls.M._apply_dev(r, out=None if M_is_id else z)       # linsys.py:661
+                if M_is_id:
+                    z = r
+                utils._ip_coef(r, zz, ls.ip_B, tmp, post=1)                # linsys.py:664
+                MMlrk_norm = numpy.float64(tmp[0].item())
+                alpha = float(mb[1])
+            rhos.append(MMlrk_norm ** 2)                                   # linsys.py:665
+            if store:
+                if k > 0:
+                    self.H[k - 1, k] = self.H[k, k - 1]
+                    self.H[k, k] = (1.0 + alpha * omega / alpha_old) / alpha
+                else:
+                    self.H[k, k] = 1.0 / alpha
+                tmp.fill_(float(MMlrk_norm))
+                sgn = (-1.0) ** (k + 1)
+                ctx.scale_dev(tmp, 1, sgn, z[0], self._Vd[k + 1])          # linsys.py:669
+                if self._Pd is not None:
+                    ctx.scale_dev(tmp, 1, sgn, r[0], self._Pd[k + 1])      # linsys.py:671
+                self.H[k + 1, k] = numpy.sqrt(rhos[-1] / rhos[-2]) / alpha
+                alpha_old = alpha
+            self._Mlrk_dev, self._MMlrk_dev = r, z
+            rkn = self._finalize_iteration(yk, MMlrk_norm)                 # linsys.py:678
+            if rkn is not None:
+                rhos[-1] = rkn ** 2                                        # linsys.py:681-683
+            self.iter += 1
+
+        self.Mlrk, self.MMlrk = r, z
+        if self.__dict__.get("_xk_dev") is None:
+            self.xk = self._get_xk(yk)
+
+    def _finalize(self):
+        """krypy/linsys.py:691-696."""
+        if self.store_arnoldi:
+            ctx = self._ctx
+            self.V = ctx.to_numpy(self._Vd[: self.iter + 1]).astype(self.dtype, copy=False)
+            if self._Pd is not None:
+                self.P = ctx.to_numpy(self._Pd[: self.iter + 1]).astype(self.dtype, copy=False)
+            self.H = self.H[: self.iter + 1, : self.iter]
+
+    @staticmethod
+    def operations(nsteps):
+        """krypy/linsys.py:698-708."""
+        return {"A": 1 + nsteps, "M": 2 + nsteps, "Ml": 2 + nsteps, "Mr": 1 + nsteps,
+                "ip_B": 2 + 2 * nsteps, "axpy": 2 + 2 * nsteps}
+
+
+class Minres(_KrylovSolver):
+    """Preconditioned MINRES (krypy/linsys.py:711-874).
+
+    Per iteration on the device: operator apply, ONE fused Lanczos kernel
+    (three-term recurrence + dot + update + norm + normalised store,
+    kry_orth_fused), the sliding-QR recurrence (kry_minres_recur) and ONE fused
+    sweep for ``z, W, y`` (kry_minres_update)."""
+
+    def __init__(self, linear_system, ortho="lanczos", **kwargs):
+        if not linear_system.self_adjoint:
+            warnings.warn("Minres applied to a non-self-adjoint linear system. Consider using Gmres.")
+        self.ortho = ortho
+        super(Minres, self).__init__(linear_system, **kwargs)
+
+    def __repr__(self):
+        return self._repr("MINRES")
+
+    def _solve(self):
+        """krypy/linsys.py:791-853."""
+        ctx = self._ctx
+        ls = self.linear_system
+        N = ls.N
+        td = self._td
+        self.lanczos = lz = utils.Arnoldi(
+            self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
+            Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype)
+        W0 = ctx.zeros((1, N), td)
+        W1 = ctx.zeros((1, N), td)
+        yk = ctx.zeros((1, N), td)
+        st = ctx.scalars(16)
+        st[6:7].fill_(float(self.MMlr0_norm))                       # y = [||r0||, 0], linsys.py:809
+        mb = ctx.mailbox
+        is_lanczos = self.ortho == "lanczos"
+        while (self.resnorms[-1] > self.tol and lz.iter < lz.maxiter and not lz.invariant):
+            k = self.iter = lz.iter
+            lz._enqueue(k)                                           # linsys.py:823
+            if is_lanczos:
+                ctx.minres_recur(k, lz._lz, st, 1, 0)                # linsys.py:827-841, 847
+            else:
+                ctx.minres_recur(k, lz._hcol_store[k:], st, 0, 0)    # [H[k-1,k], H[k,k], H[k+1,k]]
+            ctx.minres_update(lz._Vd[k], W0[0], W1[0], yk[0], st)    # linsys.py:844-846
+            W0, W1 = W1, W0
+            if is_lanczos:
+                ctx.sync()
+                resid = float(mb[0])
+                lz._finish(k, mb[6:8].copy())
+            else:
+                hc = lz._hcol[: k + 2].cpu().numpy()                 # synchronises
+                lz._hcol[: k + 2].zero_()
+                resid = float(mb[0])
+                lz._finish(k, hc)
+            self._finalize_iteration(yk, resid)                      # linsys.py:849
+        if self.__dict__.get("_xk_dev") is None:
+            self.xk = self._get_xk(yk)
+
+    def _finalize(self):
+        """krypy/linsys.py:855-862."""
+        if self.store_arnoldi:
+            if not isinstance(self.linear_system.M, utils.IdentityLinearOperator):
+                self.V, self.H, self.P = self.lanczos.get()
+            else:
+                self.V, self.H = self.lanczos.get()
+
+    @staticmethod
+    def operations(nsteps):
+        """krypy/linsys.py:864-874."""
+        return {"A": 1 + nsteps, "M": 2 + nsteps, "Ml": 2 + nsteps, "Mr": 1 + nsteps,
+                "ip_B": 2 + 2 * nsteps, "axpy": 4 + 8 * nsteps}
+
+
+class Gmres(_KrylovSolver):
+    """Preconditioned GMRES (krypy/linsys.py:877-1018).
+
+    Per iteration on the device: operator apply (kry_spmv_csr), ONE fused
+    Gram-Schmidt kernel (kry_orth_fused) and the Givens/Hessenberg update
+    (kry_givens_update), which publishes ``|y[k+1]|`` and the H and R columns
+    through the pinned mailbox -- the single host synchronisation of the step.
+
+    ``ortho``: 'mgs' (default, the reference's exact order), 'dmgs', 'lanczos',
+    and the block variants 'cgs' / 'cgs2' (see utils.Arnoldi).
+    """
+
+    def __init__(self, linear_system, ortho="mgs", **kwargs):
+        self.ortho = ortho
+        super(Gmres, self).__init__(linear_system, **kwargs)
+
+    def __repr__(self):
+        return self._repr("GMRES", ["    R: {} x {} matrix\n".format(*self.R.shape),
+                                    "    V: {} x {} matrix\n".format(*self.V.shape)])
+
+    @property
+    def V(self):
+        v = self.__dict__.get("_V_final")
+        if v is not None:
+            return v
+        return self.arnoldi.V
+
+    @V.setter
+    def V(self, value):
+        self.__dict__["_V_final"] = value
+
+    def _get_xk(self, y):
+        """krypy/linsys.py:941-949: y is a device vector holding y[:k] (or None)."""
+        x0d = self.__dict__["_x0_dev"]
+        if y is None:
+            return x0d
+        ctx = self._ctx
+        k = self.arnoldi.iter
+        if k > 0:
+            t = _device.torch()
+            Rk = t.from_numpy(numpy.ascontiguousarray(self.R[:k, :k], dtype=numpy.float64)).to(ctx.device)
+            yy = ctx.scalars(k)
+            ctx.tri_solve(k, Rk, y, yy)                                    # linsys.py:946
+            out = ctx.empty(x0d.shape, x0d.dtype)
+            Mr = self.linear_system.Mr
+            if isinstance(Mr, utils.IdentityLinearOperator):
+                ctx.block_combine(self.arnoldi._Vd, k, yy, x0d[0], out[0])  # x0 + V[:, :k] yy
+            else:
+                yk = ctx.empty(x0d.shape, x0d.dtype)
+                ctx.block_combine(self.arnoldi._Vd, k, yy, None, yk[0])     # linsys.py:947
+                Mry = Mr._apply_dev(yk)
+                ctx.axpby(1.0, x0d[0], 1.0, Mry[0], out[0])                 # linsys.py:948
+            return out
+        return x0d
+
+    def _solve(self):
+        """krypy/linsys.py:951-997."""
+        ctx = self._ctx
+        ls = self.linear_system
+        self.arnoldi = ar = utils.Arnoldi(
+            self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
+            Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype)
+        m = self.maxiter
+        self.R = numpy.zeros([m + 1, m], dtype=utils._common_type([self.dtype, numpy.float64]))
+        self._y_dev = y = ctx.scalars(m + 2)
+        y[0:1].fill_(float(self.MMlr0_norm))                               # linsys.py:969
+        cs = ctx.scalars(2 * m + 2)
+        rcol = ctx.scalars(m + 2)
+        mb = ctx.mailbox
+        is_lanczos = self.ortho == "lanczos"
+        while (self.resnorms[-1] > self.tol and ar.iter < ar.maxiter and not ar.invariant):
+            k = self.iter = ar.iter
+            ar._enqueue(k)                                                 # linsys.py:978
+            if is_lanczos:
+                # tridiagonal column from the three Lanczos entries
+                ctx.minres_recur(k, ar._lz, ar._lz_st, 1, 16)
+                ctx.sync()
+                hcol = numpy.zeros(k + 2)
+                if k > 0:
+                    hcol[k - 1] = mb[16 + 5]
+                hcol[k], hcol[k + 1] = mb[16 + 6], mb[16 + 7]
+                ar._hcol[: k + 2].copy_(_device.torch().from_numpy(hcol))
+            ctx.givens_update(k, ar._hcol, rcol, cs, y, 0)                 # linsys.py:982-991
+            ctx.sync()
+            resid = float(mb[0])
+            hcol = mb[1:k + 3].copy()
+            self.R[: k + 2, k] = mb[k + 3:2 * k + 5]
+            if is_lanczos:
+                ar._finish(k, hcol[k:k + 2])
+            else:
+                ar._finish(k, hcol)
+            self._finalize_iteration(y, resid)                             # linsys.py:993
+        if self.__dict__.get("_xk_dev") is None:
+            self.xk = self._get_xk(y if ar.iter > 0 else None)
+
+    def _finalize(self):
+        """krypy/linsys.py:999-1006."""
+        if self.store_arnoldi:
+            if not isinstance(self.linear_system.M, utils.IdentityLinearOperator):
+                self.V, self.H, self.P = self.arnoldi.get()
+            else:
+                self.V, self.H = self.arnoldi.get()
+
+    @staticmethod
+    def operations(nsteps):
+        """krypy/linsys.py:1008-1018."""
+        return {"A": 1 + nsteps, "M": 2 + nsteps, "Ml": 2 + nsteps, "Mr": 1 + nsteps,
+                "ip_B": 2 + nsteps + nsteps * (nsteps + 1) / 2,
+                "axpy": 4 + 2 * nsteps + nsteps * (nsteps + 1) / 2}
+
+
+class _RestartedSolver(object):
+    """krypy/linsys.py:1021-1072."""
+
+    def __init__(self, Solver, linear_system, max_restarts=0, **kwargs):
+        self.xk = None
+        kwargs = dict(kwargs)
+        self.resnorms = [numpy.inf]
+        if linear_system.exact_solution is not None:
+            self.errnorms = [numpy.inf]
+        tol = None
+        restart = 0
+        xk_dev = None
+        while restart == 0 or (self.resnorms[-1] > tol and restart <= max_restarts):
+            try:
+                if xk_dev is not None:
+                    kwargs.update({"x0": xk_dev})        # stays in HBM between cycles
+                sol = Solver(linear_system, **kwargs)
+            except utils.ConvergenceError as e:
+                sol = e.solver
+            xk_dev = sol.__dict__["_xk_dev"]
+            if xk_dev is None:
+                xk_dev = _ctx().to_block(sol.xk, sol._td)
+            xk_dev = xk_dev.reshape(-1)                  # flat: keeps flat_vecs semantics neutral
+            self._last = sol
+            tol = sol.tol
+            del self.resnorms[-1]
+            self.resnorms += sol.resnorms
+            if linear_system.exact_solution is not None:
+                del self.errnorms[-1]
+                self.errnorms += sol.errnorms
+            restart += 1
+        self.xk = sol.xk
+        self.tol = tol
+        if self.resnorms[-1] > tol:
+            raise utils.ConvergenceError("No convergence after %d restarts." % max_restarts, self)
+
+
+class RestartedGmres(_RestartedSolver):
+    """Restarted GMRES (krypy/linsys.py:1075-1081)."""
+
+    def __init__(self, *args, **kwargs):
+        super(RestartedGmres, self).__init__(Gmres, *args, **kwargs)

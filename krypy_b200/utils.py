@@ -1,0 +1,1401 @@
+"""Host-side mirror of ``krypy.utils`` for the hot path (SURVEY.md section 8a:
+rows a1-a13, a24): same names, argument meaning and error behaviour as the
+reference, with every N-sized operation executed by the sm_100a kernels of
+libkrypy_b200.so through ctypes.
+
+Public functions take and return ``(N, k)`` numpy arrays exactly like the
+reference; internally blocks live in HBM as ``(k, N)`` torch tensors
+("vector-major") and the solver classes call the ``*_dev`` methods
+directly so nothing N-sized crosses PCIe inside an iteration.
+
+There is no CPU fallback: anything the device path cannot do (complex dtypes,
+``ortho='house'``) raises ``NotImplementedError``.
+"""
+import time
+import warnings
+from collections import defaultdict
+
+import numpy
+
+from . import _device
+from ._lib import KRY_ORTH_CGS, KRY_ORTH_MGS
+
+__all__ = [
+    "ArgumentError", "AssumptionError", "ConvergenceError", "LinearOperatorError",
+    "InnerProductError", "RuntimeError", "Arnoldi", "Givens", "House",
+    "IdentityLinearOperator", "ZeroLinearOperator", "LinearOperator",
+    "MatrixLinearOperator", "DiagonalLinearOperator", "TimedLinearOperator", "Projection",
+    "Timer", "Timings", "arnoldi", "arnoldi_res", "get_linearoperator", "inner", "ip_euclid",
+    "norm", "norm_squared", "orthonormality", "qr", "shape_vec", "shape_vecs",
+    "find_common_dtype",
+]
+
+
+# --------------------------------------------------------------------------
+# exceptions -- krypy/utils.py:62-103
+# --------------------------------------------------------------------------
+class ArgumentError(Exception):
+    """Raised when an argument is invalid (krypy/utils.py:62-67)."""
+
+
+class AssumptionError(Exception):
+    """Raised when an assumption is not satisfied (krypy/utils.py:70-78)."""
+
+
+class ConvergenceError(Exception):
+    """Raised when a method did not converge; ``solver`` holds the populated
+    solver object (krypy/utils.py:81-91)."""
+
+    def __init__(self, msg, solver):
+        super(ConvergenceError, self).__init__(msg)
+        self.solver = solver
+
+
+class LinearOperatorError(Exception):
+    """Raised when a LinearOperator cannot be applied (krypy/utils.py:94-95)."""
+
+
+class InnerProductError(Exception):
+    """Raised when the inner product is indefinite (krypy/utils.py:98-99)."""
+
+
+class RuntimeError(Exception):
+    """Errors that fit nowhere else (krypy/utils.py:102-103; shadows the builtin
+    inside this module exactly like the reference)."""
+
+
+# --------------------------------------------------------------------------
+# small helpers
+# --------------------------------------------------------------------------
+def _ctx():
+    return _device.Context.get()
+
+
+def _is_dev(x):
+    t = _device._torch
+    return t is not None and isinstance(x, t.Tensor)
+
+
+def _isspmatrix(A):
+    import scipy.sparse as sp
+    return sp.issparse(A)   # accepts csr_array as well (superset of the reference)
+
+
+def _common_type(dtypes):
+    dtypes = [numpy.dtype(d) for d in dtypes if d is not None]
+    if not dtypes:
+        return numpy.dtype(None)      # float64, as numpy.find_common_type([], []) did
+    return numpy.result_type(*dtypes)
+
+
+def find_common_dtype(*args):
+    """krypy/utils.py:106-122: common dtype of ndarray / spmatrix / LinearOperator
+    arguments; everything else (notably None) is ignored."""
+    dtypes = []
+    for arg in args:
+        if type(arg) is numpy.ndarray or _isspmatrix(arg) or isinstance(arg, LinearOperator):
+            if hasattr(arg, "dtype"):
+                dtypes.append(arg.dtype)
+            else:
+                warnings.warn("object %s does not have a dtype." % arg.__repr__)
+        elif _is_dev(arg):
+            dtypes.append(_device.torch_to_np_dtype(arg.dtype))
+    return _common_type(dtypes)
+
+
+def _compute_dtype(npdtype):
+    """numpy dtype -> torch dtype of the device path (raises for complex)."""
+    npdtype = numpy.dtype(npdtype)
+    if npdtype.kind == "c":
+        raise NotImplementedError(
+            "krypy_b200: complex systems are not implemented on the device path "
+            "(real float32/float64 only; no CPU fallback)")
+    if npdtype == numpy.float32:
+        return _device.np_to_torch_dtype(numpy.float32)
+    return _device.np_to_torch_dtype(numpy.float64)   # ints, bools, float16 promote to fp64
+
+
+def shape_vec(x):
+    """Take a (n,) ndarray and return it as (n,1) ndarray (krypy/utils.py:125-127)."""
+    return numpy.reshape(x, (x.shape[0], 1))
+
+
+def shape_vecs(*args):
+    """krypy/utils.py:130-143."""
+    ret_args = []
+    flat_vecs = True
+    for arg in args:
+        if type(arg) is numpy.ndarray:
+            if len(arg.shape) == 1:
+                arg = shape_vec(arg)
+            else:
+                flat_vecs = False
+        ret_args.append(arg)
+    return flat_vecs, ret_args
+
+
+def _isintlike(x):
+    try:
+        return bool(int(x) == x) and numpy.ndim(x) == 0
+    except (TypeError, ValueError):
+        return False
+
+
+# --------------------------------------------------------------------------
+# LinearOperator algebra -- krypy/utils.py:1365-1636
+# --------------------------------------------------------------------------
+class LinearOperator(object):
+    """krypy/utils.py:1365-1456.  ``dot``/``dot_adj`` are user callbacks on
+    ``(N, k)`` numpy arrays; subclasses living on the device override
+    ``_apply_dev``.  A generic (host-callback) operator is applied to device
+    blocks by a D2H copy, the user's callback and an H2D copy -- the callback is
+    user code, the round trip is the price of it not being device code."""
+
+    _device_native = False
+
+    def __init__(self, shape, dtype, dot=None, dot_adj=None):
+        if len(shape) != 2 or not _isintlike(shape[0]) or not _isintlike(shape[1]):
+            raise LinearOperatorError("shape must be (m,n) with m and n integer")
+        self.shape = shape
+        self.dtype = numpy.dtype(dtype)  # defaults to float64
+        if dot is None and dot_adj is None:
+            raise LinearOperatorError("dot or dot_adj have to be defined")
+        self._dot = dot
+        self._dot_adj = dot_adj
+
+    # -- public numpy API (reference semantics) --
+    def dot(self, X):
+        X = numpy.asanyarray(X)
+        m, n = self.shape
+        if X.shape[0] != n:
+            raise LinearOperatorError("dimension mismatch")
+        if self._dot is None:
+            raise LinearOperatorError("dot undefined")
+        if X.shape[1] == 0:
+            return numpy.zeros(X.shape)
+        return self._dot(X)
+
+    def dot_adj(self, X):
+        X = numpy.asanyarray(X)
+        m, n = self.shape
+        if X.shape[0] != m:
+            raise LinearOperatorError("dimension mismatch")
+        if self._dot_adj is None:
+            raise LinearOperatorError("dot_adj undefined")
+        if X.shape[1] == 0:
+            return numpy.zeros(X.shape)
+        return self._dot_adj(X)
+
+    # -- device API (internal): Xd is a (k, N) tensor; result written to out --
+    def _apply_dev(self, Xd, out=None, adj=False):
+        ctx = _ctx()
+        fn = self._dot_adj if adj else self._dot
+        if fn is None:
+            raise LinearOperatorError("dot_adj undefined" if adj else "dot undefined")
+        Y = fn(ctx.to_numpy(Xd))
+        Yd = ctx.to_block(numpy.asarray(Y), Xd.dtype)
+        if out is not None:
+            out.copy_(Yd)
+            return out
+        return Yd
+
+    @property
+    def adj(self):
+        return _AdjointLinearOperator(self)
+
+    def __mul__(self, X):
+        try:
+            if isinstance(X, IdentityLinearOperator):
+                return self
+            elif isinstance(self, IdentityLinearOperator):
+                return X
+            elif isinstance(X, LinearOperator):
+                return _ProductLinearOperator(self, X)
+            elif numpy.isscalar(X):
+                return _ScaledLinearOperator(self, X)
+            elif _is_dev(X):
+                return self._apply_dev(X)
+            else:
+                return self.dot(X)
+        except LinearOperatorError:
+            return NotImplemented
+
+    def __rmul__(self, X):
+        try:
+            return _ScaledLinearOperator(self, X)
+        except LinearOperatorError:
+            return NotImplemented
+
+    def __pow__(self, X):
+        try:
+            return _PowerLinearOperator(self, X)
+        except LinearOperatorError:
+            return NotImplemented
+
+    def __add__(self, X):
+        try:
+            return _SumLinearOperator(self, X)
+        except LinearOperatorError:
+            return NotImplemented
+
+    def __neg__(self):
+        try:
+            return _ScaledLinearOperator(self, -1)
+        except LinearOperatorError:
+            return NotImplemented
+
+    def __sub__(self, X):
+        return self + (-X)
+
+    def __repr__(self):
+        m, n = self.shape
+        return "<%dx%d %s with dtype=%s>" % (m, n, self.__class__.__name__, str(self.dtype))
+
+
+class _DeviceOperator(LinearOperator):
+    """Base of operators whose action is a kernel: the numpy-facing ``dot`` is
+    H2D -> kernel -> D2H, the solvers call ``_apply_dev`` directly."""
+
+    _device_native = True
+
+    def __init__(self, shape, dtype):
+        super(_DeviceOperator, self).__init__(shape, dtype, self._dot_np, self._dot_adj_np)
+
+    def _np(self, X, adj):
+        ctx = _ctx()
+        X = numpy.asarray(X)
+        dt = _compute_dtype(_common_type([self.dtype, X.dtype]))
+        Yd = self._apply_dev(ctx.to_block(X, dt), adj=adj)
+        return ctx.to_numpy(Yd)
+
+    def _dot_np(self, X):
+        return self._np(X, False)
+
+    def _dot_adj_np(self, X):
+        return self._np(X, True)
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        raise NotImplementedError
+
+
+def _get_dtype(operators, dtypes=None):
+    """krypy/utils.py:1459-1465."""
+    if dtypes is None:
+        dtypes = []
+    for obj in operators:
+        if obj is not None and hasattr(obj, "dtype"):
+            dtypes.append(obj.dtype)
+    return _common_type(dtypes)
+
+
+class _SumLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1468-1483."""
+
+    def __init__(self, A, B):
+        if not isinstance(A, LinearOperator) or not isinstance(B, LinearOperator):
+            raise LinearOperatorError("both operands have to be a LinearOperator")
+        if A.shape != B.shape:
+            raise LinearOperatorError("shape mismatch")
+        self.args = (A, B)
+        super(_SumLinearOperator, self).__init__(A.shape, _get_dtype([A, B]))
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        ctx = _ctx()
+        Y0 = self.args[0]._apply_dev(Xd, adj=adj)
+        Y1 = self.args[1]._apply_dev(Xd, adj=adj)
+        if out is None:
+            out = ctx.empty(Xd.shape, Xd.dtype)
+        ctx.axpby(1.0, Y0, 1.0, Y1, out)
+        return out
+
+
+class _ProductLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1486-1501."""
+
+    def __init__(self, A, B):
+        if not isinstance(A, LinearOperator) or not isinstance(B, LinearOperator):
+            raise LinearOperatorError("both operands have to be a LinearOperator")
+        if A.shape[1] != B.shape[0]:
+            raise LinearOperatorError("shape mismatch")
+        self.args = (A, B)
+        super(_ProductLinearOperator, self).__init__((A.shape[0], B.shape[1]), _get_dtype([A, B]))
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        if adj:
+            T = self.args[0]._apply_dev(Xd, adj=True)
+            return self.args[1]._apply_dev(T, out=out, adj=True)
+        if getattr(self.args[0], "_inplace", False) and out is not None:
+            # outer factor works in place on its argument (deflation projector): no temporary
+            T = self.args[1]._apply_dev(Xd, out=out)
+            return self.args[0]._apply_dev(T, out=out)
+        T = self.args[1]._apply_dev(Xd)
+        return self.args[0]._apply_dev(T, out=out)
+
+
+class _ScaledLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1504-1519."""
+
+    def __init__(self, A, alpha):
+        if not isinstance(A, LinearOperator):
+            raise LinearOperatorError("LinearOperator expected as A")
+        if not numpy.isscalar(alpha):
+            raise LinearOperatorError("scalar expected as alpha")
+        self.args = (A, alpha)
+        super(_ScaledLinearOperator, self).__init__(A.shape, _get_dtype([A], [type(alpha)]))
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        ctx = _ctx()
+        alpha = self.args[1]
+        if numpy.iscomplexobj(alpha):
+            raise NotImplementedError("complex scaling is not supported by the device path")
+        Y = self.args[0]._apply_dev(Xd, adj=adj)
+        if out is None:
+            out = Y if Y is not Xd else ctx.empty(Xd.shape, Xd.dtype)
+        ctx.axpby(float(alpha), Y, 0.0, None, out)
+        return out
+
+
+class _PowerLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1522-1545."""
+
+    def __init__(self, A, p):
+        if not isinstance(A, LinearOperator):
+            raise LinearOperatorError("LinearOperator expected as A")
+        if A.shape[0] != A.shape[1]:
+            raise LinearOperatorError("square LinearOperator expected as A")
+        if not _isintlike(p):
+            raise LinearOperatorError("integer expected as p")
+        self.args = (A, p)
+        super(_PowerLinearOperator, self).__init__(A.shape, A.dtype)
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        res = Xd.clone()
+        for _ in range(self.args[1]):
+            res = self.args[0]._apply_dev(res, adj=adj)
+        if out is not None:
+            out.copy_(res)
+            return out
+        return res
+
+
+class _AdjointLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1548-1556."""
+
+    def __init__(self, A):
+        if not isinstance(A, LinearOperator):
+            raise LinearOperatorError("LinearOperator expected as A")
+        self.args = (A,)
+        m, n = A.shape
+        super(_AdjointLinearOperator, self).__init__((n, m), A.dtype)
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        return self.args[0]._apply_dev(Xd, out=out, adj=not adj)
+
+
+class IdentityLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1559-1569 (dtype float64, takes part in promotion, F3)."""
+
+    def __init__(self, shape):
+        super(IdentityLinearOperator, self).__init__(shape, numpy.dtype(None))
+
+    def _dot_np(self, X):
+        return X
+
+    def _dot_adj_np(self, X):
+        return X
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        if out is not None:
+            if out.data_ptr() != Xd.data_ptr():
+                out.copy_(Xd)
+            return out
+        return Xd
+
+
+class ZeroLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1572-1582."""
+
+    def __init__(self, shape):
+        super(ZeroLinearOperator, self).__init__(shape, numpy.dtype(None))
+
+    def _dot_np(self, X):
+        return numpy.zeros(X.shape)
+
+    def _dot_adj_np(self, X):
+        return numpy.zeros(X.shape)
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        if out is not None:
+            out.zero_()
+            return out
+        return _ctx().zeros(Xd.shape, Xd.dtype)
+
+
+class MatrixLinearOperator(_DeviceOperator):
+    """krypy/utils.py:1585-1602: a matrix as operator.  Sparse matrices are
+    uploaded once per compute dtype as device CSR (kry_spmv_csr), dense arrays as
+    row-major device matrices (kry_gemv_dense); the adjoint is materialised
+    lazily like the reference's cached ``A.T.conj()`` (:1596-1599)."""
+
+    def __init__(self, A):
+        if _is_dev(A):
+            if A.layout == _device.torch().sparse_csr:
+                import scipy.sparse as sp
+                A = sp.csr_matrix((A.values().cpu().numpy(), A.col_indices().cpu().numpy(),
+                                   A.crow_indices().cpu().numpy()), shape=tuple(A.shape))
+            else:
+                A = A.detach().cpu().numpy()
+        super(MatrixLinearOperator, self).__init__(A.shape, A.dtype)
+        self._A = A
+        self._A_adj = None
+        self._devcache = {}
+
+    def _dev(self, tdtype, adj=False):
+        key = (tdtype, adj)
+        obj = self._devcache.get(key)
+        if obj is None:
+            ctx = _ctx()
+            if adj and self._A_adj is None:
+                self._A_adj = self._A.T.conj()
+            A = self._A_adj if adj else self._A
+            if numpy.dtype(A.dtype).kind == "c":
+                raise NotImplementedError("complex matrices are not supported by the device path")
+            if _isspmatrix(A):
+                obj = ctx.upload_csr(A, tdtype)
+            else:
+                npdt = _device.torch_to_np_dtype(tdtype)
+                obj = _device.torch().from_numpy(
+                    numpy.ascontiguousarray(numpy.asarray(A), dtype=npdt)).to(ctx.device)
+            self._devcache[key] = obj
+        return obj
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        ctx = _ctx()
+        A = self._dev(Xd.dtype, adj)
+        k = Xd.shape[0]
+        if out is None:
+            out = ctx.empty((k, A.shape[0]), Xd.dtype)
+        sparse = isinstance(A, _device.CsrDev)
+        for j in range(k):
+            if sparse:
+                ctx.spmv(A, Xd[j], out[j])
+            else:
+                ctx.gemv(A, Xd[j], out[j])
+        return out
+
+    def __repr__(self):
+        return self._A.__repr__()
+
+
+class DiagonalLinearOperator(_DeviceOperator):
+    """A diagonal operator stored as one device vector (new; a sparse matrix
+    whose pattern is exactly the main diagonal -- e.g. the Jacobi ``M`` of config
+    C3 -- is turned into this by ``get_linearoperator``)."""
+
+    def __init__(self, d):
+        d = numpy.asarray(d).reshape(-1)
+        super(DiagonalLinearOperator, self).__init__((d.shape[0], d.shape[0]), d.dtype)
+        self._d = d
+        self._devcache = {}
+
+    def _dev(self, tdtype):
+        obj = self._devcache.get(tdtype)
+        if obj is None:
+            if numpy.dtype(self._d.dtype).kind == "c":
+                raise NotImplementedError("complex diagonal not supported by the device path")
+            obj = _ctx().to_block(self._d, tdtype)[0]
+            self._devcache[tdtype] = obj
+        return obj
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        ctx = _ctx()
+        d = self._dev(Xd.dtype)
+        if out is None:
+            out = ctx.empty(Xd.shape, Xd.dtype)
+        for j in range(Xd.shape[0]):
+            ctx.diag_mul(d, Xd[j], out[j])
+        return out
+
+
+class _FunctionDeviceOperator(_DeviceOperator):
+    """Operator defined by a function on device blocks (used for the deflation
+    projector, krypy/deflation.py:129-131)."""
+
+    _inplace = True     # fn may overwrite its argument and return it
+
+    def __init__(self, shape, dtype, fn):
+        super(_FunctionDeviceOperator, self).__init__(shape, dtype)
+        self._fn = fn
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        if adj:
+            raise LinearOperatorError("dot_adj undefined")
+        if out is None:
+            out = Xd.clone()
+        elif out.data_ptr() != Xd.data_ptr():
+            out.copy_(Xd)
+        Y = self._fn(out)
+        if Y.data_ptr() != out.data_ptr():
+            out.copy_(Y)
+        return out
+
+
+class Timer(list):
+    """krypy/utils.py:1289-1318 (wall-clock, synchronises the device on exit so
+    the measured block includes the kernels it launched)."""
+
+    def __enter__(self):
+        self.tstart = time.time()
+
+    def __exit__(self, a, b, c):
+        if _device._torch is not None and _device._torch.cuda.is_available():
+            _device._torch.cuda.synchronize()
+        self.append(time.time() - self.tstart)
+
+
+class Timings(defaultdict):
+    """krypy/utils.py:1321-1362."""
+
+    def __init__(self):
+        super(Timings, self).__init__(Timer)
+
+    def get(self, key):
+        if key in self and len(self[key]) > 0:
+            return min(self[key])
+        return 0
+
+    def get_ops(self, ops):
+        t = 0.0
+        for op, count in ops.items():
+            t += self.get(op) * count
+        return t
+
+    def __repr__(self):
+        return "Timings(" + ", ".join(["%s: %s" % (key, self.get(key)) for key in self]) + ")"
+
+
+class TimedLinearOperator(LinearOperator):
+    """krypy/utils.py:1605-1636."""
+
+    def __init__(self, linear_operator, timer=None):
+        self._linear_operator = linear_operator
+        super(TimedLinearOperator, self).__init__(
+            shape=linear_operator.shape, dtype=linear_operator.dtype,
+            dot=linear_operator.dot, dot_adj=linear_operator.dot_adj)
+        if timer is None:
+            timer = Timer()
+        self._timer = timer
+
+    def dot(self, X):
+        k = X.shape[1]
+        if k == 0:
+            return self._linear_operator.dot(X)
+        with self._timer:
+            ret = self._linear_operator.dot(X)
+        self._timer[-1] /= k
+        return ret
+
+    def dot_adj(self, X):
+        k = X.shape[1]
+        if k == 0:
+            return self._linear_operator.dot(X)
+        with self._timer:
+            ret = self._linear_operator.dot_adj(X)
+        self._timer[-1] /= k
+        return ret
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        k = Xd.shape[0]
+        if k == 0:
+            return self._linear_operator._apply_dev(Xd, out=out, adj=adj)
+        with self._timer:
+            ret = self._linear_operator._apply_dev(Xd, out=out, adj=adj)
+        self._timer[-1] /= k
+        return ret
+
+
+def _as_diagonal(A):
+    """Return the diagonal if sparse A stores exactly its main diagonal, else None."""
+    import scipy.sparse as sp
+    if not sp.issparse(A) or A.shape[0] != A.shape[1]:
+        return None
+    A = A.tocsr() if not sp.isspmatrix_csr(A) else A
+    n = A.shape[0]
+    if A.nnz != n or n == 0:
+        return None
+    if not numpy.array_equal(A.indptr, numpy.arange(n + 1)):
+        return None
+    if not numpy.array_equal(A.indices, numpy.arange(n)):
+        return None
+    return A.data
+
+
+def get_linearoperator(shape, A, timer=None):
+    """krypy/utils.py:241-273 (plus csr_array, torch tensors, diagonal detection)."""
+    ret = None
+    import scipy.sparse.linalg as scipylinalg
+
+    if isinstance(A, LinearOperator):
+        ret = A
+    elif A is None:
+        ret = IdentityLinearOperator(shape)
+    elif isinstance(A, numpy.matrix):
+        ret = MatrixLinearOperator(numpy.atleast_2d(numpy.asarray(A)))
+    elif isinstance(A, numpy.ndarray) or _isspmatrix(A) or _is_dev(A):
+        d = _as_diagonal(A) if _isspmatrix(A) else None
+        ret = DiagonalLinearOperator(d) if d is not None else MatrixLinearOperator(A)
+    elif isinstance(A, scipylinalg.LinearOperator):
+        if not hasattr(A, "dtype"):
+            raise ArgumentError("scipy LinearOperator has no dtype.")
+        ret = LinearOperator(A.shape, dot=A.matvec, dot_adj=A.rmatvec, dtype=A.dtype)
+    else:
+        raise TypeError("type not understood")
+
+    if A is not None and not isinstance(A, IdentityLinearOperator) and timer is not None:
+        ret = TimedLinearOperator(ret, timer)
+
+    if tuple(shape) != tuple(ret.shape):
+        raise LinearOperatorError("shape mismatch")
+    return ret
+
+
+# --------------------------------------------------------------------------
+# inner products and norms -- krypy/utils.py:146-238
+# --------------------------------------------------------------------------
+def _is_identity_ip(ip_B):
+    return ip_B is None or isinstance(ip_B, IdentityLinearOperator)
+
+
+def _inner_dev(Xd, Yd, ip_B=None, out=None):
+    """<X, Y> for device blocks X (m, N), Y (n, N) -> device (m, n) fp64 tensor
+    (krypy/utils.py:160-193).  Column j of the result is one kry_block_dot."""
+    ctx = _ctx()
+    m, n = Xd.shape[0], Yd.shape[0]
+    if out is None:
+        out = ctx.scalars(max(m * n, 1))[: m * n].reshape(n, m)
+    if m == 0 or n == 0:
+        return out.t()
+    if not _is_identity_ip(ip_B):
+        try:
+            B = get_linearoperator((Xd.shape[1], Xd.shape[1]), ip_B)
+        except TypeError:
+            # callable inner product on host arrays (utils.py:186-189)
+            G = numpy.asarray(ip_B(ctx.to_numpy(Xd), ctx.to_numpy(Yd)))
+            if numpy.iscomplexobj(G):
+                raise NotImplementedError("complex inner products are not supported")
+            res = _device.torch().from_numpy(numpy.ascontiguousarray(G, dtype=numpy.float64)).to(ctx.device)
+            return res
+        if m > n:
+            # (B X)^H Y: for a real self-adjoint B this equals X^T (B Y) up to round-off;
+            # follow the reference's choice of which side gets B (utils.py:190-193)
+            BX = B._apply_dev(Xd)
+            for j in range(n):
+                ctx.block_dot(BX, m, Yd[j], out[j])
+            return out.t()
+        Yd = B._apply_dev(Yd)
+    for j in range(n):
+        ctx.block_dot(Xd, m, Yd[j], out[j])
+    return out.t()
+
+
+def _ip_coef(Xd, Yd, ip_B, out, acc=None, post=0):
+    """out[0] = <x, y>_B for single-vector device blocks (1, N) without leaving the
+    device (post=1: sqrt(|.|) as numpy.sqrt(numpy.linalg.norm(ip, 2)) gives for a
+    1x1 matrix, utils.py:238); acc[0] += out[0] when given."""
+    ctx = _ctx()
+    if _is_identity_ip(ip_B):
+        ctx.block_dot(Xd, 1, Yd[0], out, post, acc)
+        return
+    try:
+        B = get_linearoperator((Xd.shape[1], Xd.shape[1]), ip_B)
+    except TypeError:
+        val = numpy.asarray(ip_B(ctx.to_numpy(Xd), ctx.to_numpy(Yd)))[0, 0]
+        if numpy.iscomplexobj(val):
+            if abs(val.imag) > 1e-10 * max(abs(val), 1e-300):
+                raise NotImplementedError("complex inner products are not supported")
+            val = val.real
+        val = float(val)
+        if post:
+            val = float(numpy.sqrt(abs(val)))
+        out[0:1].fill_(val)
+        if acc is not None:
+            acc[0:1].add_(val)
+        return
+    ctx.block_dot(Xd, 1, B._apply_dev(Yd)[0], out, post, acc)
+
+
+def ip_euclid(X, Y):
+    """Euclidean inner product X^* Y (krypy/utils.py:146-157)."""
+    return inner(X, Y)
+
+
+def inner(X, Y, ip_B=None):
+    """krypy/utils.py:160-193 for numpy ``(N,m)``, ``(N,n)`` inputs -> numpy ``(m,n)``."""
+    if _is_dev(X) or _is_dev(Y):
+        return _inner_dev(X, Y, ip_B)
+    ctx = _ctx()
+    X = numpy.asarray(X)
+    Y = numpy.asarray(Y)
+    dt = _compute_dtype(_common_type([X.dtype, Y.dtype, getattr(ip_B, "dtype", None)]))
+    res = _inner_dev(ctx.to_block(X, dt), ctx.to_block(Y, dt), ip_B)
+    return res.cpu().numpy().copy()
+
+
+def norm_squared(x, Mx=None, inner_product=ip_euclid):
+    """krypy/utils.py:196-211."""
+    assert len(x.shape) == 2
+    if Mx is None:
+        rho = inner_product(x, x)
+    else:
+        assert len(Mx.shape) == 2
+        rho = inner_product(x, Mx)
+    if rho.shape == (1, 1):
+        if abs(rho[0, 0].imag) > abs(rho[0, 0]) * 1e-10 or rho[0, 0].real < 0.0:
+            raise InnerProductError("<x,Mx> = %g. Is the inner product indefinite?" % rho[0, 0])
+    return numpy.linalg.norm(rho, 2)
+
+
+def norm(x, y=None, ip_B=None):
+    r"""krypy/utils.py:214-238: :math:`\sqrt{\langle x,y\rangle}`."""
+    if y is None:
+        y = x
+    ip = inner(x, y, ip_B=ip_B)
+    if _is_dev(ip):
+        ip = ip.cpu().numpy()
+    if ip.size == 0:
+        return 0.0
+    nrm_diag = numpy.linalg.norm(numpy.diag(ip), 2)
+    nrm_diag_imag = numpy.linalg.norm(numpy.imag(numpy.diag(ip)), 2)
+    if nrm_diag_imag > nrm_diag * 1e-10:
+        raise InnerProductError("inner product defined by ip_B not positive definite?")
+    return numpy.sqrt(numpy.linalg.norm(ip, 2))
+
+
+def orthonormality(V, ip_B=None):
+    """krypy/utils.py:297-305."""
+    return numpy.linalg.norm(numpy.eye(V.shape[1]) - inner(V, V, ip_B=ip_B), 2)
+
+
+def arnoldi_res(A, V, H, ip_B=None):
+    """krypy/utils.py:308-329."""
+    N = V.shape[0]
+    invariant = H.shape[0] == H.shape[1]
+    A = get_linearoperator((N, N), A)
+    if invariant:
+        res = A * V - numpy.dot(V, H)
+    else:
+        res = A * V[:, :-1] - numpy.dot(V, H)
+    return norm(res, ip_B=ip_B)
+
+
+# --------------------------------------------------------------------------
+# Givens / Householder -- krypy/utils.py:332-436
+# --------------------------------------------------------------------------
+def _drotg(a, b):
+    """BLAS drotg (reference-BLAS 3.10 algorithm), the host twin of the device
+    routine in csrc/kry_small.cu; returns (c, s)."""
+    anorm, bnorm = abs(a), abs(b)
+    if bnorm == 0.0:
+        return 1.0, 0.0
+    if anorm == 0.0:
+        return 0.0, 1.0
+    safmin, safmax = 2.2250738585072014e-308, 4.4942328371557898e+307
+    scl = min(safmax, max(safmin, anorm, bnorm))
+    sigma = numpy.copysign(1.0, a) if anorm > bnorm else numpy.copysign(1.0, b)
+    r = sigma * (scl * numpy.sqrt((a / scl) ** 2 + (b / scl) ** 2))
+    return a / r, b / r
+
+
+class Givens:
+    """krypy/utils.py:405-436 for a real (2,1) vector.  This 2x2 helper is scalar
+    host arithmetic; inside the solvers the rotations are generated and applied
+    on the device (kry_givens_update / kry_minres_recur)."""
+
+    def __init__(self, x):
+        if x.shape != (2, 1):
+            raise ArgumentError("x is not a vector of shape (2,1)")
+        a = x[0].item()
+        b = x[1].item()
+        if numpy.isreal(x).all():
+            a = float(numpy.real(a))
+            b = float(numpy.real(b))
+            c, s = _drotg(a, b)
+        else:
+            raise NotImplementedError("complex Givens rotations are not supported")
+        self.c = c
+        self.s = s
+        self.r = c * a + s * b
+        self.G = numpy.array([[c, s], [-numpy.conj(s), c]])
+
+    def apply(self, x):
+        return numpy.dot(self.G, x)
+
+
+class House:
+    """krypy/utils.py:332-402 is not on any BASELINE path."""
+
+    def __init__(self, x):
+        raise NotImplementedError(
+            "Householder orthogonalisation is not implemented on the device path "
+            "(use ortho='mgs', 'dmgs', 'cgs', 'cgs2' or 'lanczos')")
+
+
+# --------------------------------------------------------------------------
+# QR with inner product, Projection -- krypy/utils.py:439-707
+# --------------------------------------------------------------------------
+def _qr_dev(Xd, ip_B=None, reorthos=1):
+    """Modified Gram-Schmidt QR of a device block (k, N) in the ``ip_B`` inner
+    product (krypy/utils.py:695-707).  Returns (Q (k, N) device, R numpy (k,k))."""
+    ctx = _ctx()
+    k, N = Xd.shape
+    ld = (N + 31) // 32 * 32
+    store = ctx.empty((max(k, 1), ld), Xd.dtype)
+    Q = store[:k, :N]
+    Q.copy_(Xd)
+    Rdev = ctx.scalars(max(k * (k + 1), 1))          # row i: R[:, i] (column i) + norm slot
+    Rrows = Rdev[: k * (k + 1)].reshape(k, k + 1) if k else None
+    euclid = _is_identity_ip(ip_B)
+    tmp = ctx.scalars(2)
+    R = numpy.zeros((k, k))
+    for i in range(k):
+        qi = Q[i]
+        if euclid:
+            ctx.orth_fused(Q, Q, 0, i, qi, reorthos + 1, KRY_ORTH_MGS, Rrows[i], nrm=Rrows[i][i:])
+        else:
+            for _ in range(reorthos + 1):
+                for j in range(i):
+                    _ip_coef(Q[j:j + 1], Q[i:i + 1], ip_B, tmp, acc=Rrows[i][j:])
+                    ctx.axpy_dev(tmp, -1.0, Q[j], qi)
+            _ip_coef(Q[i:i + 1], Q[i:i + 1], ip_B, Rrows[i][i:], post=1)
+        ctx.sync()
+        col = Rrows[i][: i + 1].cpu().numpy()
+        R[: i + 1, i] = col
+        if R[i, i] >= 1e-15:                                        # utils.py:705-706
+            ctx.scale_dev(Rrows[i][i:], 1, 1.0, qi, qi)
+    return Q, R
+
+
+def qr(X, ip_B=None, reorthos=1):
+    """krypy/utils.py:680-707.  Always (re-orthogonalised) modified Gram-Schmidt
+    on the device; the reference's LAPACK shortcut for ``ip_B is None`` (:692-693)
+    differs only by column signs (R has a positive diagonal here)."""
+    if _is_dev(X):
+        return _qr_dev(X, ip_B, reorthos)
+    ctx = _ctx()
+    X = numpy.asarray(X)
+    dt = _compute_dtype(_common_type([X.dtype]))
+    if X.shape[1] == 0:
+        return X.copy(), numpy.zeros((0, 0), dtype=X.dtype)
+    Qd, R = _qr_dev(ctx.to_block(X, dt), ip_B, reorthos)
+    return ctx.to_numpy(Qd), R.astype(_common_type([X.dtype, numpy.float64]) if X.dtype.kind != "f" else X.dtype)
+
+
+class Projection(object):
+    """krypy/utils.py:439-677: oblique projection in XQRY form, bases in HBM.
+
+    ``V, W`` are exposed as ``(N, k)`` numpy arrays (lazy D2H); ``apply*`` accept
+    numpy ``(N, m)`` arrays or device blocks.  ``apply_complement`` on a single
+    vector with a Euclidean inner product is ONE fused cooperative kernel
+    (kry_project)."""
+
+    def __init__(self, X, Y=None, ip_B=None, orthogonalize=True, iterations=2):
+        import scipy.linalg
+        self.ip_B = ip_B
+        if iterations < 1:
+            raise ArgumentError("iterations < 1 not allowed")
+        self.orthogonalize = orthogonalize
+        self.iterations = iterations
+        ctx = _ctx()
+        Y = X if Y is None else Y
+        if len(X.shape) != 2:
+            raise ArgumentError("X does not have shape==(N,k)")
+        Xs = tuple(X.shape) if not _is_dev(X) else (X.shape[1], X.shape[0])
+        Ys = tuple(Y.shape) if not _is_dev(Y) else (Y.shape[1], Y.shape[0])
+        if Xs != Ys:
+            raise ArgumentError("X and Y have different shapes")
+        self._N, self._k = Xs
+        same = Y is X
+        if not _is_dev(X):
+            dt = _compute_dtype(_common_type([X.dtype, Y.dtype]))
+            Xd = ctx.to_block(X, dt)
+            Yd = Xd if same else ctx.to_block(Y, dt)
+        else:
+            Xd, Yd = X, Y
+        self._tdtype = Xd.dtype
+        self._Q_dev = self._R_dev = None
+        if self._k == 0:
+            self._Vd = self._Wd = Xd
+            self.VR = self.WR = self.Q = self.R = None
+            return
+        if orthogonalize:
+            self._Vd, self.VR = _qr_dev(Xd, ip_B=ip_B)
+        else:
+            self._Vd, self.VR = Xd, None
+        if same and orthogonalize:
+            self._Wd, self.WR = self._Vd, self.VR
+            self.Q, self.R = None, None
+        else:
+            if orthogonalize:
+                self._Wd, self.WR = _qr_dev(Yd, ip_B=ip_B)
+            else:
+                self._Wd, self.WR = Yd, None
+            M = _inner_dev(self._Wd, self._Vd, ip_B).cpu().numpy()
+            self.Q, self.R = scipy.linalg.qr(M)           # k x k host algebra (utils.py:520)
+            t = _device.torch()
+            self._Q_dev = t.from_numpy(numpy.ascontiguousarray(self.Q, dtype=numpy.float64)).to(ctx.device)
+            self._R_dev = t.from_numpy(numpy.ascontiguousarray(self.R, dtype=numpy.float64)).to(ctx.device)
+
+    @property
+    def V(self):
+        return _ctx().to_numpy(self._Vd) if self._k else numpy.zeros((self._N, 0))
+
+    @property
+    def W(self):
+        return _ctx().to_numpy(self._Wd) if self._k else numpy.zeros((self._N, 0))
+
+    # -- device implementation ------------------------------------------------
+    def _coef_transform(self, c_host, adj=False):
+        import scipy.linalg
+        if self.Q is not None and self.R is not None:
+            if adj:
+                return self.Q.dot(scipy.linalg.solve_triangular(self.R.T.conj(), c_host, lower=True))
+            return scipy.linalg.solve_triangular(self.R, self.Q.T.conj().dot(c_host))
+        return c_host
+
+    def _apply_dev(self, ad, return_Ya=False, adj=False):
+        """single application on a device block (m, N) -> Pa (m, N) [, Ya numpy (k, m)]
+        (krypy/utils.py:522-564)."""
+        ctx = _ctx()
+        t = _device.torch()
+        m = ad.shape[0]
+        Wd, Vd = (self._Vd, self._Wd) if adj else (self._Wd, self._Vd)
+        c = _inner_dev(Wd, ad, self.ip_B).cpu().numpy()          # (k, m), small
+        Ya = None
+        if return_Ya:
+            Ya = c.copy()
+            if self.WR is not None:
+                Ya = self.WR.T.conj().dot(Ya)
+        c = numpy.ascontiguousarray(self._coef_transform(c, adj=adj).T, dtype=numpy.float64)  # (m, k)
+        cd = t.from_numpy(c).to(ctx.device)
+        Pa = ctx.empty(ad.shape, ad.dtype)
+        for j in range(m):
+            ctx.block_combine(Vd, self._k, cd[j], None, Pa[j])
+        return (Pa, Ya) if return_Ya else Pa
+
+    def _complement_dev(self, ad, return_Ya=False, c_first=None, out=None):
+        """apply_complement on a device block (krypy/utils.py:604-627).  Fused
+        single-kernel path for Euclidean inner products; ``c_first`` (device, k
+        doubles per column) receives the raw W^H a of the first application."""
+        ctx = _ctx()
+        if out is None:
+            out = ad.clone()
+        elif out.data_ptr() != ad.data_ptr():
+            out.copy_(ad)
+        if self._k == 0:
+            return (out, numpy.zeros((0, ad.shape[0]))) if return_Ya else out
+        m = ad.shape[0]
+        if _is_identity_ip(self.ip_B):
+            own = c_first is None and return_Ya
+            if own:
+                c_first = ctx.scalars(self._k * m)
+            for j in range(m):
+                cf = None if c_first is None else c_first[j * self._k:(j + 1) * self._k]
+                ctx.project(self._Wd, self._Vd, self._k, out[j], self._Q_dev, self._R_dev,
+                            self.iterations, cf)
+            if return_Ya:
+                Ya = c_first[: self._k * m].reshape(m, self._k).t().cpu().numpy()
+                if self.WR is not None:
+                    Ya = self.WR.T.conj().dot(Ya)
+                return out, Ya
+            return out
+        # generic inner product: one application at a time
+        res = self._apply_dev(out, return_Ya=return_Ya)
+        x, Ya = res if return_Ya else (res, None)
+        ctx.axpby(1.0, out, -1.0, x, out)
+        for _ in range(self.iterations - 1):
+            w = self._apply_dev(out)
+            ctx.axpby(1.0, out, -1.0, w, out)
+        return (out, Ya) if return_Ya else out
+
+    # -- public numpy API -----------------------------------------------------
+    def _to_dev(self, a):
+        if _is_dev(a):
+            return a, True
+        a = numpy.asarray(a)
+        return _ctx().to_block(a, self._tdtype), False
+
+    def _ret(self, xd, was_dev):
+        return xd if was_dev else _ctx().to_numpy(xd)
+
+    def _apply(self, a, return_Ya=False):
+        """krypy/utils.py:522-552."""
+        if self._k == 0:
+            Pa = numpy.zeros(a.shape)
+            if return_Ya:
+                return Pa, numpy.zeros((0, a.shape[1]))
+            return Pa
+        ad, was_dev = self._to_dev(a)
+        res = self._apply_dev(ad, return_Ya=return_Ya)
+        if return_Ya:
+            return self._ret(res[0], was_dev), res[1]
+        return self._ret(res, was_dev)
+
+    def _apply_adj(self, a):
+        """krypy/utils.py:554-564."""
+        if self._k == 0:
+            return numpy.zeros(a.shape)
+        ad, was_dev = self._to_dev(a)
+        return self._ret(self._apply_dev(ad, adj=True), was_dev)
+
+    def apply(self, a, return_Ya=False):
+        """krypy/utils.py:566-591."""
+        if self._k == 0:
+            Pa = numpy.zeros(a.shape)
+            if return_Ya:
+                return Pa, numpy.zeros((0, a.shape[1]))
+            return Pa
+        ctx = _ctx()
+        ad, was_dev = self._to_dev(a)
+        res = self._apply_dev(ad, return_Ya=return_Ya)
+        x, Ya = res if return_Ya else (res, None)
+        for _ in range(self.iterations - 1):
+            z = ctx.empty(ad.shape, ad.dtype)
+            ctx.axpby(1.0, ad, -1.0, x, z)
+            w = self._apply_dev(z)
+            ctx.axpby(1.0, x, 1.0, w, x)
+        if return_Ya:
+            return self._ret(x, was_dev), Ya
+        return self._ret(x, was_dev)
+
+    def apply_adj(self, a):
+        """krypy/utils.py:593-602."""
+        if self._k == 0:
+            return numpy.zeros(a.shape)
+        ctx = _ctx()
+        ad, was_dev = self._to_dev(a)
+        x = self._apply_dev(ad, adj=True)
+        for _ in range(self.iterations - 1):
+            z = ctx.empty(ad.shape, ad.dtype)
+            ctx.axpby(1.0, ad, -1.0, x, z)
+            w = self._apply_dev(z, adj=True)
+            ctx.axpby(1.0, x, 1.0, w, x)
+        return self._ret(x, was_dev)
+
+    def apply_complement(self, a, return_Ya=False):
+        """krypy/utils.py:604-627."""
+        if self._k == 0:
+            if return_Ya:
+                return a.copy() if not _is_dev(a) else a.clone(), numpy.zeros((0, a.shape[1]))
+            return a.copy() if not _is_dev(a) else a.clone()
+        ad, was_dev = self._to_dev(a)
+        res = self._complement_dev(ad, return_Ya=return_Ya)
+        if return_Ya:
+            return self._ret(res[0], was_dev), res[1]
+        return self._ret(res, was_dev)
+
+    def apply_complement_adj(self, a):
+        """krypy/utils.py:629-638."""
+        if self._k == 0:
+            return a.copy()
+        ctx = _ctx()
+        ad, was_dev = self._to_dev(a)
+        x = self._apply_dev(ad, adj=True)
+        z = ctx.empty(ad.shape, ad.dtype)
+        ctx.axpby(1.0, ad, -1.0, x, z)
+        for _ in range(self.iterations - 1):
+            w = self._apply_dev(z, adj=True)
+            ctx.axpby(1.0, z, -1.0, w, z)
+        return self._ret(z, was_dev)
+
+    def _get_operator(self, fun, fun_adj):
+        N = self._N
+        return LinearOperator((N, N), _device.torch_to_np_dtype(self._tdtype), fun, fun_adj)
+
+    def operator(self):
+        """krypy/utils.py:645-654."""
+        if self._k == 0:
+            return ZeroLinearOperator((self._N, self._N))
+        return self._get_operator(self.apply, self.apply_adj)
+
+    def operator_complement(self):
+        """krypy/utils.py:656-665."""
+        if self._k == 0:
+            return IdentityLinearOperator((self._N, self._N))
+        return self._get_operator(self.apply_complement, self.apply_complement_adj)
+
+    def matrix(self):
+        """krypy/utils.py:667-677."""
+        return self.apply(numpy.eye(self._N))
+
+
+# --------------------------------------------------------------------------
+# Arnoldi / Lanczos -- krypy/utils.py:854-1081
+# --------------------------------------------------------------------------
+_ORTHO = {
+    # name: (kernel algorithm, passes)
+    "mgs": (KRY_ORTH_MGS, 1),        # utils.py:923-926: reorthos = 0
+    "dmgs": (KRY_ORTH_MGS, 2),       # reorthos = 1
+    "lanczos": (KRY_ORTH_MGS, 1),    # start = k: a single basis vector, utils.py:1000-1001
+    "cgs": (KRY_ORTH_CGS, 1),        # new: fused block classical Gram-Schmidt
+    "cgs2": (KRY_ORTH_CGS, 2),       # new: CGS with re-orthogonalisation
+}
+_CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
+
+
+class Arnoldi(object):
+    """krypy/utils.py:854-1074 with the basis resident in HBM.
+
+    ``V`` (and ``P`` when ``M`` is given) are stored vector-major as
+    ``(maxiter+1, N)`` device tensors; the ``V``/``P``/``H`` attributes and
+    ``get()`` return ``(N, k)`` numpy arrays like the reference.  One step is:
+    operator apply (kry_spmv_csr / kry_gemv_dense), ONE fused cooperative
+    Gram-Schmidt kernel (kry_orth_fused: dots, update, norm, normalised store),
+    and -- when driven by Gmres/Minres -- the small device recurrence.
+
+    ``ortho``: 'mgs', 'dmgs', 'lanczos' as in the reference (exact MGS order),
+    plus 'cgs' / 'cgs2' (block classical Gram-Schmidt, one / two passes: V is
+    read twice per pass with a single grid-wide reduction).  'house' is not
+    implemented.
+    """
+
+    def __init__(self, A, v, maxiter=None, ortho="mgs", M=None, Mv=None, Mv_norm=None, ip_B=None,
+                 dtype=None):
+        ctx = self._ctx = _ctx()
+        t = _device.torch()
+        v_dev_in = _is_dev(v)
+        N = v.shape[1] if v_dev_in else v.shape[0]
+        self.N = N
+        self.A = get_linearoperator((N, N), A)
+        self.maxiter = N if maxiter is None else maxiter
+        self.ortho = ortho
+        self.M = get_linearoperator((N, N), M)
+        if isinstance(self.M, IdentityLinearOperator):
+            self.M = None
+        self.ip_B = ip_B
+        self.dtype = _common_type([find_common_dtype(self.A, v, self.M), dtype])   # utils.py:898
+        if ortho == "house":
+            if self.M is not None or not _is_identity_ip(ip_B):
+                raise ArgumentError("Only euclidean inner product allowed with Householder orthogonalization")
+            raise NotImplementedError("ortho='house' is not implemented on the device path")
+        if ortho not in _ORTHO:
+            raise ArgumentError(
+                "Invalid value '%s' for argument 'ortho'. Valid are house, mgs, dmgs, lanczos "
+                "(and cgs, cgs2 on the device path)." % ortho)
+        self._algo, self._passes = _ORTHO[ortho]
+        td = self._td = _compute_dtype(self.dtype)
+        self.iter = 0
+        self.invariant = False
+        m1 = self.maxiter + 1
+        ld = self._ld = (N + 31) // 32 * 32
+        self._Vs = ctx.empty((m1, ld), td)
+        self._Vd = self._Vs[:, :N]
+        self._Pd = None
+        if self.M is not None:
+            self._Ps = ctx.empty((m1, ld), td)
+            self._Pd = self._Ps[:, :N]
+        # small quantities are always >= fp64 on the device path (also in fp32 storage mode)
+        self.H = numpy.zeros((self.maxiter + 1, self.maxiter), dtype=_common_type([self.dtype, numpy.float64]))
+        self._euclid = _is_identity_ip(ip_B)
+        self._q = ctx.empty((1, N), td)
+        self._t = None if (self._euclid and self.M is None) else ctx.empty((1, N), td)
+        self._hcol_store = ctx.scalars(self.maxiter + 2 + 8)
+        self._hcol = self._hcol_store[1:]       # one leading zero: H[-1, 0] of linsys.py:828
+        self._tmp = ctx.scalars(4)
+        self._lz = ctx.scalars(3)          # Lanczos: [H[k-1,k], H[k,k], H[k+1,k]]
+        self._lz_st = ctx.scalars(16)
+        self._hfro2 = 0.0
+
+        # first basis vector: utils.py:923-952
+        vd = v if v_dev_in else ctx.to_block(numpy.asarray(v), td)
+        if vd.dtype != td:
+            vd = vd.to(td)
+        if self.M is not None:
+            pd = vd
+            if Mv is None:
+                vd = self.M._apply_dev(pd)
+            else:
+                vd = Mv if _is_dev(Mv) else ctx.to_block(numpy.asarray(Mv), td)
+            if Mv_norm is None:
+                self.vnorm = self._norm_dev(pd, vd)
+            else:
+                self.vnorm = Mv_norm
+            if self.vnorm > 0:
+                self._set_scaled(self._Pd[0], pd[0], self.vnorm)
+        else:
+            if Mv_norm is None:
+                self.vnorm = self._norm_dev(vd, None)
+            else:
+                self.vnorm = Mv_norm
+        if self.vnorm > 0:
+            self._set_scaled(self._Vd[0], vd[0], self.vnorm)
+        else:
+            self.invariant = True
+
+    # -- helpers ---------------------------------------------------------------
+    def _set_scaled(self, dst, src, s):
+        """dst = src / s with a host scalar (utils.py:938, 950)."""
+        self._tmp[3:4].fill_(float(s))
+        self._ctx.scale_dev(self._tmp[3:], 1, 1.0, src, dst)
+
+    def _norm_dev(self, xd, yd):
+        """norm(x, y, ip_B) of device blocks (1, N): one sync (setup only)."""
+        _ip_coef(xd, xd if yd is None else yd, self.ip_B, self._tmp, post=1)
+        return float(self._tmp[0].item())
+
+    # -- one step, enqueue only ---------------------------------------------------
+    def _enqueue(self, k):
+        """Launch the kernels of Arnoldi step k (utils.py:964-1045) without any
+        host synchronisation.  Results: h[0..k] accumulated into self._hcol (or
+        self._lz for Lanczos), H[k+1,k] in hcol[k+1] (lz[2]), V[k+1] (P[k+1]) stored."""
+        ctx = self._ctx
+        V, P = self._Vd, self._Pd
+        q = self._q
+        self.A._apply_dev(V[k:k + 1], out=q)                       # utils.py:968
+        q0 = q[0]
+        lanczos = self.ortho == "lanczos"
+        start = k if lanczos else 0
+        Vsub = P if P is not None else V
+        if lanczos:
+            h_ptr = self._lz.data_ptr() + 8 * (1 - k)               # h[k] -> lz[1]
+            nrm = self._lz[2:]
+            pre_vec = Vsub[k - 1] if k > 0 else None
+            pre_coef = self._lz if k > 0 else None
+        else:
+            h_ptr = self._hcol.data_ptr()
+            nrm = self._hcol[k + 1:]
+            pre_vec = pre_coef = None
+        if self._euclid:
+            fused_tail = self.M is None
+            if self._algo == KRY_ORTH_CGS and (k + 1 - start) > _CGS_CHUNK:
+                # more basis vectors than reduction slots: block-wise CGS
+                j0 = start
+                while j0 < k + 1:
+                    j1 = min(j0 + _CGS_CHUNK, k + 1)
+                    last = j1 == k + 1
+                    ctx.orth_fused(V, Vsub, j0, j1, q0, self._passes, self._algo, None,
+                                   nrm=nrm if (last and fused_tail) else None,
+                                   vnext=V[k + 1] if (last and fused_tail) else None, h_ptr=h_ptr)
+                    j0 = j1
+            else:
+                ctx.orth_fused(V, Vsub, start, k + 1, q0, self._passes, self._algo, None,
+                               nrm=nrm if fused_tail else None,
+                               vnext=V[k + 1] if fused_tail else None,
+                               pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr)
+        else:
+            # generic inner product: the reference's loop, one reduction at a time
+            if pre_vec is not None:
+                ctx.axpy_dev(pre_coef, -1.0, pre_vec, q0)
+            for _ in range(self._passes):
+                for j in range(start, k + 1):
+                    hslot = self._lz[1:] if lanczos else self._hcol[j:]
+                    _ip_coef(V[j:j + 1], q, self.ip_B, self._tmp, acc=hslot)     # utils.py:1015, 1025
+                    ctx.axpy_dev(self._tmp, -1.0, Vsub[j], q0)                    # utils.py:1026-1029
+            fused_tail = False
+        if not fused_tail:
+            # utils.py:1030-1045: M apply, norm, scaled stores
+            if self.M is not None:
+                MAv = self.M._apply_dev(q, out=self._t)
+                _ip_coef(q, MAv, self.ip_B, nrm, post=1)
+                ctx.scale_dev(nrm, 1, 1.0, q0, P[k + 1])
+                ctx.scale_dev(nrm, 1, 1.0, MAv[0], V[k + 1])
+            else:
+                _ip_coef(q, q, self.ip_B, nrm, post=1)
+                ctx.scale_dev(nrm, 1, 1.0, q0, V[k + 1])
+
+    def _finish(self, k, hcol_host):
+        """Host bookkeeping of step k given H[0..k+1, k] (utils.py:1025, 1032-1039, 1048)."""
+        H = self.H
+        if self.ortho == "lanczos":
+            if k > 0:
+                H[k - 1, k] = H[k, k - 1]                         # utils.py:1003
+            H[k, k] = hcol_host[0]
+            H[k + 1, k] = hcol_host[1]
+            col2 = hcol_host[0] ** 2 + hcol_host[1] ** 2 + (H[k - 1, k] ** 2 if k > 0 else 0.0)
+        else:
+            H[: k + 2, k] = hcol_host[: k + 2]
+            col2 = float(numpy.dot(hcol_host[: k + 2], hcol_host[: k + 2]))
+        self._hfro2 += col2
+        hk = H[k + 1, k]
+        # invariant-subspace test H[k+1,k]/||H[:k+2,:k+1]||_2 <= 1e-14 (utils.py:1035-1039).
+        # ||H||_2 <= ||H||_F, so the SVD is only needed when the cheap bound cannot decide.
+        if not numpy.isfinite(hk):
+            self.invariant = True
+        elif hk <= 1e-14 * numpy.sqrt(self._hfro2):
+            nrm2 = numpy.linalg.norm(H[: k + 2, : k + 1], 2)
+            if nrm2 == 0 or hk / nrm2 <= 1e-14:
+                self.invariant = True
+        self.iter = k + 1
+
+    def advance(self):
+        """Carry out one iteration of Arnoldi (krypy/utils.py:954-1048)."""
+        if self.iter >= self.maxiter:
+            raise ArgumentError("Maximum number of iterations reached.")
+        if self.invariant:
+            raise ArgumentError("Krylov subspace was found to be invariant in the previous iteration.")
+        ctx = self._ctx
+        k = self.iter
+        self._enqueue(k)
+        if self.ortho == "lanczos":
+            ctx.minres_recur(k, self._lz, self._lz_st, 1, 0)        # publishes + shifts the 3 entries
+            ctx.sync()
+            self._finish(k, ctx.mailbox[6:8].copy())
+        else:
+            hc = self._hcol[: k + 2].cpu().numpy()                   # synchronising D2H of k+2 doubles
+            self._hcol[: k + 2].zero_()
+            self._finish(k, hc)
+
+    # -- accessors ------------------------------------------------------------------
+    def _block_np(self, Bd, ncols):
+        out = numpy.zeros((self.N, self.maxiter + 1), dtype=self.dtype)
+        if ncols > 0:
+            out[:, :ncols] = self._ctx.to_numpy(Bd[:ncols])
+        return out
+
+    def _valid_cols(self):
+        return self.iter if self.invariant else self.iter + 1
+
+    @property
+    def V(self):
+        return self._block_np(self._Vd, self._valid_cols())
+
+    @property
+    def P(self):
+        if self._Pd is None:
+            raise AttributeError("P")
+        return self._block_np(self._Pd, self._valid_cols())
+
+    def get(self):
+        """krypy/utils.py:1050-1061."""
+        k = self.iter
+        ctx = self._ctx
+        if self.invariant:
+            V, H = ctx.to_numpy(self._Vd[:k]).astype(self.dtype, copy=False), self.H[:k, :k]
+            if self.M is not None:
+                return V, H, ctx.to_numpy(self._Pd[:k]).astype(self.dtype, copy=False)
+            return V, H
+        V, H = ctx.to_numpy(self._Vd[: k + 1]).astype(self.dtype, copy=False), self.H[: k + 1, :k]
+        if self.M is not None:
+            return V, H, ctx.to_numpy(self._Pd[: k + 1]).astype(self.dtype, copy=False)
+        return V, H
+
+    def get_last(self):
+        """krypy/utils.py:1063-1074."""
+        k = self.iter
+        ctx = self._ctx
+        if self.invariant:
+            V, H = None, self.H[:k, [k - 1]]
+            if self.M is not None:
+                return V, H, None
+            return V, H
+        V, H = ctx.to_numpy(self._Vd[k:k + 1]).astype(self.dtype, copy=False), self.H[: k + 1, [k - 1]]
+        if self.M is not None:
+            return V, H, ctx.to_numpy(self._Pd[k:k + 1]).astype(self.dtype, copy=False)
+        return V, H
+
+
+def arnoldi(*args, **kwargs):
+    """krypy/utils.py:1077-1081."""
+    _arnoldi = Arnoldi(*args, **kwargs)
+    while _arnoldi.iter < _arnoldi.maxiter and not _arnoldi.invariant:
+        _arnoldi.advance()
+    return _arnoldi.get()

@@ -1,0 +1,223 @@
+"""Solver-level parity on the GPU: the CUDA path (through the KryPy-compatible
+classes, which call the C ABI) against (i) the oracle on the same seeded inputs,
+(ii) the reference fixtures in tests/golden/ and (iii) the literal known answers
+of the reference's own test-suite.
+
+Tolerances (fp64): iteration-for-iteration relative residual norms within 1e-10
+(BASELINE.json north_star); entries that are EXPLICIT residuals
+(krypy/linsys.py:450-463: the last entry of a converged/ended solve) are subject
+to cancellation in b - A x_k and get 1e-10*res + 1e-13."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+import runners
+
+pytestmark = pytest.mark.gpu
+
+KNOWN = {  # reference test/test_convenience_wrappers.py:10-12 and :37-39
+    "c1_cg": [1004.1873775173957, 1000.0003174916551, 999.9999999997555],
+    "c1_gmres": [1004.1873724888546, 1000.0003124630923, 999.999994971191],
+    "c1_minres": [1004.187372488912, 1000.0003124632159, 999.9999949713145],
+    "c1_cg_defl": [1004.1873775173271, 1000.0003174918709, 1000.0],
+    "c1_minres_defl": [1004.1873774950692, 1000.0003174918709, 1000.0],
+    "c1_gmres_defl": [1004.1873774950692, 1000.0003174918709, 1000.0],
+}
+
+def _check_history(got, ref, rtol=1e-10, atol_explicit=1e-13):
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    if len(ref) > 1:
+        np.testing.assert_allclose(got[:-1], ref[:-1], rtol=rtol, atol=1e-300)
+    assert abs(got[-1] - ref[-1]) <= rtol * abs(ref[-1]) + atol_explicit, (got[-1], ref[-1])
+
+
+@pytest.mark.parametrize("name", sorted(KNOWN))
+def test_known_answers_through_convenience_api(name):
+    """the reference's golden numbers, through krypy_b200.cg/minres/gmres"""
+    import krypy_b200 as kp
+    c = cases.case_inputs(name)
+    fn = {"cg": kp.cg, "gmres": kp.gmres, "minres": kp.minres}[c["solver"]]
+    kw = {}
+    if "U" in c["kw"]:
+        kw["U"] = c["kw"]["U"].reshape(-1)
+    else:
+        kw["inner_product"] = np.dot
+    sol, solver = fn(c["A"], c["b"], **kw)
+    assert sol.shape == c["b"].shape
+    ref = KNOWN[name]
+    tol = 1.0e-11
+    assert abs(np.sum(np.abs(sol)) - ref[0]) < tol * ref[0]
+    assert abs(np.sqrt(np.dot(sol, sol)) - ref[1]) < tol * ref[1]
+    assert abs(np.max(np.abs(sol)) - ref[2]) < tol * ref[2]
+
+
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_matches_reference_fixture_and_oracle(name):
+    gold = runners.load_golden(name)
+    orac = runners.run_oracle(name)
+    got = runners.run_product(name)    # default dtype rule = the reference's promotion (>= fp64)
+    assert bool(got["converged"]) == bool(gold["converged"])
+    for ref in (gold, orac):
+        _check_history(got["resnorms"], ref["resnorms"])
+        scale = np.abs(ref["xk"]).max() + 1e-300
+        assert np.abs(got["xk"] - ref["xk"]).max() <= 1e-8 * scale
+        for k in ("iter", "V_shape"):
+            if k in ref:
+                assert np.array_equal(got[k], ref[k]), k
+        for k in ("H", "C", "E", "UMlr", "rhos", "V_colsum_abs"):
+            if k in ref:
+                assert got[k].shape == ref[k].shape, k
+                sc = np.abs(ref[k]).max() + 1e-300
+                assert np.abs(got[k] - ref[k]).max() <= 1e-8 * sc, k
+
+
+def test_fp32_storage_minres_ipB_against_fp64_reference():
+    """BASELINE config 5 shape at test size: fp32 storage vs the fp64 reference, 1e-4 relative"""
+    import krypy_b200 as kp
+    gold = runners.load_golden("shifted_minres_ipB")
+    c = cases.case_inputs("shifted_minres_ipB")
+    ls = kp.linsys.LinearSystem(c["A"], c["b"], dtype=np.float32, **c["ls"])
+    assert ls.dtype == np.float32
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            sol = kp.linsys.Minres(ls, **c["kw"])
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+    got = np.array(sol.resnorms)
+    ref = gold["resnorms"]
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=1e-4)
+    assert sol.xk.dtype == np.float32
+
+
+@pytest.mark.parametrize("ortho", ["cgs", "cgs2", "dmgs"])
+def test_block_gram_schmidt_variants_match_reference_mgs(ortho):
+    """fused block CGS / CGS2 histories agree with the reference's MGS on the sparse
+    configs to the 1e-10 contract"""
+    gold = runners.load_golden("lap2d_gmres30")
+    got = runners.run_product("lap2d_gmres30", ortho=ortho)
+    _check_history(got["resnorms"], gold["resnorms"], rtol=1e-10)
+    gold = runners.load_golden("convdiff_defl_gmres")
+    got = runners.run_product("convdiff_defl_gmres", ortho=ortho)
+    _check_history(got["resnorms"], gold["resnorms"], rtol=1e-10)
+
+
+def test_post_solve_attribute_semantics():
+    """SURVEY 3.6 drop-in traps, checked against the reference's measured behaviour"""
+    import krypy_b200 as kp
+    A = np.diag([1e-3] + list(range(2, 101))).astype(float)
+    b = np.ones(100)
+    ls = kp.linsys.LinearSystem(A, b, self_adjoint=True, positive_definite=True)
+    for cls, it in ((kp.linsys.Cg, 55), (kp.linsys.Minres, 54), (kp.linsys.Gmres, 54)):
+        sol = cls(ls, store_arnoldi=True)
+        assert sol.iter == it
+        assert sol.V.shape == (100, 56) and sol.H.shape == (56, 55) and sol.xk.shape == (100, 1)
+        assert isinstance(sol.resnorms, list) and isinstance(sol.resnorms[1], np.floating)
+    for cls, vs, hs in ((kp.linsys.Cg, (100, 10), (10, 9)), (kp.linsys.Minres, (100, 11), (11, 10)),
+                        (kp.linsys.Gmres, (100, 11), (11, 10))):
+        with pytest.raises(kp.utils.ConvergenceError) as ei:
+            cls(ls, maxiter=10, store_arnoldi=True)
+        s = ei.value.solver
+        assert s.xk is not None and len(s.resnorms) - 1 == 10 and s.iter == 9
+        assert s.V.shape == vs and s.H.shape == hs
+    # zero right hand side
+    z = kp.linsys.Gmres(kp.linsys.LinearSystem(A, np.zeros((100, 1))))
+    assert z.resnorms == [0.0] and np.all(z.xk == 0) and z.xk.shape == (100, 1)
+    # exact initial guess
+    x = np.linalg.solve(A, b).reshape(-1, 1)
+    e = kp.linsys.Gmres(kp.linsys.LinearSystem(A, b.reshape(-1, 1)), x0=x, tol=1e-10)
+    assert len(e.resnorms) == 1 and e.iter == 0
+    np.testing.assert_allclose(e.xk, x)
+    # RestartedGmres surface
+    r = kp.linsys.RestartedGmres(ls, maxiter=20, max_restarts=10)
+    assert r.resnorms[-1] <= 1e-5 and r.xk.shape == (100, 1)
+    with pytest.raises(kp.utils.ConvergenceError):
+        kp.linsys.RestartedGmres(ls, maxiter=5, max_restarts=1)
+    # deflated attributes
+    d = kp.deflation.DeflatedGmres(kp.linsys.LinearSystem(A, b), U=np.eye(100, 2), store_arnoldi=True)
+    n = d.H.shape[1]
+    assert d.C.shape == (2, n) and d.E.shape == (2, 2) and d.B_.shape == (n + 1, 2) and d.UMlr.shape == (2, 1)
+    # final residual is what it claims to be (reference test_linsys.py:189-195)
+    for sol in (kp.linsys.Gmres(ls, tol=1e-9), kp.linsys.Cg(ls, tol=1e-9), kp.linsys.Minres(ls, tol=1e-9)):
+        _, _, rn = ls.get_residual(sol.xk, compute_norm=True)
+        np.testing.assert_almost_equal(sol.resnorms[-1], rn / ls.MMlb_norm, decimal=13)
+
+
+def test_operator_algebra_and_errors():
+    import krypy_b200 as kp
+    u = kp.utils
+    rng = np.random.default_rng(0)
+    A = rng.standard_normal((12, 12)); B = rng.standard_normal((12, 12)); X = rng.standard_normal((12, 3))
+    a, bop = u.MatrixLinearOperator(A), u.MatrixLinearOperator(B)
+    np.testing.assert_allclose((a * bop) * X, A @ B @ X, rtol=1e-12)
+    np.testing.assert_allclose((a + bop) * X, (A + B) @ X, rtol=1e-12)
+    np.testing.assert_allclose((a - bop) * X, (A - B) @ X, rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose((2.5 * a) * X, 2.5 * A @ X, rtol=1e-12)
+    np.testing.assert_allclose((a ** 2) * X, A @ A @ X, rtol=1e-12)
+    np.testing.assert_allclose(a.adj * X, A.T @ X, rtol=1e-12)
+    I = u.IdentityLinearOperator((12, 12))
+    assert (I * a) is a and (a * I) is a
+    assert (a * X[:, :0]).shape == (12, 0)
+    with pytest.raises(TypeError):
+        a * rng.standard_normal((5, 1))
+    with pytest.raises(u.LinearOperatorError):
+        u.get_linearoperator((3, 3), A)
+    with pytest.raises(TypeError):
+        u.get_linearoperator((3, 3), "nope")
+    with pytest.raises(NotImplementedError):
+        kp.linsys.LinearSystem(A.astype(complex), np.ones(12))
+    # inner / norm / qr / Projection properties (reference test_utils.py:157-246)
+    Bip = np.diag(np.linspace(1, 2, 12))
+    np.testing.assert_allclose(u.inner(X, X, ip_B=Bip), X.T @ Bip @ X, rtol=1e-12)
+    np.testing.assert_allclose(u.norm(X[:, [0]]), np.linalg.norm(X[:, 0]), rtol=1e-13)
+    Q, R = u.qr(X, ip_B=Bip)
+    np.testing.assert_allclose(Q.T @ Bip @ Q, np.eye(3), atol=1e-13)
+    np.testing.assert_allclose(Q @ R, X, atol=1e-13)
+    Y = rng.standard_normal((12, 3))
+    for its in (1, 2, 3):
+        P = u.Projection(X, Y, ip_B=Bip, iterations=its)
+        z = rng.standard_normal((12, 2))
+        Pz = P.apply(z)
+        np.testing.assert_allclose(P.apply(Pz), Pz, atol=1e-12)              # P^2 = P
+        np.testing.assert_allclose(Pz + P.apply_complement(z), z, atol=1e-12)
+        np.testing.assert_allclose(u.inner(Y, P.apply_complement(z), ip_B=Bip), 0, atol=1e-12)
+        _, Ya = P.apply(z, return_Ya=True)
+        np.testing.assert_allclose(Ya, u.inner(Y, z, ip_B=Bip), atol=1e-12)
+    Pe = u.Projection(X)
+    np.testing.assert_allclose(X.T @ Pe.apply_complement(z), 0, atol=1e-12)
+
+
+@pytest.mark.parametrize("ortho", ["mgs", "dmgs", "lanczos", "cgs2"])
+@pytest.mark.parametrize("with_M", [False, True])
+@pytest.mark.parametrize("ipB", ["none", "matrix", "callable"])
+def test_arnoldi_relation(ortho, with_M, ipB):
+    """reference test_utils.py:440-542 (assert_arnoldi): first vector, Hessenberg
+    structure, Arnoldi residual and orthogonality"""
+    import krypy_b200 as kp
+    u = kp.utils
+    rng = np.random.default_rng(5)
+    N = 10
+    Bm = np.diag(np.linspace(1, 5, N))
+    sym = ortho == "lanczos"
+    K = rng.standard_normal((N, N))
+    K = K + K.T if sym else K
+    ip_B = {"none": None, "matrix": Bm, "callable": (lambda X, Y: X.T.conj() @ Bm @ Y)}[ipB]
+    Bmat = np.eye(N) if ipB == "none" else Bm
+    M = 2.0 * np.eye(N) if with_M else None
+    A = np.linalg.solve(Bmat, K) if sym else K          # self-adjoint in <.,.>_B when needed
+    v = rng.standard_normal((N, 1))
+    res = u.arnoldi(A, v, maxiter=6, ortho=ortho, M=M, ip_B=ip_B)
+    V, H = res[0], res[1]
+    n = H.shape[1]
+    assert V.shape == (N, n + 1) and H.shape == (n + 1, n)
+    assert np.allclose(np.tril(H, -2), 0)
+    assert np.all(np.diag(H, -1) >= 0)
+    MA = (M @ A) if with_M else A
+    ipM = Bmat if not with_M else np.linalg.inv(M) @ Bmat
+    np.testing.assert_allclose(MA @ V[:, :n], V @ H, atol=1e-12 * np.linalg.norm(MA))
+    np.testing.assert_allclose(V.T @ ipM @ V, np.eye(n + 1), atol=1e-11)
+    if with_M:
+        np.testing.assert_allclose(M @ res[2], V, atol=1e-13)
