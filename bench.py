@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- GMRES iterations/s and HBM GB/s on BASELINE.json's headline config.
+
+Workload (config.workload): C2 = GMRES(30) on the 2-D 5-point Laplacian in CSR,
+n=3162 (N=9,998,244, nnz=49,978,572), fp64, b = default_rng(0).standard_normal.
+A "step" is ONE GMRES(30) restart cycle (30 Arnoldi iterations + the cycle's initial and
+final explicit residual and the solution update), driven through the public
+krypy-compatible API (krypy_b200.linsys.Gmres, x0 = previous cycle's x) exactly as
+RestartedGmres does.
+
+  value : iterations/s with A, b resident in HBM (CUDA events around K cycles, max over ranks)
+  e2e   : same metric through the public API from HOST (pinned) buffers: every step uploads
+          A (rowptr, colidx, vals), b and x0 and downloads x_k inside the timed region
+  roofline : dominant kernel = the fused Gram-Schmidt kernel (kry_orth_fused), algorithmic
+          bytes per launch (2(k+1)+5)*N*8 / CUDA-event time per launch, live
+  cpu_baseline : the oracle (numpy/scipy port of the reference's algorithm) on the host cores
+
+  --impl reference : times the oracle port alone (rank 0 only) on a bounded sample per step.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GRID = 3162
+RESTART = 30
+TOL = 1e-12
+METRIC = "gmres_iterations_per_second"
+UNIT = "iterations/s"
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=10)
+    p.add_argument("--warmup", type=int, default=3)
+    p.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    p.add_argument("--n", type=int, default=N_GRID, help="grid size n (N = n*n); default = config C2")
+    p.add_argument("--ortho", default="cgs", help="cgs (fused block, default) | mgs | dmgs | cgs2")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--cpu-iters", type=int, default=8, help="iterations of the bounded CPU sample")
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy read+write)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------
+class Clocks(object):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.lines = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def stop(self, t0, t1):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, smax, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ts, line in self.lines:
+            if ts < t0 - 0.2 or ts > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                for nm, v in zip(names, f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        if not sm:
+            for ts, line in self.lines[-3:]:
+                f = [x.strip() for x in line.split(",")]
+                try:
+                    sm.append(float(f[1]))
+                    smax = float(f[2])
+                except Exception:
+                    pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": smax,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# CPU reference arm (oracle port of the reference's algorithm)
+# ---------------------------------------------------------------------------------------
+def cpu_cycle(A, b, iters):
+    """one truncated GMRES cycle of the oracle at full N: returns (iterations, seconds, resnorms)"""
+    from oracle import krylov_oracle as ko
+    t = time.perf_counter()
+    try:
+        r = ko.gmres(ko.System(A, b), maxiter=iters, tol=TOL)
+    except ko.OracleConvergenceError as e:
+        r = e.result
+    dt = time.perf_counter() - t
+    return len(r.resnorms) - 1, dt, list(map(float, r.resnorms))
+
+
+def cpu_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        n = [d.get("num_threads", 1) for d in threadpool_info() if d.get("user_api") == "blas"]
+        return max(n) if n else (os.cpu_count() or 1)
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    import numpy as np  # noqa: F401
+    from krypy_b200 import problems
+    n = args.n
+    A = problems.laplace2d(n)
+    b = problems.rhs_normal(n * n)
+    iters = 4          # bounded sample per step: first 4 Arnoldi steps of a GMRES(30) cycle
+    for _ in range(args.warmup):
+        cpu_cycle(A, b, iters)
+    t_tot, it_tot = 0.0, 0
+    for _ in range(args.steps):
+        it, dt, _ = cpu_cycle(A, b, iters)
+        t_tot += dt
+        it_tot += it
+    val = it_tot / t_tot
+    cores = cpu_threads()
+    sample = ("oracle/krylov_oracle.py (numpy/scipy port of krypy's Gmres, same ops and data layout) on "
+              "the full N=%d system; each step = the first %d Arnoldi iterations of one GMRES(30) cycle "
+              "(cheaper than the 30-step average, so this favours the CPU)" % (n * n, iters))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_tot / args.steps,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(args, world),
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def config_dict(args, world):
+    n = args.n
+    return {"workload": "C2: GMRES(30) restart cycles, 2-D 5-point Laplacian CSR, n=%d, N=%d, fp64, "
+                        "b=default_rng(0).standard_normal; one step = one 30-iteration cycle" % (n, n * n),
+            "N": n * n, "restart": RESTART, "tol": TOL, "ortho": args.ortho,
+            "partition": "single GPU" if world == 1 else "row-partitioned over %d GPUs" % world,
+            "l2": "inputs larger than L2 (basis 2.5 GB, A 0.64 GB vs 126 MB L2): no flush needed"}
+
+
+# ---------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import warnings
+    torch.cuda.set_device(local_rank)
+    import krypy_b200 as kp
+    from krypy_b200 import _device, problems
+
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    n = args.n
+    N = n * n
+    ctx = _device.Context.get()
+    warnings.simplefilter("ignore")
+
+    # ---- problem (host) ---------------------------------------------------------------
+    if world == 1:
+        A = problems.laplace2d(n)
+        b = problems.rhs_normal(N)
+        ls = kp.linsys.LinearSystem(A, b)
+        make_solver = lambda x0: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho)
+    else:
+        from krypy_b200 import dist as kdist
+        part = kdist.RowPartition(N, world, rank)
+        A = problems.laplace2d(n, rows=(part.lo, part.hi))
+        b = problems.rhs_normal(N)[part.lo:part.hi]
+        ls = kdist.DistLinearSystem(A, b, part)
+        make_solver = lambda x0: kdist.DistGmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho)
+
+    def cycle(x0):
+        try:
+            sol = make_solver(x0)
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+        return sol
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up ----------------------------------------------------------------------
+    x = None
+    for _ in range(max(args.warmup, 1)):
+        sol = cycle(x)
+        x = sol.__dict__["_xk_dev"].reshape(-1)
+
+    # ---- timed region: value (device-resident inputs) ------------------------------------
+    clocks = Clocks(local_rank)
+    if rank == 0:
+        clocks.start()
+        time.sleep(0.3)
+    timer = _device.KernelTimer()
+    ctx.timer = timer
+    ctx.reset_launch_count()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.time()
+    e0.record()
+    iters = 0
+    hist = []
+    for _ in range(args.steps):
+        sol = cycle(x)
+        x = sol.__dict__["_xk_dev"].reshape(-1)
+        iters += len(sol.resnorms) - 1
+        hist.append(sol.resnorms)
+    e1.record()
+    barrier()
+    t1 = time.time()
+    ms = e0.elapsed_time(e1)
+    ctx.timer = None
+    launches = ctx.launch_count()
+    if dist is not None:
+        tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    clk = clocks.stop(t0, t1) if rank == 0 else None
+    value = iters / (ms * 1e-3)
+
+    # ---- per-kernel roofline from the live CUDA-event brackets ------------------------------
+    peak, peak_src = peaks()
+    summ = timer.summary()
+    roof = None
+    extra = {}
+    nloc = N if world == 1 else (part.hi - part.lo)
+    if "orth" in summ:
+        o = summ["orth"]
+        # algorithmic bytes per launch: Vdot once + Vsub once per pass (nv vectors each), q read twice +
+        # written once per pass, + phase C (read q, write v_next): SURVEY 8d "[2(k+1)+3]Ns + 2Ns"
+        by = 0.0
+        for (nq, nv, passes, algo, has_next) in o["meta"]:
+            by += (passes * (2 * nv + 3) + (2 if has_next else 0)) * nq * 8.0
+        ach = by / (o["ms_total"] * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": "orth_kernel<double,2> (kry_orth_fused, ortho=%s)" % args.ortho,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "peak_source": peak_src, "launches": o["launches"],
+                "avg_launch_ms": o["ms_total"] / max(o["launches"], 1),
+                "algorithmic_bytes_per_launch_avg": by / max(o["launches"], 1),
+                "share_of_step": o["ms_total"] / ms}
+    if "spmv" in summ:
+        s = summ["spmv"]
+        by = sum(nnz * 12.0 + 4.0 * (nr + 1) + 2.0 * nr * 8.0 for (nr, nnz) in s["meta"])
+        ach = by / (s["ms_total"] * 1e-3) / 1e9
+        extra["roofline_spmv"] = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,8> (kry_spmv_csr)",
+                                  "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "launches": s["launches"], "avg_launch_ms": s["ms_total"] / max(s["launches"], 1),
+                                  "share_of_step": s["ms_total"] / ms}
+        if roof is not None:
+            byo = roof["algorithmic_bytes_per_launch_avg"] * roof["launches"]
+            pair = (by + byo) / ((s["ms_total"] + summ["orth"]["ms_total"]) * 1e-3) / 1e9
+            extra["roofline_spmv_plus_orth"] = {"achieved": pair, "unit": "GB/s", "frac_of_measured_peak": pair / peak,
+                                                "frac_of_8TBs_nominal": pair / 8000.0}
+    # whole-iteration algorithmic bytes (383.5*N per iteration at m=30) -> GB/s of the full step
+    extra["whole_step_algorithmic_gbs"] = 383.5 * N * value / 1e9
+
+    # ---- e2e: public API from host buffers, copies inside the timed region --------------------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        e2e = run_e2e(args, kp, torch, A, b, x)
+
+    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        it, dt, rn = cpu_cycle(A, b, args.cpu_iters)
+        cpu = {"value": it / dt, "unit": UNIT, "cores": cpu_threads(), "kind": "port",
+               "sample": "oracle/krylov_oracle.py (numpy/scipy port of krypy.linsys.Gmres, reference data layout) "
+                         "on the full N=%d system: the first %d Arnoldi iterations of one GMRES(30) cycle, %.1f s "
+                         "(cheaper than the 30-step average: favours the CPU)" % (N, it, dt)}
+        # parity of the first cycle's history against the CPU run, same inputs (x0 = None)
+        try:
+            first = kp.linsys.Gmres(ls, maxiter=args.cpu_iters, tol=TOL, ortho=args.ortho)
+        except kp.utils.ConvergenceError as e:
+            first = e.solver
+        a, r = np.array(first.resnorms), np.array(rn)
+        m = min(len(a), len(r))
+        extra["parity_vs_cpu_max_rel"] = float(np.max(np.abs(a[:m] - r[:m]) / r[:m]))
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": config_dict(args, world), "iterations": iters, "clocks": clk,
+            "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+            "final_resnorm": float(hist[-1][-1]),
+        }
+        line.update(extra)
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def run_e2e(args, kp, torch, A, b, x_dev):
+    """Every step: host (pinned) A, b, x0 -> LinearSystem -> one Gmres(30) cycle -> x_k on the host."""
+    import numpy as np
+    import scipy.sparse as sp
+
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+
+    keep = []
+    parts = []
+    for arr in (A.data, A.indices.astype(np.int32), A.indptr.astype(np.int32)):
+        v, t = pin(arr)
+        keep.append(t)
+        parts.append(v)
+    Ah = sp.csr_matrix((parts[0], parts[1], parts[2]), shape=A.shape)
+    Ah.has_sorted_indices = True
+    bh, tb = pin(b)
+    keep.append(tb)
+    xh, tx = pin(x_dev.cpu().numpy())
+    keep.append(tx)
+    h2d = parts[0].nbytes + parts[1].nbytes + parts[2].nbytes + bh.nbytes + xh.nbytes
+    d2h = xh.nbytes
+
+    def step(x0h):
+        ls = kp.linsys.LinearSystem(Ah, bh)
+        try:
+            sol = kp.linsys.Gmres(ls, x0=x0h, maxiter=RESTART, tol=TOL, ortho=args.ortho)
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+        return sol.xk, len(sol.resnorms) - 1       # .xk: device -> host read of the step's result
+
+    xk, _ = step(xh)                                 # warm-up
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    steps = max(2, min(args.steps, 5))
+    e0.record()
+    its = 0
+    for _ in range(steps):
+        xk, it = step(xk)
+        its += it
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    return {"value": its / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": ms / steps,
+            "api": "krypy_b200.linsys.LinearSystem(A_host, b_host) + Gmres(x0=x_host, maxiter=30) per step"}
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

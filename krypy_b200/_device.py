@@ -71,6 +71,31 @@ class CsrDev(object):
         return (self.rowptr.numel() + self.colidx.numel()) * 4 + self.vals.numel() * self.vals.element_size()
 
 
+class KernelTimer(object):
+    """CUDA-event brackets around selected kernel launches (bench.py roofline):
+    events are recorded on the launching stream; ``summary()`` synchronises."""
+
+    def __init__(self):
+        self.events = {}
+
+    def bracket(self, tag, meta, fn):
+        t = torch()
+        e0 = t.cuda.Event(enable_timing=True)
+        e1 = t.cuda.Event(enable_timing=True)
+        e0.record()
+        fn()
+        e1.record()
+        self.events.setdefault(tag, []).append((e0, e1, meta))
+
+    def summary(self):
+        torch().cuda.synchronize()
+        out = {}
+        for tag, lst in self.events.items():
+            ms = [e0.elapsed_time(e1) for (e0, e1, _) in lst]
+            out[tag] = dict(launches=len(lst), ms_total=float(sum(ms)), meta=[m for (_, _, m) in lst], ms=ms)
+        return out
+
+
 class Context(object):
     """One per (process, device): owns the kry_ctx handle and the pinned mailbox."""
 
@@ -106,6 +131,7 @@ class Context(object):
         check(lib.kry_device_info(h, info))
         self.sm_count, self.cc, self.l2_bytes = int(info[0]), int(info[1]), int(info[2])
         self.orth_blocks = int(info[5])
+        self.timer = None          # set to a KernelTimer by bench.py
 
     # ---- stream / sync ------------------------------------------------
     def use_current_stream(self):
@@ -172,6 +198,11 @@ class Context(object):
 
     # ---- operators -------------------------------------------------------
     def spmv(self, A, x, y, w=None, dot_out=None):
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            tm.bracket("spmv", (A.shape[0], A.nnz), lambda: self.spmv(A, x, y, w, dot_out))
+            self.timer = tm
+            return
         check(self.lib.kry_spmv_csr(self.h, code(A.vals), A.shape[0], A.shape[1], A.nnz,
                                     A.rowptr.data_ptr(), A.colidx.data_ptr(), A.vals.data_ptr(),
                                     x.data_ptr(), _p(y), _p(w), _p(dot_out)))
@@ -213,6 +244,13 @@ class Context(object):
 
     def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
                    pre_coef=None, h_ptr=None):
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            tm.bracket("orth", (q.numel(), int(nv) - int(j0), int(passes), int(algo), vnext is not None),
+                       lambda: self.orth_fused(Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec,
+                                               pre_coef, h_ptr))
+            self.timer = tm
+            return
         ld = Vdot.stride(0) if Vdot is not None else 0
         hp = h_ptr if h_ptr is not None else _p(h)
         check(self.lib.kry_orth_fused(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, int(j0), int(nv),

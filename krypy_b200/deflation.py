@@ -170,6 +170,11 @@ class _DeflationMixin(object):
         self._ncols += 1
         return Av
 
+    def _discard_speculative(self):
+        # the look-ahead step of Gmres applied the projector once more than the reference would
+        if self._ncols > 0:
+            self._ncols -= 1
+
     def _get_initial_residual(self, x0):
         """Projected initial residual M P Ml (b - A x0) (krypy/deflation.py:145-159)."""
         ls = self.linear_system

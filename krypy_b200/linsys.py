@@ -654,10 +654,30 @@ class Gmres(_KrylovSolver):
         rcol = ctx.scalars(m + 2)
         mb = ctx.mailbox
         is_lanczos = self.ortho == "lanczos"
+        t = _device.torch()
+        HALF = 8192                          # two mailbox halves: step k uses half k & 1
+        events = (t.cuda.Event(), t.cuda.Event())
+        # Look-ahead: step k+1 is enqueued BEFORE the host waits for step k, so the device
+        # never idles on the host's convergence test.  An Arnoldi step does not depend on the
+        # host's decision; if the loop ends at k the speculative step is simply discarded
+        # (it only touched V[k+2], y[k+1:], cs[2k+2:], which nothing reads afterwards).
+        lookahead = (not self.explicit_residual and ls.exact_solution is None and not is_lanczos
+                     and 2 * m + 5 <= HALF)
+
+        def off_of(k):
+            return (k & 1) * HALF if lookahead else 0
+
+        def launch(k):
+            ar._enqueue(k)                                                 # linsys.py:978
+            ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))         # linsys.py:982-991
+            events[k & 1].record()
+
+        launched = -1
+        k = -1
         while (self.resnorms[-1] > self.tol and ar.iter < ar.maxiter and not ar.invariant):
             k = self.iter = ar.iter
-            ar._enqueue(k)                                                 # linsys.py:978
             if is_lanczos:
+                ar._enqueue(k)
                 # tridiagonal column from the three Lanczos entries
                 ctx.minres_recur(k, ar._lz, ar._lz_st, 1, 16)
                 ctx.sync()
@@ -665,19 +685,34 @@ class Gmres(_KrylovSolver):
                 if k > 0:
                     hcol[k - 1] = mb[16 + 5]
                 hcol[k], hcol[k + 1] = mb[16 + 6], mb[16 + 7]
-                ar._hcol[: k + 2].copy_(_device.torch().from_numpy(hcol))
-            ctx.givens_update(k, ar._hcol, rcol, cs, y, 0)                 # linsys.py:982-991
-            ctx.sync()
-            resid = float(mb[0])
-            hcol = mb[1:k + 3].copy()
-            self.R[: k + 2, k] = mb[k + 3:2 * k + 5]
+                ar._hcol[: k + 2].copy_(t.from_numpy(hcol))
+                ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))
+                events[k & 1].record()
+                launched = k
+            if launched < k:
+                launch(k)
+                launched = k
+            if lookahead and k + 1 < ar.maxiter and launched < k + 1:
+                launch(k + 1)
+                launched = k + 1
+            events[k & 1].synchronize()
+            off = off_of(k)
+            resid = float(mb[off])
+            hcol = mb[off + 1:off + k + 3].copy()
+            self.R[: k + 2, k] = mb[off + k + 3:off + 2 * k + 5]
             if is_lanczos:
                 ar._finish(k, hcol[k:k + 2])
             else:
                 ar._finish(k, hcol)
             self._finalize_iteration(y, resid)                             # linsys.py:993
+        if launched > k:
+            self._discard_speculative()
         if self.__dict__.get("_xk_dev") is None:
             self.xk = self._get_xk(y if ar.iter > 0 else None)
+
+    def _discard_speculative(self):
+        """hook: a look-ahead Arnoldi step was enqueued but not consumed"""
+        pass
 
     def _finalize(self):
         """krypy/linsys.py:999-1006."""

@@ -61,21 +61,21 @@ def case_inputs(name):
         c["kw"] = dict(U=rng.standard_normal((n * n, 5)), maxiter=30, tol=1e-10,
                        store_arnoldi=True)
     elif name == "shifted_minres_ipB":
-        n = 16
+        n = 48      # 30 steps at N=2304: no Ritz value converges, the history is well conditioned
         A, B = problems.shifted_laplace_B(n, sigma=0.3, dtype=np.float32)
         c["A"] = A
         c["b"] = problems.rhs_normal(n * n, dtype=np.float32)
         c["ls"] = dict(ip_B=B, self_adjoint=True)
         c["solver"] = "minres"
-        c["kw"] = dict(tol=1e-5, maxiter=50)
+        c["kw"] = dict(tol=1e-5, maxiter=30)
     elif name == "shifted_minres_ipB_f64":
-        n = 16
+        n = 48
         A, B = problems.shifted_laplace_B(n, sigma=0.3, dtype=np.float64)
         c["A"] = A
         c["b"] = problems.rhs_normal(n * n)
         c["ls"] = dict(ip_B=B, self_adjoint=True)
         c["solver"] = "minres"
-        c["kw"] = dict(tol=1e-9, maxiter=120, store_arnoldi=True)
+        c["kw"] = dict(tol=1e-9, maxiter=30, store_arnoldi=True)
     elif name in ("dense_gmres_M_ipB", "dense_minres_M_ipB", "dense_cg_M_ipB"):
         # preconditioned + non-Euclidean inner product (test_utils.py:355-383 style)
         N = 30

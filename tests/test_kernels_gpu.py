@@ -267,7 +267,7 @@ def test_orth_lanczos_with_P_basis(ctx, dt):
     h_ptr = lz.data_ptr() + 8 * (1 - k)
     ctx.orth_fused(Vd, Pd, k, k + 1, qd, 1, KRY_ORTH_MGS, None, nrm=None, vnext=None,
                    pre_vec=Pd[k - 1], pre_coef=lz, h_ptr=h_ptr)
-    qr, hr, _ = _mgs_ref(Vh.astype(np.float64), Ph.astype(np.float64), q, k, 1,
+    qr, hr, _ = _mgs_ref(Vh[:k + 1].astype(np.float64), Ph[:k + 1].astype(np.float64), q, k, 1,
                          pre=(0.37, Ph[k - 1].astype(np.float64)))
     rt = 1e-12 if dt == np.float64 else 2e-5
     np.testing.assert_allclose(lz.cpu().numpy()[1], hr[k], rtol=rt * 100, atol=rt * 100)
@@ -360,7 +360,7 @@ def test_givens_update_matches_oracle_and_table(ctx):
         ctx.sync()
         got = cs[:2].cpu().numpy()
         np.testing.assert_allclose(got, [c, s], rtol=4e-16, atol=0)
-        np.testing.assert_allclose(rcol[0].item(), r, rtol=4e-16, atol=0)
+        np.testing.assert_allclose(rcol[0].item(), r, rtol=2e-15, atol=0)   # r = c*a + s*b: 2 roundings
 
 
 def test_tri_solve(ctx):
