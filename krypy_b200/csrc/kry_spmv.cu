@@ -1,25 +1,27 @@
 // CSR SpMV for sm_100a.
 //
-// Short-row matrices (stencils: 5/7 nnz per row) use a persistent kernel in
-// which one elected thread stages each 256-row block's contiguous vals[] and
-// colidx[] ranges into shared memory with 1-D TMA bulk copies
-// (cp.async.bulk.shared::cluster.global + mbarrier complete_tx, SASS UBLKCP)
-// through a STAGES-deep ring, so tens of KB per SM are in flight without
-// holding registers.  Consumers then run thread-per-row out of shared memory:
-// for banded matrices the x gathers of neighbouring threads are contiguous
-// (coalesced ld.global.nc), and each row is summed sequentially left to right
-// with separately rounded multiply and add -- the same order and rounding as
-// scipy's csr_matvec, so y is bit-identical to the reference's SpMV in fp64.
+// Short-row matrices (stencils: 5/7 nnz per row) use a persistent, warp-specialised
+// kernel: one producer warp stages each 256-row block's contiguous vals[] and colidx[]
+// ranges into shared memory with 1-D TMA bulk copies (cp.async.bulk.shared::cluster.global
+// + mbarrier complete_tx, SASS UBLKCP) through a STAGES-deep ring (full/empty mbarriers),
+// so tens of KB per SM are in flight without holding registers.  Eight consumer warps run
+// thread-per-row out of shared memory: for banded matrices the x gathers of neighbouring
+// threads are contiguous (coalesced ld.global.nc), the next tile's row pointers are
+// prefetched into registers while the current tile is computed, and each row is summed
+// sequentially left to right with separately rounded multiply and add -- the same order and
+// rounding as scipy's csr_matvec, so y is bit-identical to the reference's SpMV in fp64.
 //
-// Long-row matrices (or unaligned arrays) use a warp-per-row kernel with
-// coalesced direct loads and a shuffle reduction.
+// Long-row matrices (or unaligned arrays) use a warp-per-row kernel with coalesced direct
+// loads and a shuffle reduction.
+#include <stdlib.h>
 #include "kry_common.cuh"
 
 #define KRY_ENTER(ctx)                                                         \
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
     KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
 
-#define SPMV_R 256   // rows per tile == threads per CTA
+#define SPMV_R 256                    // rows per tile == consumer threads per CTA
+#define SPMV_THREADS (SPMV_R + 32)    // 8 consumer warps + 1 producer warp
 
 // ---- mbarrier / bulk-copy PTX ------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -34,6 +36,9 @@ __device__ __forceinline__ void mbar_fence_init() {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
                  : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
@@ -58,12 +63,14 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
         "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+__device__ __forceinline__ void consumer_bar_sync() {   // named barrier 1 over the consumer threads
+    asm volatile("bar.sync 1, %0;" ::"n"(SPMV_R) : "memory");
+}
 
-template <typename T, int CPR>
+template <typename T, int CPR, int STAGES>
 struct SpmvCfg {
     static const int CAP = SPMV_R * CPR + 8;                       // entries per stage (multiple of 4)
     static const int STAGE_BYTES = CAP * (int)(sizeof(T) + sizeof(int));
-    static const int STAGES = (CPR <= 8) ? 4 : 2;
     static const int SMEM_BYTES = 128 + STAGES * STAGE_BYTES;
 };
 
@@ -91,22 +98,33 @@ __device__ __forceinline__ void finish_dot(double acc, double* partials, unsigne
     }
 }
 
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void consumer_bar_sync() {   // named barrier 1 over the 256 consumer threads
-    asm volatile("bar.sync 1, %0;" ::"n"(SPMV_R) : "memory");
+struct TileRows {   // row-pointer values a consumer thread needs for one tile
+    int s, e, a, b;
+};
+
+__device__ __forceinline__ TileRows load_tile_rows(const int* __restrict__ rowptr, long long nrows, long long t,
+                                                   int tid) {
+    TileRows r;
+    const long long r0 = t * SPMV_R;
+    const long long r1 = (r0 + SPMV_R < nrows) ? r0 + SPMV_R : nrows;
+    r.s = __ldg(rowptr + r0);
+    r.e = __ldg(rowptr + r1);
+    const long long row = r0 + tid;
+    if (row < r1) {
+        r.a = __ldg(rowptr + row);
+        r.b = __ldg(rowptr + row + 1);
+    } else {
+        r.a = r.b = 0;
+    }
+    return r;
 }
 
-#define SPMV_THREADS (SPMV_R + 32)   // 8 consumer warps (thread per row) + 1 producer warp
-
-template <typename T, int CPR, bool DOT>
+template <typename T, int CPR, int STAGES, bool DOT>
 __global__ void __launch_bounds__(SPMV_THREADS)
 spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowptr,
                    const int* __restrict__ colidx, const T* __restrict__ vals, const T* __restrict__ x, T* y,
                    const T* __restrict__ w, double* partials, unsigned int* ticket, double* dot_out) {
-    typedef SpmvCfg<T, CPR> Cfg;
-    const int STAGES = Cfg::STAGES;
+    typedef SpmvCfg<T, CPR, STAGES> Cfg;
     const int CAP = Cfg::CAP;
     extern __shared__ __align__(128) unsigned char smem[];
     __shared__ double red_sm[32];
@@ -133,14 +151,23 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
     double dot_acc = 0.0;
     if (tid >= SPMV_R) {
         // ---------------- producer warp: one elected lane drives the TMA ring ----------------
-        if (tid == SPMV_R) {
+        if (tid == SPMV_R && nmine > 0) {
+            long long t = blockIdx.x;
+            long long r0 = t * SPMV_R;
+            long long r1 = (r0 + SPMV_R < nrows) ? r0 + SPMV_R : nrows;
+            int s = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
             for (long long it = 0; it < nmine; ++it) {
+                // prefetch the next tile's extent before blocking on the ring slot
+                int s_n = 0, e_n = 0;
+                if (it + 1 < nmine) {
+                    const long long tn = blockIdx.x + (it + 1) * G;
+                    const long long q0 = tn * SPMV_R;
+                    const long long q1 = (q0 + SPMV_R < nrows) ? q0 + SPMV_R : nrows;
+                    s_n = __ldg(rowptr + q0);
+                    e_n = __ldg(rowptr + q1);
+                }
                 const int st = (int)(it % STAGES);
                 if (it >= STAGES) mbar_wait(&empty[st], (uint32_t)(((it / STAGES) - 1) & 1));
-                const long long t = blockIdx.x + it * G;
-                const long long r0 = t * SPMV_R;
-                const long long r1 = (r0 + SPMV_R < nrows) ? r0 + SPMV_R : nrows;
-                const int s = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
                 const int s_al = s & ~3;
                 const int e_al = (e + 3) & ~3;
                 const int e_bulk = e_al < nnz_al ? e_al : nnz_al;
@@ -154,26 +181,27 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
                 } else {
                     mbar_expect_tx(&full[st], 0u);  // nothing staged: complete the phase at once
                 }
+                s = s_n;
+                e = e_n;
             }
         }
-    } else {
+    } else if (nmine > 0) {
         // ---------------- consumers: thread per row out of shared memory ----------------
+        TileRows cur = load_tile_rows(rowptr, nrows, blockIdx.x, tid);
         for (long long it = 0; it < nmine; ++it) {
             const long long t = blockIdx.x + it * G;
+            // next tile's row pointers: issued now, consumed next iteration
+            TileRows nxt = cur;
+            if (it + 1 < nmine) nxt = load_tile_rows(rowptr, nrows, t + G, tid);
             const int st = (int)(it % STAGES);
             const uint32_t parity = (uint32_t)((it / STAGES) & 1);
             const long long r0 = t * SPMV_R;
             const long long r1 = (r0 + SPMV_R < nrows) ? r0 + SPMV_R : nrows;
-            const int s = __ldg(rowptr + r0), e = __ldg(rowptr + r1);
+            const int s = cur.s, e = cur.e, a = cur.a, b = cur.b;
             const int s_al = s & ~3;
             const int e_al = (e + 3) & ~3;
             const bool staged = (e_al - s_al) <= CAP;
             const long long row = r0 + tid;
-            int a = 0, b = 0;
-            if (row < r1) {
-                a = __ldg(rowptr + row);
-                b = __ldg(rowptr + row + 1);
-            }
             T* sv = reinterpret_cast<T*>(stage_base + (size_t)st * Cfg::STAGE_BYTES);
             int* sc = reinterpret_cast<int*>(stage_base + (size_t)st * Cfg::STAGE_BYTES + (size_t)CAP * sizeof(T));
             double sum = 0.0;
@@ -199,8 +227,16 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
                     sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 2], x2));
                     sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 3], x3));
                 }
-                for (; jj < end; ++jj)
-                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj], (double)__ldg(x + sc[jj])));
+                if (jj < end) {   // 1..3 remaining entries: gather first, then the ordered sum
+                    const int n = end - jj;
+                    const int c0 = sc[jj];
+                    const int c1 = n > 1 ? sc[jj + 1] : c0;
+                    const int c2 = n > 2 ? sc[jj + 2] : c0;
+                    const double x0 = (double)__ldg(x + c0), x1 = (double)__ldg(x + c1), x2 = (double)__ldg(x + c2);
+                    sum = __dadd_rn(sum, __dmul_rn((double)sv[jj], x0));
+                    if (n > 1) sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 1], x1));
+                    if (n > 2) sum = __dadd_rn(sum, __dmul_rn((double)sv[jj + 2], x2));
+                }
             } else {
                 for (int jj = a; jj < b; ++jj)
                     sum = __dadd_rn(sum, __dmul_rn((double)__ldg(vals + jj), (double)__ldg(x + __ldg(colidx + jj))));
@@ -212,6 +248,7 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
             // this warp is done with slot st: let the producer refill it
             __syncwarp();
             if ((tid & 31) == 0) mbar_arrive(&empty[st]);
+            cur = nxt;
         }
     }
     if (DOT) finish_dot(dot_acc, partials, ticket, dot_out, red_sm, &last_flag);
@@ -242,11 +279,21 @@ spmv_warp_kernel(long long nrows, const int* __restrict__ rowptr, const int* __r
     if (DOT) finish_dot(dot_acc, partials, ticket, dot_out, red_sm, &last_flag);
 }
 
-template <typename T, int CPR, bool DOT>
+static int spmv_stage_override() {   // tuning knob: KRY_SPMV_STAGES=2|3|4
+    static int v = -1;
+    if (v < 0) {
+        const char* s = getenv("KRY_SPMV_STAGES");
+        v = s ? atoi(s) : 0;
+        if (v != 2 && v != 3 && v != 4) v = 0;
+    }
+    return v;
+}
+
+template <typename T, int CPR, int STAGES, bool DOT>
 static int launch_staged(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
                          const T* vals, const T* x, T* y, const T* w, double* dot_out) {
-    typedef SpmvCfg<T, CPR> Cfg;
-    auto kern = spmv_staged_kernel<T, CPR, DOT>;
+    typedef SpmvCfg<T, CPR, STAGES> Cfg;
+    auto kern = spmv_staged_kernel<T, CPR, STAGES, DOT>;
     static thread_local int occ[16] = {0};
     int& o = occ[ctx->device & 15];
     if (o == 0) {
@@ -262,9 +309,17 @@ static int launch_staged(kry_ctx* ctx, long long nrows, long long nnz, const int
     int g = (int)(ntiles < cap ? ntiles : cap);
     if (g < 1) g = 1;
     kern<<<g, SPMV_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(nrows, nnz, rowptr, colidx, vals, x, y, w,
-                                                      ctx->d_partials, ctx->d_ticket + 1, dot_out);
+                                                            ctx->d_partials, ctx->d_ticket + 1, dot_out);
     KRY_LAUNCHED(ctx);
     return KRY_OK;
+}
+
+template <typename T, int CPR, bool DOT>
+static int launch_staged_cpr(kry_ctx* ctx, int stages, long long nrows, long long nnz, const int* rowptr,
+                             const int* colidx, const T* vals, const T* x, T* y, const T* w, double* dot_out) {
+    if (stages == 2) return launch_staged<T, CPR, 2, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    if (stages == 4) return launch_staged<T, CPR, 4, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    return launch_staged<T, CPR, 3, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
 }
 
 template <typename T, bool DOT>
@@ -272,9 +327,17 @@ static int spmv_dispatch(kry_ctx* ctx, long long nrows, long long nnz, const int
                          const T* vals, const T* x, T* y, const T* w, double* dot_out) {
     const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
     const bool al = kry_aligned16(vals) && kry_aligned16(colidx);
-    if (al && avg <= 7.5) return launch_staged<T, 8, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
-    if (al && avg <= 15.0) return launch_staged<T, 16, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
-    if (al && avg <= 30.0) return launch_staged<T, 32, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    const int ov = spmv_stage_override();
+    // stage capacity (entries per row) just above the mean row length; a 2-deep ring measured
+    // fastest on B200 (118 us vs 121/133 us for 3/4 stages on config C2: occupancy beats depth)
+    if (al && avg <= 5.5)
+        return launch_staged_cpr<T, 6, DOT>(ctx, ov ? ov : 2, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    if (al && avg <= 7.5)
+        return launch_staged_cpr<T, 8, DOT>(ctx, ov ? ov : 2, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    if (al && avg <= 15.0)
+        return launch_staged_cpr<T, 16, DOT>(ctx, ov ? ov : 2, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
+    if (al && avg <= 30.0)
+        return launch_staged<T, 32, 2, DOT>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out);
     long long need = (nrows * 32 + KRY_THREADS - 1) / KRY_THREADS;
     long long cap = (long long)ctx->sm_count * 8;
     int g = (int)(need < cap ? need : cap);
