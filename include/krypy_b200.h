@@ -158,6 +158,12 @@ int kry_minres_recur(kry_ctx* ctx, int k, double* h3_dev, double* st_dev, int sh
 int kry_minres_update(kry_ctx* ctx, int dtype, long long n, const void* v, void* w0, const void* w1,
                       void* yk, const double* st_dev);
 
+/* c_out[0..d) = R^{-1} Q^H c_in (Q, R: d x d row-major; krypy/utils.py:547-548), the small
+ * transform of the deflation projector when its block dot and block update run as separate
+ * kernels (row-partitioned multi-GPU runs). */
+int kry_small_qr_apply(kry_ctx* ctx, int d, const double* Q_dev, const double* R_dev,
+                       const double* c_in_dev, double* c_out_dev);
+
 /* ---- CG fused update (one streaming kernel) ------------------------------ */
 /* krypy/linsys.py:634-665 with a diagonal (Jacobi) or identity M:
  *   alpha = rho / pAp_dev[0];  yk += alpha p;  r -= alpha Ap;
@@ -169,6 +175,34 @@ int kry_minres_update(kry_ctx* ctx, int dtype, long long n, const void* v, void*
 int kry_cg_update(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk,
                   void* r, void* z, const void* dinv, double rho, const double* pAp_dev,
                   int mailbox_off);
+
+/* ---- multi-GPU exchange over NVLink peer memory (one process per GPU) ------- */
+/* The reference has no distributed path; these entry points carry the
+ * exchange steps of the row-partitioned solve: the remote entries of x that
+ * the local rows of A reference (krypy/utils.py:1593-1594 applied to a row block) and the
+ * global sums behind utils.inner/norm (utils.py:183, 226).
+ * kry_peer_alloc: cudaMalloc'ed, zeroed, IPC-exportable buffer.  kry_ipc_export/open:
+ * 64-byte cudaIpcMemHandle_t passed between ranks by the host (e.g. all_gather_object). */
+int kry_peer_alloc(kry_ctx* ctx, long long bytes, void** out);
+int kry_peer_free(kry_ctx* ctx, void* p);
+int kry_ipc_export(kry_ctx* ctx, const void* p, unsigned char handle[64]);
+int kry_ipc_open(kry_ctx* ctx, const unsigned char handle[64], void** out);
+int kry_ipc_close(kry_ctx* ctx, void* p);
+/* dst[i] = peer_bases_dev[halo_peer[i]][elem_offset + halo_off[i]]  (/ div_dev[0] if given):
+ * P2P loads of the remote vector entries the local CSR rows need. */
+int kry_halo_gather(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev,
+                    long long elem_offset, const int* halo_peer, const int* halo_off,
+                    const double* div_dev, void* dst);
+/* inout_dev[0..n) <- sum over ranks (n <= 64), deterministic rank-order sum, bitwise identical
+ * on every rank.  peer_slots_dev[r]: rank r's slot array (2*world*64 doubles, zeroed);
+ * peer_flags_dev[r]: rank r's flag array (world u64, zeroed).  epoch: strictly increasing,
+ * identical on all ranks, shared by all peer operations.  post/acc_dev as in kry_block_dot
+ * (applied to the global sum). */
+int kry_peer_allreduce(kry_ctx* ctx, int world, int rank, unsigned long long epoch, int n,
+                       double* inout_dev, double* const* peer_slots_dev,
+                       unsigned long long* const* peer_flags_dev, int post, double* acc_dev);
+int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long epoch,
+                     double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 
 #ifdef __cplusplus
 }

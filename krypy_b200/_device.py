@@ -52,7 +52,9 @@ def code(t):
 
 
 def _p(t):
-    return None if t is None else t.data_ptr()
+    if t is None or isinstance(t, int):
+        return t
+    return t.data_ptr()
 
 
 class CsrDev(object):
@@ -132,6 +134,8 @@ class Context(object):
         self.sm_count, self.cc, self.l2_bytes = int(info[0]), int(info[1]), int(info[2])
         self.orth_blocks = int(info[5])
         self.timer = None          # set to a KernelTimer by bench.py
+        self.comm = None           # set to a dist.PeerComm: reductions become global sums
+        self._tmpc = None
 
     # ---- stream / sync ------------------------------------------------
     def use_current_stream(self):
@@ -206,6 +210,8 @@ class Context(object):
         check(self.lib.kry_spmv_csr(self.h, code(A.vals), A.shape[0], A.shape[1], A.nnz,
                                     A.rowptr.data_ptr(), A.colidx.data_ptr(), A.vals.data_ptr(),
                                     x.data_ptr(), _p(y), _p(w), _p(dot_out)))
+        if self.comm is not None and dot_out is not None:
+            self.comm.allreduce(dot_out, 1)
 
     def gemv(self, A, x, y):
         check(self.lib.kry_gemv_dense(self.h, code(A), A.shape[0], A.shape[1], A.data_ptr(),
@@ -230,8 +236,14 @@ class Context(object):
     # ---- tall-skinny -----------------------------------------------------
     def block_dot(self, V, nv, q, out, post=0, acc=None):
         """out[j] = <V[j], q>, j < nv.  V: (>=nv, N) tensor (row stride = ld)."""
+        if self.comm is not None:
+            # row-partitioned run: local partial sums, then the global sum over NVLink peer memory
+            check(self.lib.kry_block_dot(self.h, code(q), q.numel(), _p(V), V.stride(0) if V is not None else 0,
+                                         int(nv), q.data_ptr(), _p(out), 0, None))
+            self.comm.allreduce(out, int(nv), post=int(post), acc=acc)
+            return
         check(self.lib.kry_block_dot(self.h, code(q), q.numel(), _p(V), V.stride(0) if V is not None else 0,
-                                     int(nv), q.data_ptr(), out.data_ptr(), int(post), _p(acc)))
+                                     int(nv), q.data_ptr(), _p(out), int(post), _p(acc)))
 
     def block_axpy(self, V, nv, coef, sign, q):
         check(self.lib.kry_block_axpy(self.h, code(q), q.numel(), V.data_ptr(), V.stride(0), int(nv),
@@ -251,13 +263,71 @@ class Context(object):
                                                pre_coef, h_ptr))
             self.timer = tm
             return
+        if self.comm is not None:
+            return self._orth_split(Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr)
         ld = Vdot.stride(0) if Vdot is not None else 0
         hp = h_ptr if h_ptr is not None else _p(h)
         check(self.lib.kry_orth_fused(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, int(j0), int(nv),
                                       q.data_ptr(), int(passes), int(algo), _p(pre_vec), _p(pre_coef),
                                       hp, _p(nrm), _p(vnext)))
 
+    def _orth_split(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr):
+        """Row-partitioned Gram-Schmidt step: the phases of kry_orth_fused as separate kernels
+        with the global sums (NVLink peer all-reduce) between them.  CGS: one reduction of nv
+        values per pass; MGS: one per basis vector (exact reference order, latency bound)."""
+        from ._lib import KRY_ORTH_CGS
+        if self._tmpc is None:
+            self._tmpc = self.scalars(64)
+        tmp = self._tmpc
+        hbase = h_ptr if h_ptr is not None else h.data_ptr()
+        if pre_vec is not None:
+            self.axpy_dev(pre_coef, -1.0, pre_vec, q)
+        for _ in range(int(passes)):
+            if algo == KRY_ORTH_CGS:
+                j = int(j0)
+                while j < nv:
+                    c = min(64, int(nv) - j)
+                    self.block_dot(Vdot[j:], c, q, tmp, 0, hbase + 8 * j)
+                    self.block_axpy(Vsub[j:], c, tmp, -1.0, q)
+                    j += c
+            else:
+                for j in range(int(j0), int(nv)):
+                    self.block_dot(Vdot[j:], 1, q, tmp, 0, hbase + 8 * j)
+                    self.axpy_dev(tmp, -1.0, Vsub[j], q)
+        if nrm is not None:
+            self.block_dot(q.reshape(1, -1), 1, q, nrm, 1, None)
+            if vnext is not None:
+                self.scale_dev(nrm, 1, 1.0, q, vnext)
+
+    def alloc_basis(self, rows, N, dtype, op=None):
+        """(rows, ld) storage for a vector-major basis.  Row-partitioned runs place it in a
+        peer-mapped region with room for the halo behind each row, so the SpMV exchange reads
+        the peers' basis rows in place (no staging copy)."""
+        ext = getattr(op, "_ext_len", None) if op is not None else None
+        if self.comm is not None and ext is not None:
+            ld = (max(int(ext), int(N)) + 31) // 32 * 32
+            return self.comm.shared_basis(int(rows), ld, dtype)
+        ld = (int(N) + 31) // 32 * 32
+        return self.empty((int(rows), ld), dtype)
+
     def project(self, W, V, d, a, Q, R, iterations, c_first):
+        if self.comm is not None:
+            if self._tmpc is None:
+                self._tmpc = self.scalars(64)
+            if int(d) > 32:
+                raise NotImplementedError("row-partitioned projector supports d <= 32")
+            tmp, tmp2 = self._tmpc[:32], self._tmpc[32:]
+            for it in range(int(iterations)):
+                self.block_dot(W, d, a, tmp, 0, None)
+                if it == 0 and c_first is not None:
+                    c_first[: int(d)].copy_(tmp[: int(d)])
+                coef = tmp
+                if Q is not None:
+                    check(self.lib.kry_small_qr_apply(self.h, int(d), Q.data_ptr(), R.data_ptr(), tmp.data_ptr(),
+                                                      tmp2.data_ptr()))
+                    coef = tmp2
+                self.block_axpy(V, d, coef, -1.0, a)
+            return
         check(self.lib.kry_project(self.h, code(a), a.numel(), W.data_ptr(), W.stride(0), V.data_ptr(),
                                    V.stride(0), int(d), a.data_ptr(), _p(Q), _p(R), int(iterations),
                                    _p(c_first)))

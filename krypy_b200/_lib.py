@@ -59,6 +59,17 @@ PROTOTYPES = {
                                   c_void_p]),
     "kry_cg_update": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_double, c_void_p, c_int]),
+    "kry_peer_alloc": (c_int, [c_void_p, c_ll, ctypes.POINTER(c_void_p)]),
+    "kry_peer_free": (c_int, [c_void_p, c_void_p]),
+    "kry_ipc_export": (c_int, [c_void_p, c_void_p, ctypes.c_char_p]),
+    "kry_ipc_open": (c_int, [c_void_p, ctypes.c_char_p, ctypes.POINTER(c_void_p)]),
+    "kry_ipc_close": (c_int, [c_void_p, c_void_p]),
+    "kry_halo_gather": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p,
+                                c_void_p]),
+    "kry_peer_allreduce": (c_int, [c_void_p, c_int, c_int, ctypes.c_ulonglong, c_int, c_void_p,
+                                   c_void_p, c_void_p, c_int, c_void_p]),
+    "kry_small_qr_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "kry_peer_barrier": (c_int, [c_void_p, c_int, c_int, ctypes.c_ulonglong, c_void_p, c_void_p]),
 }
 
 

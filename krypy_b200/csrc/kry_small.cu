@@ -120,7 +120,42 @@ __global__ void minres_recur_kernel(int k, double* h3, double* st, int shift, do
     }
 }
 
+__global__ void __launch_bounds__(128) small_qr_apply_kernel(int d, const double* Q, const double* R,
+                                                             const double* c_in, double* c_out) {
+    extern __shared__ double sh[];
+    double* c = sh;        // d
+    double* t = sh + d;    // d
+    for (int i = threadIdx.x; i < d; i += blockDim.x) c[i] = c_in[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) {
+        double s = 0.0;
+        for (int j = 0; j < d; ++j) s = fma(Q[(long long)j * d + i], c[j], s);     // Q^H c
+        t[i] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = d - 1; j >= 0; --j) {   // column-oriented back substitution with R
+            const double xj = t[j] / R[(long long)j * d + j];
+            t[j] = xj;
+            for (int i = 0; i < j; ++i) t[i] = fma(-xj, R[(long long)i * d + j], t[i]);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < d; i += blockDim.x) c_out[i] = t[i];
+}
+
 extern "C" {
+
+int kry_small_qr_apply(kry_ctx* ctx, int d, const double* Q_dev, const double* R_dev, const double* c_in_dev,
+                       double* c_out_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(d >= 0 && d <= 2048, "bad d");
+    if (d == 0) return KRY_OK;
+    KRY_REQUIRE(Q_dev && R_dev && c_in_dev && c_out_dev, "NULL argument");
+    small_qr_apply_kernel<<<1, 128, sizeof(double) * 2 * (size_t)d, ctx->stream>>>(d, Q_dev, R_dev, c_in_dev, c_out_dev);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
 
 int kry_givens_update(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev, double* cs_dev, double* y_dev,
                       int mailbox_off) {

@@ -1,0 +1,365 @@
+"""Row-partitioned multi-GPU execution: one process per
+GPU (torchrun), contiguous row blocks of A, b, x and of every basis vector.
+
+The reference has no distributed path; this module adds one *behind the same
+solver classes*: after ``dist.init()`` every inner product / norm computed by the
+device layer becomes a global sum and a ``DistCsrOperator`` applies the row block
+of A to a distributed vector.  Exchange steps run in our own kernels over NVLink
+peer memory (csrc/kry_peer.cu):
+
+  * SpMV exchange  : ``kry_halo_gather`` -- P2P loads of exactly the remote entries
+    of x that the local rows reference, straight out of the peers' basis rows (CUDA
+    IPC mapped), written behind the local segment so the SpMV kernel sees one
+    contiguous extended vector.  For a banded matrix this moves 2*bandwidth values
+    instead of the all-gather's N.
+  * reductions     : ``kry_peer_allreduce`` -- P2P stores of the partial sums into
+    every peer + release/acquire flags, fixed rank-order sum (bitwise identical on
+    all ranks, so the replicated Givens/convergence logic cannot diverge).
+
+``torch.distributed`` is used only at set-up (exchange of IPC handles) and for the
+optional NCCL all-gather comparison path (``KRY_DIST_EXCHANGE=allgather``).
+
+Host-side planning (RowPartition, HaloPlan) is plain numpy and is covered by the
+world_size-2 gloo tests on CPU.
+"""
+import ctypes
+import os
+import weakref
+
+import numpy as np
+
+from . import _device, linsys, utils
+from ._lib import check
+
+__all__ = ["RowPartition", "HaloPlan", "PeerComm", "DistCsrOperator", "DistLinearSystem",
+           "DistGmres", "DistCg", "DistMinres", "init", "shutdown", "local_rows"]
+
+
+def _roundup(x, a):
+    return (x + a - 1) // a * a
+
+
+class RowPartition(object):
+    """Contiguous row blocks of equal size ``block`` (a multiple of 32; the last block may be
+    shorter or empty).  rank r owns rows [r*block, min((r+1)*block, N))."""
+
+    def __init__(self, N, world, rank):
+        self.N, self.world, self.rank = int(N), int(world), int(rank)
+        self.block = _roundup((self.N + self.world - 1) // self.world, 32)
+        self.lo = min(self.rank * self.block, self.N)
+        self.hi = min(self.lo + self.block, self.N)
+        self.nloc = self.hi - self.lo
+
+    def owner(self, cols):
+        return np.asarray(cols) // self.block
+
+    def bounds(self, r):
+        lo = min(r * self.block, self.N)
+        return lo, min(lo + self.block, self.N)
+
+
+def local_rows(A, part):
+    """rows [lo, hi) of a global scipy sparse matrix, global column indices"""
+    return A.tocsr()[part.lo:part.hi, :]
+
+
+class HaloPlan(object):
+    """What a rank needs from its peers to apply its row block (pure numpy).
+
+    ``A_rows``: scipy CSR of shape (nloc, N) with GLOBAL column indices.
+    Produces the local matrix with columns renumbered into the extended vector
+    ``[ x_local (block entries) | halo (nhalo entries) ]`` -- entry order inside each
+    row is unchanged, so the row sums are bitwise those of the global matrix --
+    and, per halo entry, the owning rank and the offset inside that rank's block.
+    """
+
+    def __init__(self, A_rows, part):
+        import scipy.sparse as sp
+        A_rows = sp.csr_matrix(A_rows)
+        assert A_rows.shape == (part.nloc, part.N), (A_rows.shape, part.nloc, part.N)
+        cols = A_rows.indices.astype(np.int64)
+        remote = (cols < part.lo) | (cols >= part.hi)
+        self.halo_cols = np.unique(cols[remote])
+        self.nhalo = int(self.halo_cols.shape[0])
+        owner = part.owner(self.halo_cols)
+        self.halo_peer = owner.astype(np.int32)
+        self.halo_off = (self.halo_cols - owner * part.block).astype(np.int32)
+        self.nloc, self.block = part.nloc, part.block
+        self.ext = part.block + self.nhalo                      # length of the extended vector
+        new_cols = np.where(remote, part.block + np.searchsorted(self.halo_cols, cols), cols - part.lo)
+        self.indptr = A_rows.indptr.astype(np.int32)
+        self.indices = new_cols.astype(np.int32)
+        self.data = A_rows.data
+
+    def local_matrix(self):
+        import scipy.sparse as sp
+        return sp.csr_matrix((self.data, self.indices, self.indptr), shape=(self.nloc, self.ext))
+
+
+def extend_vector(plan, part, x_blocks):
+    """numpy reference of the halo exchange (used by the CPU tests)."""
+    xe = np.zeros(plan.ext, dtype=np.result_type(*[b.dtype for b in x_blocks]))
+    xe[: part.nloc] = x_blocks[part.rank]
+    for i in range(plan.nhalo):
+        xe[part.block + i] = x_blocks[plan.halo_peer[i]][plan.halo_off[i]]
+    return xe
+
+
+# ---------------------------------------------------------------------------------------
+# peer memory
+# ---------------------------------------------------------------------------------------
+class _RawCuda(object):
+    """__cuda_array_interface__ holder so torch can view memory we cudaMalloc'ed."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False),
+                                         "version": 2}
+
+
+class SharedRegion(object):
+    """A cudaMalloc'ed buffer every rank has mapped: base (mine), peer pointer table (device)."""
+
+    def __init__(self, comm, nbytes):
+        t = _device.torch()
+        ctx = comm.ctx
+        self.nbytes = int(nbytes)
+        p = ctypes.c_void_p()
+        check(ctx.lib.kry_peer_alloc(ctx.h, self.nbytes, ctypes.byref(p)))
+        self.base = int(p.value)
+        buf = ctypes.create_string_buffer(64)
+        check(ctx.lib.kry_ipc_export(ctx.h, ctypes.c_void_p(self.base), buf))
+        handles = comm.all_gather_object(bytes(buf.raw))
+        self.peer = []
+        self._opened = []
+        for r, h in enumerate(handles):
+            if r == comm.rank:
+                self.peer.append(self.base)
+            else:
+                q = ctypes.c_void_p()
+                check(ctx.lib.kry_ipc_open(ctx.h, ctypes.c_char_p(h), ctypes.byref(q)))
+                self.peer.append(int(q.value))
+                self._opened.append(int(q.value))
+        self.peer_table = t.tensor(self.peer, dtype=t.int64, device=ctx.device)
+        self.bytes_view = t.as_tensor(_RawCuda(self.base, self.nbytes), device=ctx.device)
+
+    def view(self, dtype):
+        return self.bytes_view.view(dtype)
+
+    def contains(self, ptr, nbytes):
+        return self.base <= ptr and ptr + nbytes <= self.base + self.nbytes
+
+
+class PeerComm(object):
+    """Global sums and barriers over NVLink peer memory + the shared-region pool."""
+
+    def __init__(self, ctx, world, rank):
+        import torch.distributed as td
+        self.ctx, self.world, self.rank = ctx, int(world), int(rank)
+        self._td = td
+        self.epoch = 0
+        self.regions = []
+        self._free = {}
+        self.slots = SharedRegion(self, 2 * self.world * 64 * 8)
+        self.flags = SharedRegion(self, max(self.world, 8) * 8)
+        self.regions = []
+        self.exchange = os.environ.get("KRY_DIST_EXCHANGE", "halo")     # halo | allgather
+        self.reduce = os.environ.get("KRY_DIST_REDUCE", "peer")         # peer | nccl
+        self.barrier_sync()
+
+    def all_gather_object(self, obj):
+        out = [None] * self.world
+        self._td.all_gather_object(out, obj)
+        return out
+
+    def barrier_sync(self):
+        _device.torch().cuda.synchronize()
+        self._td.barrier()
+
+    # -- device-side collectives (stream ordered, no host sync) --
+    def allreduce(self, x, n, post=0, acc=None):
+        """x[0:n] <- global sum (n may exceed 64: chunked); post/acc as kry_block_dot"""
+        ctx = self.ctx
+        if self.reduce == "nccl":
+            t = _device.torch()
+            self._td.all_reduce(x[:n])
+            if post == 1:
+                x[:n].abs_().sqrt_()
+            if acc is not None:
+                a = acc if not isinstance(acc, int) else None
+                if a is None:
+                    raise NotImplementedError("raw accumulator pointer with the NCCL reduction path")
+                a[:n].add_(x[:n])
+            return
+        xp = x if isinstance(x, int) else x.data_ptr()
+        ap = None if acc is None else (acc if isinstance(acc, int) else acc.data_ptr())
+        i = 0
+        while i < n:
+            c = min(64, n - i)
+            self.epoch += 1
+            check(ctx.lib.kry_peer_allreduce(ctx.h, self.world, self.rank, self.epoch, c, xp + 8 * i,
+                                             self.slots.peer_table.data_ptr(), self.flags.peer_table.data_ptr(),
+                                             int(post), None if ap is None else ap + 8 * i))
+            i += c
+
+    def barrier(self):
+        ctx = self.ctx
+        if self.reduce == "nccl":
+            self._td.barrier()
+            return
+        self.epoch += 1
+        check(ctx.lib.kry_peer_barrier(ctx.h, self.world, self.rank, self.epoch,
+                                       self.slots.peer_table.data_ptr(), self.flags.peer_table.data_ptr()))
+
+    # -- shared-region pool (collective: every rank must call in the same order) --
+    def get_region(self, nbytes):
+        nbytes = _roundup(int(nbytes), 512)
+        lst = self._free.get(nbytes)
+        if lst:
+            return lst.pop()
+        reg = SharedRegion(self, nbytes)
+        self.regions.append(reg)
+        return reg
+
+    def release_region(self, reg):
+        self._free.setdefault(reg.nbytes, []).append(reg)
+
+    def find_region(self, ptr, nbytes):
+        for reg in self.regions:
+            if reg.contains(ptr, nbytes):
+                return reg
+        return None
+
+    def shared_basis(self, rows, ld, dtype):
+        """(rows, ld) tensor in a peer-mapped region; the region returns to the pool when the
+        tensor is garbage collected."""
+        es = 8 if dtype == _device.torch().float64 else 4
+        reg = self.get_region(rows * ld * es)
+        ten = reg.view(dtype)[: rows * ld].view(rows, ld)
+        weakref.finalize(ten, self.release_region, reg)
+        return ten
+
+
+_COMM = None
+
+
+def init(world=None, rank=None):
+    """Attach a PeerComm to this process's device context: from now on every reduction of the
+    device layer is a global sum.  Requires an initialised torch.distributed process group."""
+    global _COMM
+    import torch.distributed as td
+    if not td.is_initialized():
+        raise RuntimeError("torch.distributed is not initialised")
+    ctx = _device.Context.get()
+    world = td.get_world_size() if world is None else world
+    rank = td.get_rank() if rank is None else rank
+    if _COMM is None:
+        _COMM = PeerComm(ctx, world, rank)
+        ctx.comm = _COMM
+    return _COMM
+
+
+def shutdown():
+    global _COMM
+    if _COMM is not None:
+        _COMM.ctx.comm = None
+        _COMM = None
+
+
+# ---------------------------------------------------------------------------------------
+# distributed operator
+# ---------------------------------------------------------------------------------------
+class DistCsrOperator(utils._DeviceOperator):
+    """Row block of a global sparse matrix acting on row-partitioned vectors.
+
+    ``shape`` is reported as ``(nloc, nloc)`` so the (local) LinearSystem machinery accepts it;
+    ``N_global`` holds the true dimension."""
+
+    def __init__(self, A_rows, part, comm=None):
+        self.part = part
+        self.comm = comm if comm is not None else _COMM
+        if self.comm is None:
+            raise RuntimeError("call krypy_b200.dist.init() first")
+        self.plan = HaloPlan(A_rows, part)
+        self.N_global = part.N
+        super(DistCsrOperator, self).__init__((part.nloc, part.nloc), A_rows.dtype)
+        self._ext_len = self.plan.ext
+        self._devcache = {}
+        self._xbuf = {}
+        self._napply = 0
+
+    def _dev(self, td):
+        obj = self._devcache.get(td)
+        if obj is None:
+            ctx = self.comm.ctx
+            t = _device.torch()
+            npdt = _device.torch_to_np_dtype(td)
+            pl = self.plan
+            A = _device.CsrDev(t.from_numpy(pl.indptr).to(ctx.device), t.from_numpy(pl.indices).to(ctx.device),
+                               t.from_numpy(np.ascontiguousarray(pl.data, dtype=npdt)).to(ctx.device),
+                               (pl.nloc, pl.ext))
+            hp = t.from_numpy(pl.halo_peer).to(ctx.device)
+            ho = t.from_numpy(pl.halo_off).to(ctx.device)
+            obj = (A, hp, ho)
+            self._devcache[td] = obj
+        return obj
+
+    def _exchange_buffer(self, td):
+        """two alternating peer-mapped staging vectors for inputs that do not live in a shared basis"""
+        key = (td, self._napply & 1)
+        buf = self._xbuf.get(key)
+        if buf is None:
+            buf = self.comm.shared_basis(1, _roundup(self.plan.ext, 32), td)
+            self._xbuf[key] = buf
+        return buf
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        if adj:
+            raise utils.LinearOperatorError("dot_adj undefined for a row-partitioned operator")
+        comm, ctx, pl = self.comm, self.comm.ctx, self.plan
+        A, hp, ho = self._dev(Xd.dtype)
+        k = Xd.shape[0]
+        es = Xd.element_size()
+        if out is None:
+            out = ctx.empty((k, pl.nloc), Xd.dtype)
+        for j in range(k):
+            x = Xd[j]
+            reg = comm.find_region(x.data_ptr(), pl.ext * es)
+            if reg is None:
+                buf = self._exchange_buffer(Xd.dtype)
+                self._napply += 1
+                ctx.axpby(1.0, x, 0.0, None, buf[0][: pl.nloc])
+                x = buf[0]
+                reg = comm.find_region(x.data_ptr(), pl.ext * es)
+            off = (x.data_ptr() - reg.base) // es
+            xext = reg.view(Xd.dtype)[off: off + pl.ext]
+            comm.barrier()                           # every rank's segment of this vector is complete
+            if pl.nhalo:
+                check(ctx.lib.kry_halo_gather(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(), off,
+                                              hp.data_ptr(), ho.data_ptr(), None,
+                                              xext.data_ptr() + pl.block * es))
+            ctx.spmv(A, xext, out[j])
+        return out
+
+
+class DistLinearSystem(linsys.LinearSystem):
+    """LinearSystem over a row partition: ``A_rows`` are this rank's rows (scipy CSR, global
+    column indices), ``b`` this rank's segment of the right-hand side."""
+
+    def __init__(self, A_rows, b, part, **kwargs):
+        comm = init()
+        op = A_rows if isinstance(A_rows, DistCsrOperator) else DistCsrOperator(A_rows, part, comm)
+        self.part = part
+        self.N_global = part.N
+        super(DistLinearSystem, self).__init__(op, b, **kwargs)
+
+
+class DistGmres(linsys.Gmres):
+    pass
+
+
+class DistCg(linsys.Cg):
+    pass
+
+
+class DistMinres(linsys.Minres):
+    pass

@@ -244,7 +244,8 @@ class _KrylovSolver(object):
         self._ctx = ctx = _ctx()
         ctx.use_current_stream()
         N = ls.N
-        self.maxiter = N if maxiter is None else maxiter
+        # (row-partitioned runs: N is the local length, the default maxiter the global dimension)
+        self.maxiter = getattr(ls, "N_global", N) if maxiter is None else maxiter
         self.explicit_residual = explicit_residual
         self.store_arnoldi = store_arnoldi
         self.tol = tol
@@ -425,7 +426,8 @@ class Cg(_KrylovSolver):
         M_is_id = isinstance(ls.M, utils.IdentityLinearOperator)
         Mdiag = _diag_of(ls.M)
         euclid = utils._is_identity_ip(ls.ip_B)
-        fast = euclid and (M_is_id or Mdiag is not None)
+        # (the fused update publishes a LOCAL rho: row-partitioned runs take the general path)
+        fast = euclid and (M_is_id or Mdiag is not None) and ctx.comm is None
         z = r if M_is_id else MMlr0d.clone()       # MMlrk (aliases Mlrk when M is the identity)
         dinv = Mdiag._dev(td) if (fast and Mdiag is not None) else None
         p = MMlr0d.clone()

@@ -1131,6 +1131,13 @@ class Projection(object):
 # --------------------------------------------------------------------------
 # Arnoldi / Lanczos -- krypy/utils.py:854-1081
 # --------------------------------------------------------------------------
+def _rightmost_factor(op):
+    """the factor of an operator product that is applied to the basis vector first"""
+    while isinstance(op, _ProductLinearOperator):
+        op = op.args[1]
+    return op
+
+
 _ORTHO = {
     # name: (kernel algorithm, passes)
     "mgs": (KRY_ORTH_MGS, 1),        # utils.py:923-926: reorthos = 0
@@ -1186,12 +1193,12 @@ class Arnoldi(object):
         self.iter = 0
         self.invariant = False
         m1 = self.maxiter + 1
-        ld = self._ld = (N + 31) // 32 * 32
-        self._Vs = ctx.empty((m1, ld), td)
+        self._Vs = ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A))
+        self._ld = self._Vs.stride(0)
         self._Vd = self._Vs[:, :N]
         self._Pd = None
         if self.M is not None:
-            self._Ps = ctx.empty((m1, ld), td)
+            self._Ps = ctx.alloc_basis(m1, N, td)
             self._Pd = self._Ps[:, :N]
         # small quantities are always >= fp64 on the device path (also in fp32 storage mode)
         self.H = numpy.zeros((self.maxiter + 1, self.maxiter), dtype=_common_type([self.dtype, numpy.float64]))

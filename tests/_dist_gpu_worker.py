@@ -1,0 +1,109 @@
+"""N-rank worker (NCCL for set-up, NVLink peer kernels for the exchange): row-partitioned
+solves against the oracle run on the undistributed system."""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def main():
+    lr = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(lr)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    rank, world = dist.get_rank(), dist.get_world_size()
+    import krypy_b200 as kp
+    from krypy_b200 import dist as kd, problems, _device
+    from oracle import krylov_oracle as ko
+    warnings.simplefilter("ignore")
+    comm = kd.init()
+    ctx = _device.Context.get()
+
+    # ---- peer all-reduce / barrier ---------------------------------------------------------
+    for n in (1, 5, 64, 100):
+        x = torch.arange(n, dtype=torch.float64, device="cuda") * (rank + 1) + 0.25 * rank
+        acc = torch.ones(n, dtype=torch.float64, device="cuda")
+        comm.allreduce(x, n, post=0, acc=acc)
+        ref = sum(np.arange(n) * (r + 1) + 0.25 * r for r in range(world))
+        assert np.allclose(x.cpu().numpy(), ref, rtol=1e-15), (n, rank)
+        assert np.allclose(acc.cpu().numpy(), 1 + ref, rtol=1e-15)
+    for _ in range(50):
+        comm.barrier()
+    torch.cuda.synchronize()
+
+    # ---- distributed SpMV (halo gather over peer memory) --------------------------------------
+    for A in (problems.laplace2d(37), problems.convdiff2d(23), problems.poisson3d(9)):
+        N = A.shape[0]
+        part = kd.RowPartition(N, world, rank)
+        op = kd.DistCsrOperator(kd.local_rows(A, part), part)
+        x = np.random.default_rng(3).standard_normal(N)
+        xd = ctx.to_block(x[part.lo:part.hi], torch.float64)
+        for rep in range(3):                       # staging buffers alternate
+            yd = op._apply_dev(xd)
+            assert np.array_equal(ctx.to_numpy(yd)[:, 0], (A @ x)[part.lo:part.hi]), rank
+
+    # ---- solvers: histories vs the oracle on the global system ---------------------------------
+    def check(got, ref, rtol=1e-10):
+        got, ref = np.array(got), np.array(ref)
+        assert got.shape == ref.shape, (got.shape, ref.shape)
+        assert np.all(np.abs(got - ref) <= rtol * np.abs(ref) + 1e-13), np.max(np.abs(got - ref) / ref)
+
+    n = 40
+    A = problems.laplace2d(n)
+    N = n * n
+    b = problems.rhs_normal(N)
+    part = kd.RowPartition(N, world, rank)
+    ls = kd.DistLinearSystem(kd.local_rows(A, part), b[part.lo:part.hi], part)
+    for ortho in ("cgs", "mgs", "cgs2"):
+        try:
+            sol = kp.linsys.RestartedGmres(ls, maxiter=20, max_restarts=2, tol=1e-12, ortho=ortho)
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+        try:
+            ref = ko.restarted_gmres(ko.System(A, b), maxiter=20, max_restarts=2, tol=1e-12)
+        except ko.OracleConvergenceError as e:
+            ref = e.result
+        check(sol.resnorms, ref.resnorms)
+        assert np.abs(sol.xk[:, 0] - ref.xk[part.lo:part.hi, 0]).max() < 1e-9 * np.abs(ref.xk).max()
+
+    A = problems.poisson3d(12)
+    N = A.shape[0]
+    b = problems.rhs_normal(N)
+    part = kd.RowPartition(N, world, rank)
+    Mj = problems.jacobi_csr(A)
+    ls = kd.DistLinearSystem(kd.local_rows(A, part), b[part.lo:part.hi], part,
+                             M=Mj[part.lo:part.hi, part.lo:part.hi], self_adjoint=True, positive_definite=True)
+    sol = kp.linsys.Cg(ls, tol=1e-8, maxiter=200)
+    ref = ko.cg(ko.System(A, b, M=Mj), tol=1e-8, maxiter=200)
+    check(sol.resnorms, ref.resnorms, rtol=1e-9)
+
+    A, B = problems.shifted_laplace_B(48, sigma=0.3, dtype=np.float64)
+    N = A.shape[0]
+    b = problems.rhs_normal(N)
+    part = kd.RowPartition(N, world, rank)
+    ls = kd.DistLinearSystem(kd.local_rows(A, part), b[part.lo:part.hi], part,
+                             ip_B=B[part.lo:part.hi, part.lo:part.hi], self_adjoint=True)
+    try:
+        sol = kp.linsys.Minres(ls, tol=1e-9, maxiter=30)
+    except kp.utils.ConvergenceError as e:
+        sol = e.solver
+    try:
+        ref = ko.minres(ko.System(A, b, B=B), tol=1e-9, maxiter=30)
+    except ko.OracleConvergenceError as e:
+        ref = e.result
+    check(sol.resnorms, ref.resnorms)
+
+    torch.cuda.synchronize()
+    dist.barrier()
+    dist.destroy_process_group()
+    print("rank %d ok" % rank)
+
+
+if __name__ == "__main__":
+    main()

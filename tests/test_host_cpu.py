@@ -1,0 +1,115 @@
+"""CPU-only tests: C-ABI surface (library loads, exports every declared symbol), host logic
+that needs no kernel launch, and the world_size-2 gloo run of the row-partition planning."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from krypy_b200 import _lib
+    lib = _lib.load()
+    hdr = open(os.path.join(ROOT, "include", "krypy_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(kry_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 30
+    for name in declared:
+        assert hasattr(lib, name), "library does not export %s" % name
+    # and the ctypes prototypes cover exactly the header
+    assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
+    assert lib.kry_version() == 1
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import krypy_b200 as kp
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kp.gmres(np.eye(4), np.ones(4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        kp.linsys.LinearSystem(np.eye(4), np.ones(4))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "krypy_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "oracle" not in src.replace("no CPU fallback", ""), fn
+
+
+def test_problem_generators_match_kron_definitions():
+    import scipy.sparse as sp
+    from krypy_b200 import problems
+    n = 7
+    I = sp.identity(n)
+    T = sp.diags([-1, 2, -1], [-1, 0, 1], shape=(n, n))
+    L = (sp.kron(I, T) + sp.kron(T, I)).tocsr()
+    assert abs(problems.laplace2d(n) - L).max() == 0
+    c = 0.1
+    C = c * sp.diags([-1, 0, 1], [-1, 0, 1], shape=(n, n))
+    CD = (sp.kron(I, T + C) + sp.kron(T + 0.5 * C, I)).tocsr()
+    assert abs(problems.convdiff2d(n, c) - CD).max() < 1e-15
+    L3 = (sp.kron(sp.kron(I, I), T) + sp.kron(sp.kron(I, T), I) + sp.kron(sp.kron(T, I), I)).tocsr()
+    assert abs(problems.poisson3d(n) - L3).max() == 0
+    A, B = problems.shifted_laplace_B(n, sigma=0.3, dtype=np.float64)
+    K = (L - 0.3 * sp.identity(n * n)).toarray()
+    assert np.allclose(B.toarray() @ A.toarray(), K)                 # A = B^-1 (L - sigma I)
+    for M in (problems.laplace2d(n), problems.poisson3d(4), problems.convdiff2d(n)):
+        assert M.indices.dtype == np.int32 and M.has_sorted_indices
+    # row blocks with global column indices
+    assert abs(problems.laplace2d(n, rows=(10, 30)) - L[10:30]).max() == 0
+
+
+def test_host_operator_dispatch_and_dtype_rules():
+    import scipy.sparse as sp
+    from krypy_b200 import utils as u
+    A = np.arange(9.0).reshape(3, 3)
+    assert isinstance(u.get_linearoperator((3, 3), A), u.MatrixLinearOperator)
+    assert isinstance(u.get_linearoperator((3, 3), None), u.IdentityLinearOperator)
+    assert isinstance(u.get_linearoperator((3, 3), sp.diags([1.0, 2.0, 3.0]).tocsr()), u.DiagonalLinearOperator)
+    assert isinstance(u.get_linearoperator((3, 3), sp.csr_array(A)), u.MatrixLinearOperator)   # F7 superset
+    with pytest.raises(TypeError):
+        u.get_linearoperator((3, 3), "nope")
+    with pytest.raises(u.LinearOperatorError):
+        u.get_linearoperator((4, 4), A)
+    op = u.MatrixLinearOperator(A)
+    I = u.IdentityLinearOperator((3, 3))
+    assert (I * op) is op and (op * I) is op                         # utils.py:1409-1412
+    assert isinstance(op * op, u._ProductLinearOperator) and isinstance(2 * op, u._ScaledLinearOperator)
+    assert u.find_common_dtype(op, I, np.ones(3, dtype=np.float32)) == np.float64   # F3
+    assert u.find_common_dtype(None, "x") == np.float64
+    flat, (x,) = u.shape_vecs(np.ones(3))
+    assert flat and x.shape == (3, 1)
+    g = u.Givens(np.array([[3.0], [-4.0]]))
+    assert (g.c, g.s, g.r) == (-0.6, 0.8, -5.0)
+    g = u.Givens(np.array([[0.0], [0.0]]))
+    assert (g.c, g.s, g.r) == (1.0, 0.0, 0.0)
+    with pytest.raises(NotImplementedError):
+        u._compute_dtype(np.complex128)
+
+
+def test_givens_host_twin_matches_reference_table():
+    import runners
+    from krypy_b200 import utils as u
+    tab = runners.load_golden("givens_table")["table"]
+    for a, b, c, s, r in tab:
+        g = u.Givens(np.array([[a], [b]]))
+        np.testing.assert_allclose([g.c, g.s, g.r], [c, s, r], rtol=2e-15, atol=0)
+
+
+def test_row_partition_planning_world2_gloo():
+    env = dict(os.environ)
+    env["OMP_NUM_THREADS"] = "1"
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+           "--master-addr", "127.0.0.1", "--master-port", "29611",
+           os.path.join(ROOT, "tests", "_dist_worker.py")]
+    out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=240)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    assert "rank 0 ok" in out.stdout and "rank 1 ok" in out.stdout
