@@ -195,13 +195,14 @@ int kry_halo_gather(kry_ctx* ctx, int dtype, long long nhalo, const void* const*
                     const double* div_dev, void* dst);
 /* inout_dev[0..n) <- sum over ranks (n <= 64), deterministic rank-order sum, bitwise identical
  * on every rank.  peer_slots_dev[r]: rank r's slot array (2*world*64 doubles, zeroed);
- * peer_flags_dev[r]: rank r's flag array (world u64, zeroed).  epoch: strictly increasing,
- * identical on all ranks, shared by all peer operations.  post/acc_dev as in kry_block_dot
+ * peer_flags_dev[r]: rank r's flag array (world u64, zeroed).  epoch_dev: this rank's operation
+ * counter in device memory (zeroed at set-up, incremented by every peer operation, so the
+ * launch arguments are replayable from a CUDA graph); all ranks issue the same sequence.  post/acc_dev as in kry_block_dot
  * (applied to the global sum). */
-int kry_peer_allreduce(kry_ctx* ctx, int world, int rank, unsigned long long epoch, int n,
+int kry_peer_allreduce(kry_ctx* ctx, int world, int rank, unsigned long long* epoch_dev, int n,
                        double* inout_dev, double* const* peer_slots_dev,
                        unsigned long long* const* peer_flags_dev, int post, double* acc_dev);
-int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long epoch,
+int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long* epoch_dev,
                      double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 
 #ifdef __cplusplus

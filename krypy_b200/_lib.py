@@ -66,10 +66,10 @@ PROTOTYPES = {
     "kry_ipc_close": (c_int, [c_void_p, c_void_p]),
     "kry_halo_gather": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p,
                                 c_void_p]),
-    "kry_peer_allreduce": (c_int, [c_void_p, c_int, c_int, ctypes.c_ulonglong, c_int, c_void_p,
+    "kry_peer_allreduce": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p]),
     "kry_small_qr_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "kry_peer_barrier": (c_int, [c_void_p, c_int, c_int, ctypes.c_ulonglong, c_void_p, c_void_p]),
+    "kry_peer_barrier": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
 }
 
 

@@ -41,10 +41,14 @@ __device__ __forceinline__ double ld_volatile_f64(const double* p) {
 
 // slots layout on every rank: [2 parities][world][PEER_SLOT] doubles; flags: [world] u64
 __global__ void __launch_bounds__(128)
-peer_allreduce_kernel(int world, int rank, unsigned long long epoch, int n, double* inout,
+peer_allreduce_kernel(int world, int rank, unsigned long long* epoch_dev, int n, double* inout,
                       double* const* peer_slots, unsigned long long* const* peer_flags, int post, double* acc) {
     __shared__ int timed_out;
     const int tid = threadIdx.x;
+    // the operation counter lives in device memory (one increment per peer operation, in stream
+    // order, identical on every rank): the launch arguments never change, so the iteration can
+    // be replayed from a CUDA graph
+    const unsigned long long epoch = *epoch_dev + 1ull;
     if (tid == 0) timed_out = 0;
     __syncthreads();
     const size_t par = (size_t)(epoch & 1ull) * (size_t)world * PEER_SLOT;
@@ -80,6 +84,7 @@ peer_allreduce_kernel(int world, int rank, unsigned long long epoch, int n, doub
         inout[i] = s;
         if (acc) acc[i] += s;
     }
+    if (tid == 0) *epoch_dev = epoch;
 }
 
 template <typename T>
@@ -162,23 +167,23 @@ int kry_halo_gather(kry_ctx* ctx, int dtype, long long nhalo, const void* const*
     return KRY_OK;
 }
 
-int kry_peer_allreduce(kry_ctx* ctx, int world, int rank, unsigned long long epoch, int n, double* inout_dev,
+int kry_peer_allreduce(kry_ctx* ctx, int world, int rank, unsigned long long* epoch_dev, int n, double* inout_dev,
                        double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev, int post,
                        double* acc_dev) {
     KRY_ENTER(ctx);
     KRY_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "bad world/rank");
     KRY_REQUIRE(n >= 0 && n <= PEER_SLOT, "n must be <= 64");
-    KRY_REQUIRE(epoch > 0, "epoch must be positive and strictly increasing");
+    KRY_REQUIRE(epoch_dev != nullptr, "epoch_dev is NULL");
     KRY_REQUIRE(peer_slots_dev && peer_flags_dev && (n == 0 || inout_dev), "NULL argument");
-    peer_allreduce_kernel<<<1, 128, 0, ctx->stream>>>(world, rank, epoch, n, inout_dev, peer_slots_dev,
+    peer_allreduce_kernel<<<1, 128, 0, ctx->stream>>>(world, rank, epoch_dev, n, inout_dev, peer_slots_dev,
                                                       peer_flags_dev, post, acc_dev);
     KRY_LAUNCHED(ctx);
     return KRY_OK;
 }
 
-int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long epoch, double* const* peer_slots_dev,
-                     unsigned long long* const* peer_flags_dev) {
-    return kry_peer_allreduce(ctx, world, rank, epoch, 0, nullptr, peer_slots_dev, peer_flags_dev, 0, nullptr);
+int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long* epoch_dev,
+                     double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev) {
+    return kry_peer_allreduce(ctx, world, rank, epoch_dev, 0, nullptr, peer_slots_dev, peer_flags_dev, 0, nullptr);
 }
 
 }  // extern "C"

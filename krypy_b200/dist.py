@@ -156,7 +156,7 @@ class PeerComm(object):
         import torch.distributed as td
         self.ctx, self.world, self.rank = ctx, int(world), int(rank)
         self._td = td
-        self.epoch = 0
+        self.epoch_dev = _device.torch().zeros(1, dtype=_device.torch().int64, device=ctx.device)
         self.regions = []
         self._free = {}
         self.slots = SharedRegion(self, 2 * self.world * 64 * 8)
@@ -195,8 +195,7 @@ class PeerComm(object):
         i = 0
         while i < n:
             c = min(64, n - i)
-            self.epoch += 1
-            check(ctx.lib.kry_peer_allreduce(ctx.h, self.world, self.rank, self.epoch, c, xp + 8 * i,
+            check(ctx.lib.kry_peer_allreduce(ctx.h, self.world, self.rank, self.epoch_dev.data_ptr(), c, xp + 8 * i,
                                              self.slots.peer_table.data_ptr(), self.flags.peer_table.data_ptr(),
                                              int(post), None if ap is None else ap + 8 * i))
             i += c
@@ -206,8 +205,7 @@ class PeerComm(object):
         if self.reduce == "nccl":
             self._td.barrier()
             return
-        self.epoch += 1
-        check(ctx.lib.kry_peer_barrier(ctx.h, self.world, self.rank, self.epoch,
+        check(ctx.lib.kry_peer_barrier(ctx.h, self.world, self.rank, self.epoch_dev.data_ptr(),
                                        self.slots.peer_table.data_ptr(), self.flags.peer_table.data_ptr()))
 
     # -- shared-region pool (collective: every rank must call in the same order) --

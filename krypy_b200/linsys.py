@@ -598,8 +598,9 @@ class Gmres(_KrylovSolver):
     and the block variants 'cgs' / 'cgs2' (see utils.Arnoldi).
     """
 
-    def __init__(self, linear_system, ortho="mgs", **kwargs):
+    def __init__(self, linear_system, ortho="mgs", _workspace=None, **kwargs):
         self.ortho = ortho
+        self._ws = _workspace
         super(Gmres, self).__init__(linear_system, **kwargs)
 
     def __repr__(self):
@@ -647,13 +648,27 @@ class Gmres(_KrylovSolver):
         ls = self.linear_system
         self.arnoldi = ar = utils.Arnoldi(
             self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
-            Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype)
+            Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype,
+            _workspace=self._ws)
         m = self.maxiter
+        ws = self._ws
         self.R = numpy.zeros([m + 1, m], dtype=utils._common_type([self.dtype, numpy.float64]))
-        self._y_dev = y = ctx.scalars(m + 2)
+        if ws is not None:
+            self._y_dev = y = ws.tensor("y", (m + 2,), lambda: ctx.scalars(m + 2))
+            cs = ws.tensor("cs", (2 * m + 2,), lambda: ctx.scalars(2 * m + 2))
+            rcol = ws.tensor("rcol", (m + 2,), lambda: ctx.scalars(m + 2))
+            y.zero_()
+        else:
+            self._y_dev = y = ctx.scalars(m + 2)
+            cs = ctx.scalars(2 * m + 2)
+            rcol = ctx.scalars(m + 2)
         y[0:1].fill_(float(self.MMlr0_norm))                               # linsys.py:969
-        cs = ctx.scalars(2 * m + 2)
-        rcol = ctx.scalars(m + 2)
+        # CUDA graphs: from the second cycle over the same workspace on, step k is one graph launch
+        use_graphs = (ws is not None and type(self) is Gmres and ws.graphs_enabled(ctx)
+                      and self.ortho != "lanczos")
+        ws_warm = ws is not None and ws.uses >= 1      # buffers and lazy kernel set-up exist already
+        if ws is not None:
+            ws.uses += 1
         mb = ctx.mailbox
         is_lanczos = self.ortho == "lanczos"
         t = _device.torch()
@@ -670,8 +685,20 @@ class Gmres(_KrylovSolver):
             return (k & 1) * HALF if lookahead else 0
 
         def launch(k):
-            ar._enqueue(k)                                                 # linsys.py:978
-            ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))         # linsys.py:982-991
+            g = ws.graphs.get(k) if use_graphs else None
+            if g is None and use_graphs and ws_warm:
+                g = t.cuda.CUDAGraph()
+                with t.cuda.graph(g):
+                    ctx.use_current_stream()
+                    ar._enqueue(k)
+                    ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))
+                ctx.use_current_stream()
+                ws.graphs[k] = g
+            if g is not None:
+                g.replay()
+            else:
+                ar._enqueue(k)                                             # linsys.py:978
+                ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))     # linsys.py:982-991
             events[k & 1].record()
 
         launched = -1
@@ -744,6 +771,8 @@ class _RestartedSolver(object):
         tol = None
         restart = 0
         xk_dev = None
+        if Solver is Gmres and "_workspace" not in kwargs:
+            kwargs["_workspace"] = utils.SolverWorkspace()
         while restart == 0 or (self.resnorms[-1] > tol and restart <= max_restarts):
             try:
                 if xk_dev is not None:

@@ -1149,6 +1149,37 @@ _ORTHO = {
 _CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
 
 
+class SolverWorkspace(object):
+    """Device buffers (and the CUDA graphs recorded over them) that persist across the restart
+    cycles of one restarted solve.  The reference re-allocates everything per cycle
+    (linsys.py:1046-1051); keeping the buffers makes every Arnoldi step's launch sequence
+    identical from cycle to cycle, so step k is captured once into a CUDA graph and replayed
+    with a single launch afterwards (the host-bound regime of the multi-GPU configurations)."""
+
+    def __init__(self, graphs=None):
+        import os
+        self.bufs = {}
+        self.graphs = {}
+        self.uses = 0
+        if graphs is None:
+            graphs = os.environ.get("KRY_GRAPHS", "auto")
+        self.graph_mode = graphs          # "auto" (row-partitioned runs only) | "on" | "off"
+
+    def tensor(self, name, key, factory):
+        k = (name,) + tuple(key)
+        t = self.bufs.get(k)
+        if t is None:
+            t = self.bufs[k] = factory()
+        return t
+
+    def graphs_enabled(self, ctx):
+        if ctx.timer is not None or self.graph_mode == "off":
+            return False
+        if self.graph_mode == "on":
+            return True
+        return ctx.comm is not None
+
+
 class Arnoldi(object):
     """krypy/utils.py:854-1074 with the basis resident in HBM.
 
@@ -1166,8 +1197,9 @@ class Arnoldi(object):
     """
 
     def __init__(self, A, v, maxiter=None, ortho="mgs", M=None, Mv=None, Mv_norm=None, ip_B=None,
-                 dtype=None):
+                 dtype=None, _workspace=None):
         ctx = self._ctx = _ctx()
+        ws = self._ws = _workspace
         t = _device.torch()
         v_dev_in = _is_dev(v)
         N = v.shape[1] if v_dev_in else v.shape[0]
@@ -1193,7 +1225,10 @@ class Arnoldi(object):
         self.iter = 0
         self.invariant = False
         m1 = self.maxiter + 1
-        self._Vs = ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A))
+        if ws is not None:
+            self._Vs = ws.tensor("V", (m1, N, td), lambda: ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A)))
+        else:
+            self._Vs = ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A))
         self._ld = self._Vs.stride(0)
         self._Vd = self._Vs[:, :N]
         self._Pd = None
@@ -1203,13 +1238,24 @@ class Arnoldi(object):
         # small quantities are always >= fp64 on the device path (also in fp32 storage mode)
         self.H = numpy.zeros((self.maxiter + 1, self.maxiter), dtype=_common_type([self.dtype, numpy.float64]))
         self._euclid = _is_identity_ip(ip_B)
-        self._q = ctx.empty((1, N), td)
+        if ws is not None:
+            # buffers persist across restart cycles so that a step's launch arguments are stable
+            # (CUDA-graph replay); everything that must start from zero is re-zeroed here
+            self._q = ws.tensor("q", (1, N, td), lambda: ctx.empty((1, N), td))
+            self._hcol_store = ws.tensor("hcol", (self.maxiter + 10,), lambda: ctx.scalars(self.maxiter + 2 + 8))
+            self._tmp = ws.tensor("tmp", (4,), lambda: ctx.scalars(4))
+            self._lz = ws.tensor("lz", (3,), lambda: ctx.scalars(3))
+            self._lz_st = ws.tensor("lz_st", (16,), lambda: ctx.scalars(16))
+            for buf in (self._hcol_store, self._tmp, self._lz, self._lz_st):
+                buf.zero_()
+        else:
+            self._q = ctx.empty((1, N), td)
+            self._hcol_store = ctx.scalars(self.maxiter + 2 + 8)
+            self._tmp = ctx.scalars(4)
+            self._lz = ctx.scalars(3)          # Lanczos: [H[k-1,k], H[k,k], H[k+1,k]]
+            self._lz_st = ctx.scalars(16)
         self._t = None if (self._euclid and self.M is None) else ctx.empty((1, N), td)
-        self._hcol_store = ctx.scalars(self.maxiter + 2 + 8)
         self._hcol = self._hcol_store[1:]       # one leading zero: H[-1, 0] of linsys.py:828
-        self._tmp = ctx.scalars(4)
-        self._lz = ctx.scalars(3)          # Lanczos: [H[k-1,k], H[k,k], H[k+1,k]]
-        self._lz_st = ctx.scalars(16)
         self._hfro2 = 0.0
 
         # first basis vector: utils.py:923-952
