@@ -288,6 +288,11 @@ def run_b200(args, rank, world, local_rank):
     # ---- per-kernel roofline from the live CUDA-event brackets ------------------------------
     peak, peak_src = peaks()
     summ = timer.summary()
+    traffic = {}
+    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")     # ncu dram__bytes per launch (committed)
+    if os.path.exists(tpath) and n == N_GRID and world == 1:
+        with open(tpath) as f:
+            traffic = json.load(f)
     roof = None
     extra = {}
     nloc = N if world == 1 else (part.hi - part.lo)
@@ -300,7 +305,10 @@ def run_b200(args, rank, world, local_rank):
             by += (passes * (2 * nv + 3) + (2 if has_next else 0)) * nq * 8.0
         ach = by / (o["ms_total"] * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": "orth_kernel<double,2> (kry_orth_fused, ortho=%s)" % args.ortho,
-                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": traffic.get("orth", {}).get("traffic_per_launch"),
+                "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum+dram__bytes_write.sum, "
+                                  "mean over the 30 launches of one GMRES(30) cycle)" if traffic else None,
                 "peak_source": peak_src, "launches": o["launches"],
                 "avg_launch_ms": o["ms_total"] / max(o["launches"], 1),
                 "algorithmic_bytes_per_launch_avg": by / max(o["launches"], 1),
@@ -314,6 +322,8 @@ def run_b200(args, rank, world, local_rank):
         ach = by / (s["ms_total"] * 1e-3) / 1e9
         extra["roofline_spmv"] = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,8> (kry_spmv_csr)",
                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                  "traffic": traffic.get("spmv", {}).get("traffic_per_launch"),
+                                  "algorithmic_bytes_per_launch": by / max(s["launches"], 1),
                                   "launches": s["launches"], "avg_launch_ms": s["ms_total"] / max(s["launches"], 1),
                                   "share_of_step": (s["ms_total"] / ms) if world == 1 else None}
         if roof is not None:
@@ -346,6 +356,10 @@ def run_b200(args, rank, world, local_rank):
         m = min(len(a), len(r))
         extra["parity_vs_cpu_max_rel"] = float(np.max(np.abs(a[:m] - r[:m]) / r[:m]))
 
+    if rank == 0 and os.environ.get("KRY_TRACE"):
+        tr = sol.__dict__.get("_trace", [])
+        sys.stderr.write("phase trace (ms since start): " + ", ".join(
+            "%s=%.3f" % (nm, 1e3 * (tt - tr[0][1])) for nm, tt in tr) + "\n")
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,

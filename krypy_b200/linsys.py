@@ -17,6 +17,17 @@ __all__ = ["LinearSystem", "Cg", "Minres", "Gmres", "RestartedGmres", "TimedLine
            "ConvertedTimedLinearSystem"]
 
 
+_TRACE = bool(__import__("os").environ.get("KRY_TRACE"))
+
+
+def _mark(obj, name):
+    """KRY_TRACE=1: synchronised wall-clock marks of the solver phases (diagnostics only)"""
+    if _TRACE:
+        import time
+        _device.torch().cuda.synchronize()
+        obj.__dict__.setdefault("_trace", []).append((name, time.perf_counter()))
+
+
 def _host_vec(x):
     """numpy view (N,1) of a public vector argument, or None."""
     if x is None:
@@ -243,6 +254,7 @@ class _KrylovSolver(object):
         self.linear_system = ls = linear_system
         self._ctx = ctx = _ctx()
         ctx.use_current_stream()
+        _mark(self, "start")
         N = ls.N
         # (row-partitioned runs: N is the local length, the default maxiter the global dimension)
         self.maxiter = getattr(ls, "N_global", N) if maxiter is None else maxiter
@@ -272,6 +284,7 @@ class _KrylovSolver(object):
 
         # initial residual (linsys.py:359)
         self.MMlr0, self.Mlr0, self.MMlr0_norm = self._get_initial_residual(x0d)
+        _mark(self, "initial_residual")
         if x0d is None:
             x0d = ctx.zeros((1, N), self._td)
         self.x0 = x0d
@@ -287,7 +300,10 @@ class _KrylovSolver(object):
         if ls.exact_solution is not None:                       # linsys.py:393-402
             self.errnorms = []
             self.errnorms.append(self._errnorm(self._get_xk(None)))
-        self._solve()
+        try:
+            self._solve()
+        finally:
+            _mark(self, "solve_end")
         self._finalize()
 
     # -- hooks -----------------------------------------------------------------
@@ -703,8 +719,11 @@ class Gmres(_KrylovSolver):
 
         launched = -1
         k = -1
+        _mark(self, "arnoldi_init")
         while (self.resnorms[-1] > self.tol and ar.iter < ar.maxiter and not ar.invariant):
             k = self.iter = ar.iter
+            if k == ar.maxiter - 1:
+                _mark(self, "last_iteration_begin")
             if is_lanczos:
                 ar._enqueue(k)
                 # tridiagonal column from the three Lanczos entries
