@@ -178,6 +178,10 @@ class Context(object):
             raise NotImplementedError("complex vectors are not supported by the device path")
         if X.ndim == 1:
             X = X.reshape(-1, 1)
+        if X.shape[1] > 1 and X.shape[0] * X.shape[1] > (1 << 20):
+            # wide blocks (deflation spaces): upload as is, transpose on the device
+            Xd = t.from_numpy(np.ascontiguousarray(X)).to(self.device)
+            return Xd.to(dtype).t().contiguous()
         Xh = np.ascontiguousarray(X.T, dtype=torch_to_np_dtype(dtype))
         return t.from_numpy(Xh).to(self.device)
 
