@@ -205,6 +205,29 @@ int kry_peer_allreduce(kry_ctx* ctx, int world, int rank, unsigned long long* ep
 int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long* epoch_dev,
                      double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 
+/* ---- row-partitioned Gram-Schmidt step with the exchange fused into the kernels ------- */
+/* The phases of kry_orth_fused (krypy/utils.py:1012-1045) for a row-partitioned basis; the
+ * global sums travel inside the producing/consuming kernels (P2P stores + release flag in the
+ * producer's last CTA, acquire + rank-order sum in every CTA of the consumer):
+ *   kry_dist_dot    c_local = V^H q (nv <= 64), published to all peers
+ *   kry_dist_update c = global sum; h_acc_dev[j] += c_j; q -= V c; want_nrm: publishes ||q||^2
+ *   kry_dist_scale  nrm = sqrt(global sum) -> nrm_out_dev[0]; vnext = q / nrm (vnext may be NULL)
+ *   kry_dist_halo   handshake (every rank's vector is complete) + kry_halo_gather
+ * peer arguments as for kry_peer_allreduce. */
+int kry_dist_dot(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
+                 int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                 unsigned long long* const* peer_flags_dev);
+int kry_dist_update(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, void* q,
+                    double* h_acc_dev, int want_nrm, int world, int rank, unsigned long long* epoch_dev,
+                    double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
+int kry_dist_scale(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext, double* nrm_out_dev,
+                   int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                   unsigned long long* const* peer_flags_dev);
+int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev,
+                  long long elem_offset, const int* halo_peer, const int* halo_off, void* dst, int world,
+                  int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                  unsigned long long* const* peer_flags_dev);
+
 #ifdef __cplusplus
 }
 #endif

@@ -286,6 +286,28 @@ class Context(object):
         hbase = h_ptr if h_ptr is not None else h.data_ptr()
         if pre_vec is not None:
             self.axpy_dev(pre_coef, -1.0, pre_vec, q)
+        comm = self.comm
+        fused = (algo == KRY_ORTH_CGS and comm.reduce == "peer" and int(nv) > int(j0))
+        if fused:
+            # exchange fused into the kernels: dot(+publish) -> update(+acquire, +||q||^2 publish) -> scale
+            lib, w, r = self.lib, comm.world, comm.rank
+            ep, sl, fl = comm.epoch_dev.data_ptr(), comm.slots.peer_table.data_ptr(), comm.flags.peer_table.data_ptr()
+            dt, n, ld = code(q), q.numel(), Vdot.stride(0)
+            es = q.element_size()
+            for p in range(int(passes)):
+                j = int(j0)
+                while j < nv:
+                    c = min(64, int(nv) - j)
+                    lastc = (p == int(passes) - 1) and (j + c == int(nv))
+                    check(lib.kry_dist_dot(self.h, dt, n, Vdot.data_ptr() + j * ld * es, ld, c, q.data_ptr(),
+                                           w, r, ep, sl, fl))
+                    check(lib.kry_dist_update(self.h, dt, n, Vsub.data_ptr() + j * ld * es, ld, c, q.data_ptr(),
+                                              hbase + 8 * j, 1 if (lastc and nrm is not None) else 0,
+                                              w, r, ep, sl, fl))
+                    j += c
+            if nrm is not None:
+                check(lib.kry_dist_scale(self.h, dt, n, q.data_ptr(), _p(vnext), nrm.data_ptr(), w, r, ep, sl, fl))
+            return
         for _ in range(int(passes)):
             if algo == KRY_ORTH_CGS:
                 j = int(j0)

@@ -1,0 +1,463 @@
+// Row-partitioned Gram-Schmidt step with the NVLink exchange FUSED into the compute kernels
+// (one process per GPU, peers mapped with CUDA IPC, see kry_peer.cu):
+//
+//   kry_dist_dot    : c_local = Vdot^H q      ; the last CTA stores the partial sums straight into
+//                     every peer's slot array (P2P stores) and releases its flag
+//   kry_dist_update : every CTA acquires the peers' flags, sums the partials in rank order
+//                     (bitwise identical everywhere), q -= Vsub c, ||q||^2 partials; the last CTA
+//                     publishes the local ||q||^2 the same way
+//   kry_dist_scale  : acquires, nrm = sqrt(sum), v_next = q / nrm
+//   kry_dist_halo   : flag handshake (all ranks' basis rows are complete) + P2P gather of the
+//                     remote entries of v_k that the local CSR rows reference
+//
+// Compared with separate all-reduce kernels this removes four launches and four kernel
+// boundaries per Arnoldi step; no NCCL call and no host synchronisation is involved.
+// Protocol: one monotone operation counter per rank in device memory (epoch_dev, identical
+// sequence on all ranks); slot arrays are double buffered by epoch parity; a rank publishes
+// epoch e only after it has observed every peer's epoch e-1.
+#include "kry_common.cuh"
+
+#define KRY_ENTER(ctx)                                                         \
+    KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+#define PEER_MAX_RANKS 16
+#define PEER_SLOT 64
+
+struct PeerArgs {
+    int world, rank;
+    unsigned long long* epoch_dev;
+    double* const* slots;                 // [rank] -> that rank's [2][world][PEER_SLOT] doubles
+    unsigned long long* const* flags;     // [rank] -> that rank's [world] u64
+};
+
+__device__ __forceinline__ void dst_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long dld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double dld_volatile_f64(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dglobal_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// the calling CTA stores vals[0..n) into every rank's slot row for `epoch` and releases the flag
+__device__ __forceinline__ void peer_publish(const PeerArgs& pa, unsigned long long epoch, const double* vals_smem,
+                                             int n) {
+    const size_t par = (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
+    for (int idx = threadIdx.x; idx < pa.world * n; idx += blockDim.x) {
+        const int r = idx / n, i = idx - r * n;
+        pa.slots[r][par + (size_t)pa.rank * PEER_SLOT + i] = vals_smem[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pa.world) dst_release_sys(pa.flags[threadIdx.x] + pa.rank, epoch);
+}
+
+// every thread of the CTA returns once all ranks have published `epoch` (false on time-out)
+__device__ __forceinline__ bool peer_wait(const PeerArgs& pa, unsigned long long epoch, int* flag_smem) {
+    if (threadIdx.x == 0) *flag_smem = 1;
+    __syncthreads();
+    if (threadIdx.x < pa.world) {
+        const unsigned long long* f = pa.flags[pa.rank] + threadIdx.x;
+        const unsigned long long t0 = dglobal_timer_ns();
+        while (dld_acquire_sys(f) < epoch) {
+            if (dglobal_timer_ns() - t0 > 10000000000ull) {
+                *flag_smem = 0;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    __threadfence_system();
+    return *flag_smem != 0;
+}
+
+// fixed rank-order sum of slot i of `epoch` (my own slot array)
+__device__ __forceinline__ double peer_sum(const PeerArgs& pa, unsigned long long epoch, int i) {
+    const double* mine = pa.slots[pa.rank] + (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
+    double s = 0.0;
+    for (int r = 0; r < pa.world; ++r) s += dld_volatile_f64(mine + (size_t)r * PEER_SLOT + i);
+    return s;
+}
+
+__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
+
+// ---------------------------------------------------------------------------
+// K1: local block dot + publish
+// ---------------------------------------------------------------------------
+#define DD_JT 8
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2)
+dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, const T* q, double* partials,
+                unsigned int* ticket, PeerArgs pa) {
+    __shared__ double sm[32];
+    __shared__ double fin[PEER_SLOT];
+    __shared__ bool last;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int jb = 0; jb < nv; jb += DD_JT) {
+        double acc[DD_JT];
+#pragma unroll
+        for (int t = 0; t < DD_JT; ++t) acc[t] = 0.0;
+        for (long long i = i0; i < nvec; i += stride) {
+            double qv[VEC];
+            VecIO<T, VEC>::loadrw(q, i, qv);
+            double vv[DD_JT][VEC];
+#pragma unroll
+            for (int t = 0; t < DD_JT; ++t) {
+                int j = jb + t;
+                j = j < nv ? j : nv - 1;
+                VecIO<T, VEC>::load(V + (long long)j * ldv, i, vv[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < DD_JT; ++t)
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) acc[t] = fma(vv[t][u], qv[u], acc[t]);
+        }
+        if (blockIdx.x == 0) {
+            for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
+                const double qe = (double)q[i];
+#pragma unroll
+                for (int t = 0; t < DD_JT; ++t)
+                    if (jb + t < nv) acc[t] = fma((double)V[(long long)(jb + t) * ldv + i], qe, acc[t]);
+            }
+        }
+#pragma unroll
+        for (int t = 0; t < DD_JT; ++t) {
+            double s = kry_block_sum(acc[t], sm);
+            if (threadIdx.x == 0 && jb + t < nv)
+                partials[(long long)(jb + t) * KRY_MAX_PARTIAL_BLOCKS + blockIdx.x] = s;
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        for (int j = 0; j < nv; ++j) {
+            double v = 0.0;
+            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
+                v += __ldcg(partials + (long long)j * KRY_MAX_PARTIAL_BLOCKS + b);
+            double s = kry_block_sum(v, sm);
+            if (threadIdx.x == 0) fin[j] = s;
+        }
+        __syncthreads();
+        peer_publish(pa, E + 1ull, fin, nv);
+        if (threadIdx.x == 0) {
+            *pa.epoch_dev = E + 1ull;
+            *ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K2: acquire + global sum, q -= Vsub c, ||q||^2 (+ publish)
+// ---------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2)
+dist_update_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, T* q, double* h_acc, int want_nrm,
+                   double* partials, unsigned int* ticket, PeerArgs pa) {
+    __shared__ double sm[32];
+    __shared__ double c_s[PEER_SLOT];
+    __shared__ int okflag;
+    __shared__ bool last;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);     // the epoch kry_dist_dot published
+    const bool ok = peer_wait(pa, E, &okflag);
+    for (int j = threadIdx.x; j < nv; j += blockDim.x) c_s[j] = ok ? peer_sum(pa, E, j) : nan_f64();
+    __syncthreads();
+    if (blockIdx.x == 0 && h_acc)
+        for (int j = threadIdx.x; j < nv; j += blockDim.x) h_acc[j] += c_s[j];
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    double nrm2 = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+        for (int jb = 0; jb < nv; jb += 8) {
+            double vv[8][VEC];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) {
+                int j = jb + t < nv ? jb + t : nv - 1;
+                VecIO<T, VEC>::load(V + (long long)j * ldv, i, vv[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 8; ++t)
+                if (jb + t < nv) {
+                    const double c = c_s[jb + t];
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) qv[u] = fma(-c, vv[t][u], qv[u]);
+                }
+        }
+        VecIO<T, VEC>::store(q, i, qv);
+        if (want_nrm) {
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                const double r = (double)(T)qv[u];
+                nrm2 = fma(r, r, nrm2);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
+            double qe = (double)q[i];
+            for (int j = 0; j < nv; ++j) qe = fma(-c_s[j], (double)V[(long long)j * ldv + i], qe);
+            q[i] = (T)qe;
+            qe = (double)q[i];
+            if (want_nrm) nrm2 = fma(qe, qe, nrm2);
+        }
+    }
+    if (!want_nrm) return;
+    double s = kry_block_sum(nrm2, sm);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        double v = 0.0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v += __ldcg(partials + b);
+        double tot = kry_block_sum(v, sm);
+        __syncthreads();
+        if (threadIdx.x == 0) c_s[0] = tot;
+        __syncthreads();
+        peer_publish(pa, E + 1ull, c_s, 1);
+        if (threadIdx.x == 0) {
+            *pa.epoch_dev = E + 1ull;
+            *ticket = 0u;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// K3: acquire ||q||^2, v_next = q / nrm
+// ---------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2)
+dist_scale_kernel(long long n, const T* q, T* vnext, double* nrm_out, PeerArgs pa) {
+    __shared__ int okflag;
+    __shared__ double nrm_s;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
+    const bool ok = peer_wait(pa, E, &okflag);
+    if (threadIdx.x == 0) nrm_s = ok ? sqrt(fabs(peer_sum(pa, E, 0))) : nan_f64();
+    __syncthreads();
+    const double nrm = nrm_s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) nrm_out[0] = nrm;
+    if (vnext == nullptr) return;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] = nrm > 0.0 ? qv[u] / nrm : 0.0;
+        VecIO<T, VEC>::store(vnext, i, qv);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x)
+            vnext[i] = (T)(nrm > 0.0 ? (double)q[i] / nrm : 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// K4: handshake + halo gather
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(KRY_THREADS)
+dist_halo_kernel(long long nhalo, const T* const* peer_bases, long long elem_offset,
+                 const int* __restrict__ halo_peer, const int* __restrict__ halo_off, T* dst,
+                 unsigned int* ticket, PeerArgs pa) {
+    __shared__ int okflag;
+    __shared__ bool last;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
+    if (blockIdx.x == 0) {
+        // everything this rank wrote before this kernel (its segment of v_k) is complete
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < pa.world) dst_release_sys(pa.flags[threadIdx.x] + pa.rank, E + 1ull);
+    }
+    const bool ok = peer_wait(pa, E + 1ull, &okflag);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhalo; i += stride) {
+        const T* src = peer_bases[__ldg(halo_peer + i)] + elem_offset;
+        const T v = *(const volatile T*)(src + __ldg(halo_off + i));
+        dst[i] = ok ? v : (T)nan_f64();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *pa.epoch_dev = E + 1ull;
+        *ticket = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static inline int dgrid(const kry_ctx* ctx, long long nvec, int per_sm) {
+    long long need = (nvec + KRY_THREADS - 1) / KRY_THREADS;
+    long long cap = (long long)ctx->sm_count * per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+static int make_peer(PeerArgs& pa, int world, int rank, unsigned long long* epoch_dev, double* const* slots,
+                     unsigned long long* const* flags) {
+    KRY_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "bad world/rank");
+    KRY_REQUIRE(epoch_dev && slots && flags, "NULL peer argument");
+    pa.world = world;
+    pa.rank = rank;
+    pa.epoch_dev = epoch_dev;
+    pa.slots = slots;
+    pa.flags = flags;
+    return KRY_OK;
+}
+
+template <typename T>
+static int dist_dot_launch(kry_ctx* ctx, long long n, const T* V, long long ldv, int nv, const T* q, PeerArgs pa) {
+    const int W = VecWidth<T>::value;
+    bool al = kry_aligned16(V) && kry_aligned16(q) && (ldv % W == 0);
+    if (al)
+        dist_dot_kernel<T, W><<<dgrid(ctx, n / W, 2), KRY_THREADS, 0, ctx->stream>>>(
+            n, V, ldv, nv, q, ctx->d_partials, ctx->d_ticket + 4, pa);
+    else
+        dist_dot_kernel<T, 1><<<dgrid(ctx, n, 2), KRY_THREADS, 0, ctx->stream>>>(
+            n, V, ldv, nv, q, ctx->d_partials, ctx->d_ticket + 4, pa);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+template <typename T>
+static int dist_update_launch(kry_ctx* ctx, long long n, const T* V, long long ldv, int nv, T* q, double* h_acc,
+                              int want_nrm, PeerArgs pa) {
+    const int W = VecWidth<T>::value;
+    bool al = kry_aligned16(V) && kry_aligned16(q) && (ldv % W == 0);
+    // partials of the norm live behind the dot partials' slot 0..63 region: use slot 64's row
+    double* part = ctx->d_partials + (size_t)KRY_MAX_SLOTS * KRY_MAX_PARTIAL_BLOCKS;
+    if (al)
+        dist_update_kernel<T, W><<<dgrid(ctx, n / W, 2), KRY_THREADS, 0, ctx->stream>>>(
+            n, V, ldv, nv, q, h_acc, want_nrm, part, ctx->d_ticket + 5, pa);
+    else
+        dist_update_kernel<T, 1><<<dgrid(ctx, n, 2), KRY_THREADS, 0, ctx->stream>>>(
+            n, V, ldv, nv, q, h_acc, want_nrm, part, ctx->d_ticket + 5, pa);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+template <typename T>
+static int dist_scale_launch(kry_ctx* ctx, long long n, const T* q, T* vnext, double* nrm_out, PeerArgs pa) {
+    const int W = VecWidth<T>::value;
+    bool al = kry_aligned16(q) && (!vnext || kry_aligned16(vnext));
+    if (al)
+        dist_scale_kernel<T, W><<<dgrid(ctx, n / W, 4), KRY_THREADS, 0, ctx->stream>>>(n, q, vnext, nrm_out, pa);
+    else
+        dist_scale_kernel<T, 1><<<dgrid(ctx, n, 4), KRY_THREADS, 0, ctx->stream>>>(n, q, vnext, nrm_out, pa);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+extern "C" {
+
+int kry_dist_dot(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
+                 int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                 unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && nv >= 1 && nv <= PEER_SLOT && V && q, "bad arguments (1 <= nv <= 64)");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    if (dtype == KRY_F64) return dist_dot_launch<double>(ctx, n, (const double*)V, ldv, nv, (const double*)q, pa);
+    if (dtype == KRY_F32) return dist_dot_launch<float>(ctx, n, (const float*)V, ldv, nv, (const float*)q, pa);
+    kry_set_error("kry_dist_dot: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_dist_update(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, void* q,
+                    double* h_acc_dev, int want_nrm, int world, int rank, unsigned long long* epoch_dev,
+                    double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && nv >= 1 && nv <= PEER_SLOT && V && q, "bad arguments (1 <= nv <= 64)");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    if (dtype == KRY_F64)
+        return dist_update_launch<double>(ctx, n, (const double*)V, ldv, nv, (double*)q, h_acc_dev, want_nrm, pa);
+    if (dtype == KRY_F32)
+        return dist_update_launch<float>(ctx, n, (const float*)V, ldv, nv, (float*)q, h_acc_dev, want_nrm, pa);
+    kry_set_error("kry_dist_update: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_dist_scale(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext, double* nrm_out_dev, int world,
+                   int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                   unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && q && nrm_out_dev, "bad arguments");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    if (dtype == KRY_F64) return dist_scale_launch<double>(ctx, n, (const double*)q, (double*)vnext, nrm_out_dev, pa);
+    if (dtype == KRY_F32) return dist_scale_launch<float>(ctx, n, (const float*)q, (float*)vnext, nrm_out_dev, pa);
+    kry_set_error("kry_dist_scale: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev, long long elem_offset,
+                  const int* halo_peer, const int* halo_off, void* dst, int world, int rank,
+                  unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                  unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(nhalo >= 0, "negative size");
+    KRY_REQUIRE(nhalo == 0 || (peer_bases_dev && halo_peer && halo_off && dst), "NULL argument");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    long long need = (nhalo + KRY_THREADS - 1) / KRY_THREADS;
+    if (need < 1) need = 1;
+    long long cap = (long long)ctx->sm_count * 4;
+    int g = (int)(need < cap ? need : cap);
+    if (dtype == KRY_F64)
+        dist_halo_kernel<double><<<g, KRY_THREADS, 0, ctx->stream>>>(
+            nhalo, (const double* const*)peer_bases_dev, elem_offset, halo_peer, halo_off, (double*)dst,
+            ctx->d_ticket + 6, pa);
+    else if (dtype == KRY_F32)
+        dist_halo_kernel<float><<<g, KRY_THREADS, 0, ctx->stream>>>(
+            nhalo, (const float* const*)peer_bases_dev, elem_offset, halo_peer, halo_off, (float*)dst,
+            ctx->d_ticket + 6, pa);
+    else {
+        kry_set_error("kry_dist_halo: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+}  // extern "C"

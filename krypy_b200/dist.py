@@ -330,11 +330,18 @@ class DistCsrOperator(utils._DeviceOperator):
                 reg = comm.find_region(x.data_ptr(), pl.ext * es)
             off = (x.data_ptr() - reg.base) // es
             xext = reg.view(Xd.dtype)[off: off + pl.ext]
-            comm.barrier()                           # every rank's segment of this vector is complete
-            if pl.nhalo:
-                check(ctx.lib.kry_halo_gather(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(), off,
-                                              hp.data_ptr(), ho.data_ptr(), None,
-                                              xext.data_ptr() + pl.block * es))
+            if comm.reduce == "peer":
+                # one kernel: flag handshake (every rank's segment of this vector is complete) + P2P gather
+                check(ctx.lib.kry_dist_halo(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(), off,
+                                            hp.data_ptr(), ho.data_ptr(), xext.data_ptr() + pl.block * es,
+                                            comm.world, comm.rank, comm.epoch_dev.data_ptr(),
+                                            comm.slots.peer_table.data_ptr(), comm.flags.peer_table.data_ptr()))
+            else:
+                comm.barrier()
+                if pl.nhalo:
+                    check(ctx.lib.kry_halo_gather(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(),
+                                                  off, hp.data_ptr(), ho.data_ptr(), None,
+                                                  xext.data_ptr() + pl.block * es))
             ctx.spmv(A, xext, out[j])
         return out
 
