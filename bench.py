@@ -210,8 +210,8 @@ def run_b200(args, rank, world, local_rank):
         b = problems.rhs_normal(N)
         ls = kp.linsys.LinearSystem(A, b)
         ws = kp.utils.SolverWorkspace()
-        make_solver = lambda x0: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho,
-                                                 _workspace=ws)
+        make_solver = lambda x0, r0=None: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho,
+                                                          _workspace=ws, _x0_residual=r0)
     else:
         from krypy_b200 import dist as kdist
         part = kdist.RowPartition(N, world, rank)
@@ -219,14 +219,19 @@ def run_b200(args, rank, world, local_rank):
         b = problems.rhs_normal(N)[part.lo:part.hi]
         ls = kdist.DistLinearSystem(A, b, part)
         ws = kp.utils.SolverWorkspace()      # persistent buffers + one CUDA graph per Arnoldi step
-        make_solver = lambda x0: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho,
-                                                 _workspace=ws)
+        make_solver = lambda x0, r0=None: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho,
+                                                          _workspace=ws, _x0_residual=r0)
+
+    carry = {"r": None}
 
     def cycle(x0):
+        # exactly what RestartedGmres does per restart (x0 = previous x_k, and the explicit residual the
+        # previous cycle computed for it is handed over instead of being recomputed)
         try:
-            sol = make_solver(x0)
+            sol = make_solver(x0, carry["r"] if x0 is not None else None)
         except kp.utils.ConvergenceError as e:
             sol = e.solver
+        carry["r"] = sol.__dict__.get("_last_residual")
         return sol
 
     def barrier():

@@ -155,12 +155,15 @@ dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, con
     __syncthreads();
     if (last) {
         __threadfence();
-        for (int j = 0; j < nv; ++j) {
-            double v = 0.0;
-            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-                v += __ldcg(partials + (long long)j * KRY_MAX_PARTIAL_BLOCKS + b);
-            double s = kry_block_sum(v, sm);
-            if (threadIdx.x == 0) fin[j] = s;
+        {   // final local sums: one warp per basis vector, lanes stride over the CTAs (fixed order)
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            for (int j = w; j < nv; j += nw) {
+                double v = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32)
+                    v += __ldcg(partials + (long long)j * KRY_MAX_PARTIAL_BLOCKS + b);
+                v = kry_warp_sum(v);
+                if (lane == 0) fin[j] = v;
+            }
         }
         __syncthreads();
         peer_publish(pa, E + 1ull, fin, nv);
@@ -183,8 +186,21 @@ dist_update_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, 
     __shared__ int okflag;
     __shared__ bool last;
     const unsigned long long E = dld_volatile_u64(pa.epoch_dev);     // the epoch kry_dist_dot published
+    __shared__ double stage[PEER_MAX_RANKS * PEER_SLOT];
     const bool ok = peer_wait(pa, E, &okflag);
-    for (int j = threadIdx.x; j < nv; j += blockDim.x) c_s[j] = ok ? peer_sum(pa, E, j) : nan_f64();
+    {   // all world*nv partials are fetched in parallel, then summed in rank order
+        const double* mine = pa.slots[pa.rank] + (size_t)(E & 1ull) * (size_t)pa.world * PEER_SLOT;
+        for (int idx = threadIdx.x; idx < pa.world * nv; idx += blockDim.x) {
+            const int r = idx / nv, j = idx - r * nv;
+            stage[r * PEER_SLOT + j] = dld_volatile_f64(mine + (size_t)r * PEER_SLOT + j);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < nv; j += blockDim.x) {
+            double sum = 0.0;
+            for (int r = 0; r < pa.world; ++r) sum += stage[r * PEER_SLOT + j];
+            c_s[j] = ok ? sum : nan_f64();
+        }
+    }
     __syncthreads();
     if (blockIdx.x == 0 && h_acc)
         for (int j = threadIdx.x; j < nv; j += blockDim.x) h_acc[j] += c_s[j];

@@ -183,15 +183,18 @@ block_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, co
     __syncthreads();
     if (last) {
         __threadfence();
-        for (int j = 0; j < nv; ++j) {
-            double v = 0.0;
-            for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x)
-                v += __ldcg(partials + (long long)j * KRY_MAX_PARTIAL_BLOCKS + b);
-            double s = kry_block_sum(v, sm);
-            if (threadIdx.x == 0) {
-                if (post == 1) s = sqrt(fabs(s));   // sqrt(||ip||_2) of a 1x1 matrix, utils.py:238
-                out[j] = s;
-                if (acc_out) acc_out[j] += s;
+        {   // one warp per basis vector, lanes stride over the CTAs (fixed order, parallel over j)
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+            for (int j = w; j < nv; j += nw) {
+                double s = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32)
+                    s += __ldcg(partials + (long long)j * KRY_MAX_PARTIAL_BLOCKS + b);
+                s = kry_warp_sum(s);
+                if (lane == 0) {
+                    if (post == 1) s = sqrt(fabs(s));   // sqrt(||ip||_2) of a 1x1 matrix, utils.py:238
+                    out[j] = s;
+                    if (acc_out) acc_out[j] += s;
+                }
             }
         }
         if (threadIdx.x == 0) *ticket = 0u;

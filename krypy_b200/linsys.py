@@ -248,7 +248,7 @@ class _KrylovSolver(object):
     Mlr0 = _LazyVec("Mlr0")
 
     def __init__(self, linear_system, x0=None, tol=1e-5, maxiter=None, explicit_residual=False,
-                 store_arnoldi=False, dtype=None):
+                 store_arnoldi=False, dtype=None, _x0_residual=None):
         if not isinstance(linear_system, LinearSystem):
             raise utils.ArgumentError("linear_system is not an instance of LinearSystem")
         self.linear_system = ls = linear_system
@@ -282,8 +282,14 @@ class _KrylovSolver(object):
                 raise utils.ArgumentError("x0 has the wrong length")
         x0d = self._get_initial_guess(x0d)
 
-        # initial residual (linsys.py:359)
-        self.MMlr0, self.Mlr0, self.MMlr0_norm = self._get_initial_residual(x0d)
+        # initial residual (linsys.py:359).  A restart hands over the explicit residual the previous
+        # cycle computed for exactly this x0 (linsys.py:460 and :359 evaluate the same expression).
+        self._last_residual = None
+        if _x0_residual is not None and x0d is not None and type(self)._get_initial_residual is \
+                _KrylovSolver._get_initial_residual:
+            self.MMlr0, self.Mlr0, self.MMlr0_norm = _x0_residual
+        else:
+            self.MMlr0, self.Mlr0, self.MMlr0_norm = self._get_initial_residual(x0d)
         _mark(self, "initial_residual")
         if x0d is None:
             x0d = ctx.zeros((1, N), self._td)
@@ -335,6 +341,7 @@ class _KrylovSolver(object):
         """krypy/linsys.py:430-493."""
         ls = self.linear_system
         self.xk = None
+        self._last_residual = None
         if ls.exact_solution is not None:
             self.xk = self._get_xk(yk)
             self.errnorms.append(self._errnorm(self.__dict__["_xk_dev"]))
@@ -343,7 +350,8 @@ class _KrylovSolver(object):
                 or self.iter + 1 == self.maxiter):
             if self.__dict__.get("_xk_dev") is None:
                 self.xk = self._get_xk(yk)
-            _, _, rkn = ls._get_residual_dev(self.__dict__["_xk_dev"], compute_norm=True)
+            MMlrk, Mlrk, rkn = ls._get_residual_dev(self.__dict__["_xk_dev"], compute_norm=True)
+            self._last_residual = (MMlrk, Mlrk, rkn)
             self.resnorms.append(rkn / ls.MMlb_norm)
             if self.resnorms[-1] > self.tol:
                 if self.iter + 1 == self.maxiter:
@@ -803,6 +811,7 @@ class _RestartedSolver(object):
             if xk_dev is None:
                 xk_dev = _ctx().to_block(sol.xk, sol._td)
             xk_dev = xk_dev.reshape(-1)                  # flat: keeps flat_vecs semantics neutral
+            kwargs["_x0_residual"] = sol.__dict__.get("_last_residual")
             self._last = sol
             tol = sol.tol
             del self.resnorms[-1]
