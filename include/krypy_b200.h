@@ -214,6 +214,14 @@ int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long* epoc
  *   kry_dist_scale  nrm = sqrt(global sum) -> nrm_out_dev[0]; vnext = q / nrm (vnext may be NULL)
  *   kry_dist_halo   handshake (every rank's vector is complete) + kry_halo_gather
  * peer arguments as for kry_peer_allreduce. */
+/* kry_orth_fused for a row-partitioned basis as ONE cooperative kernel: after each grid-wide
+ * reduction CTA 0 publishes the local sums to all peers and every CTA completes the global sum
+ * (same arguments as kry_orth_fused + the peer arguments of kry_peer_allreduce; CGS: nv-j0 <= 64). */
+int kry_orth_fused_dist(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub,
+                        long long ldv, int j0, int nv, void* q, int passes, int algo,
+                        const void* pre_vec, const double* pre_coef_dev, double* h_dev, double* nrm_dev,
+                        void* vnext, int world, int rank, unsigned long long* epoch_dev,
+                        double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 int kry_dist_dot(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
                  int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
                  unsigned long long* const* peer_flags_dev);
@@ -223,6 +231,13 @@ int kry_dist_update(kry_ctx* ctx, int dtype, long long n, const void* V, long lo
 int kry_dist_scale(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext, double* nrm_out_dev,
                    int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
                    unsigned long long* const* peer_flags_dev);
+/* kry_dist_scale + "my segment of vnext is complete" handshake + halo gather of vnext in ONE
+ * kernel: the next SpMV on vnext needs no further exchange (halo_dst = vnext + block). */
+int kry_dist_scale_halo(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext,
+                        double* nrm_out_dev, long long nhalo, const void* const* peer_bases_dev,
+                        long long elem_offset, const int* halo_peer, const int* halo_off, void* halo_dst,
+                        int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                        unsigned long long* const* peer_flags_dev);
 int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev,
                   long long elem_offset, const int* halo_peer, const int* halo_off, void* dst, int world,
                   int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,

@@ -259,23 +259,25 @@ class Context(object):
                                          out.data_ptr()))
 
     def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
-                   pre_coef=None, h_ptr=None):
+                   pre_coef=None, h_ptr=None, halo_op=None):
         if self.timer is not None:
             tm, self.timer = self.timer, None
             tm.bracket("orth", (q.numel(), int(nv) - int(j0), int(passes), int(algo), vnext is not None),
                        lambda: self.orth_fused(Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec,
-                                               pre_coef, h_ptr))
+                                               pre_coef, h_ptr, halo_op))
             self.timer = tm
             return
         if self.comm is not None:
-            return self._orth_split(Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr)
+            return self._orth_split(Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr,
+                                    halo_op)
         ld = Vdot.stride(0) if Vdot is not None else 0
         hp = h_ptr if h_ptr is not None else _p(h)
         check(self.lib.kry_orth_fused(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, int(j0), int(nv),
                                       q.data_ptr(), int(passes), int(algo), _p(pre_vec), _p(pre_coef),
                                       hp, _p(nrm), _p(vnext)))
 
-    def _orth_split(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr):
+    def _orth_split(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr,
+                    halo_op=None):
         """Row-partitioned Gram-Schmidt step: the phases of kry_orth_fused as separate kernels
         with the global sums (NVLink peer all-reduce) between them.  CGS: one reduction of nv
         values per pass; MGS: one per basis vector (exact reference order, latency bound)."""
@@ -287,6 +289,29 @@ class Context(object):
         if pre_vec is not None:
             self.axpy_dev(pre_coef, -1.0, pre_vec, q)
         comm = self.comm
+        if comm.reduce == "peer" and comm.orth_mode == "coop":
+            # ONE cooperative kernel per call: the reductions are completed over NVLink inside it
+            lib, w, r = self.lib, comm.world, comm.rank
+            ep, sl, fl = comm.epoch_dev.data_ptr(), comm.slots.peer_table.data_ptr(), comm.flags.peer_table.data_ptr()
+            ld = Vdot.stride(0) if Vdot is not None else 0
+            if algo != KRY_ORTH_CGS or int(nv) - int(j0) <= 64:
+                check(lib.kry_orth_fused_dist(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, int(j0), int(nv),
+                                              q.data_ptr(), int(passes), int(algo), _p(pre_vec), _p(pre_coef),
+                                              hbase, _p(nrm), _p(vnext), w, r, ep, sl, fl))
+                return
+            j = int(j0)
+            first = True
+            while j < nv:                                  # block-wise CGS over chunks of 64 basis vectors
+                j1 = min(j + 64, int(nv))
+                lastc = j1 == int(nv)
+                check(lib.kry_orth_fused_dist(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, j, j1,
+                                              q.data_ptr(), int(passes), int(algo),
+                                              _p(pre_vec) if first else None, _p(pre_coef) if first else None,
+                                              hbase, _p(nrm) if lastc else None, _p(vnext) if lastc else None,
+                                              w, r, ep, sl, fl))
+                first = False
+                j = j1
+            return
         fused = (algo == KRY_ORTH_CGS and comm.reduce == "peer" and int(nv) > int(j0))
         if fused:
             # exchange fused into the kernels: dot(+publish) -> update(+acquire, +||q||^2 publish) -> scale
@@ -306,7 +331,15 @@ class Context(object):
                                               w, r, ep, sl, fl))
                     j += c
             if nrm is not None:
-                check(lib.kry_dist_scale(self.h, dt, n, q.data_ptr(), _p(vnext), nrm.data_ptr(), w, r, ep, sl, fl))
+                hal = halo_op._halo_args(vnext) if (halo_op is not None and vnext is not None) else None
+                if hal is not None:
+                    # scale + "segment complete" handshake + halo gather of v_next in one kernel
+                    peer_tab, off, hp, ho, nhalo, dst = hal
+                    check(lib.kry_dist_scale_halo(self.h, dt, n, q.data_ptr(), vnext.data_ptr(), nrm.data_ptr(),
+                                                  nhalo, peer_tab, off, hp, ho, dst, w, r, ep, sl, fl))
+                    comm.halo_ready = vnext.data_ptr()
+                else:
+                    check(lib.kry_dist_scale(self.h, dt, n, q.data_ptr(), _p(vnext), nrm.data_ptr(), w, r, ep, sl, fl))
             return
         for _ in range(int(passes)):
             if algo == KRY_ORTH_CGS:

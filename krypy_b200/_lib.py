@@ -68,12 +68,17 @@ PROTOTYPES = {
                                 c_void_p]),
     "kry_peer_allreduce": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                    c_void_p, c_void_p, c_int, c_void_p]),
+    "kry_orth_fused_dist": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int,
+                                    c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
+                                    c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "kry_dist_dot": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p,
                              c_void_p, c_void_p]),
     "kry_dist_update": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_void_p, c_void_p, c_void_p]),
     "kry_dist_scale": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p,
                                c_void_p, c_void_p]),
+    "kry_dist_scale_halo": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll,
+                                    c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "kry_dist_halo": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "kry_small_qr_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

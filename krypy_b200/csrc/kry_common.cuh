@@ -125,3 +125,84 @@ __device__ __forceinline__ double kry_reduce_partials(const volatile double* par
     for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partials[b];
     return kry_block_sum(v, sm);
 }
+
+// ---------------------------------------------------------------------------
+// NVLink peer exchange helpers (shared by kry_dist.cu and the cooperative kernels)
+// ---------------------------------------------------------------------------
+#define PEER_MAX_RANKS 16
+#define PEER_SLOT 64
+
+struct PeerArgs {
+    int world, rank;
+    unsigned long long* epoch_dev;
+    double* const* slots;                 // [rank] -> that rank's [2][world][PEER_SLOT] doubles
+    unsigned long long* const* flags;     // [rank] -> that rank's [world] u64
+};
+
+__device__ __forceinline__ void dst_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long dld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dld_volatile_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double dld_volatile_f64(const double* p) {
+    double v;
+    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long dglobal_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// the calling CTA stores vals[0..n) into every rank's slot row for `epoch` and releases the flag
+__device__ __forceinline__ void peer_publish(const PeerArgs& pa, unsigned long long epoch, const double* vals_smem,
+                                             int n) {
+    const size_t par = (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
+    for (int idx = threadIdx.x; idx < pa.world * n; idx += blockDim.x) {
+        const int r = idx / n, i = idx - r * n;
+        pa.slots[r][par + (size_t)pa.rank * PEER_SLOT + i] = vals_smem[i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x < pa.world) dst_release_sys(pa.flags[threadIdx.x] + pa.rank, epoch);
+}
+
+// every thread of the CTA returns once all ranks have published `epoch` (false on time-out)
+__device__ __forceinline__ bool peer_wait(const PeerArgs& pa, unsigned long long epoch, int* flag_smem) {
+    if (threadIdx.x == 0) *flag_smem = 1;
+    __syncthreads();
+    if (threadIdx.x < pa.world) {
+        const unsigned long long* f = pa.flags[pa.rank] + threadIdx.x;
+        const unsigned long long t0 = dglobal_timer_ns();
+        while (dld_acquire_sys(f) < epoch) {
+            if (dglobal_timer_ns() - t0 > 10000000000ull) {
+                *flag_smem = 0;
+                break;
+            }
+        }
+    }
+    // the polling threads' ld.acquire.sys + the CTA barrier order every later access of the CTA
+    // after the peers' releases (causality is cumulative): no CTA-wide system fence needed
+    __syncthreads();
+    return *flag_smem != 0;
+}
+
+// fixed rank-order sum of slot i of `epoch` (my own slot array)
+__device__ __forceinline__ double peer_sum(const PeerArgs& pa, unsigned long long epoch, int i) {
+    const double* mine = pa.slots[pa.rank] + (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
+    double s = 0.0;
+    for (int r = 0; r < pa.world; ++r) s += dld_volatile_f64(mine + (size_t)r * PEER_SLOT + i);
+    return s;
+}
+
+__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
+

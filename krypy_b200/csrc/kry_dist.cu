@@ -21,82 +21,6 @@
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
     KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
 
-#define PEER_MAX_RANKS 16
-#define PEER_SLOT 64
-
-struct PeerArgs {
-    int world, rank;
-    unsigned long long* epoch_dev;
-    double* const* slots;                 // [rank] -> that rank's [2][world][PEER_SLOT] doubles
-    unsigned long long* const* flags;     // [rank] -> that rank's [world] u64
-};
-
-__device__ __forceinline__ void dst_release_sys(unsigned long long* p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long dld_acquire_sys(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long dld_volatile_u64(const unsigned long long* p) {
-    unsigned long long v;
-    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ double dld_volatile_f64(const double* p) {
-    double v;
-    asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ unsigned long long dglobal_timer_ns() {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-// the calling CTA stores vals[0..n) into every rank's slot row for `epoch` and releases the flag
-__device__ __forceinline__ void peer_publish(const PeerArgs& pa, unsigned long long epoch, const double* vals_smem,
-                                             int n) {
-    const size_t par = (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
-    for (int idx = threadIdx.x; idx < pa.world * n; idx += blockDim.x) {
-        const int r = idx / n, i = idx - r * n;
-        pa.slots[r][par + (size_t)pa.rank * PEER_SLOT + i] = vals_smem[i];
-    }
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x < pa.world) dst_release_sys(pa.flags[threadIdx.x] + pa.rank, epoch);
-}
-
-// every thread of the CTA returns once all ranks have published `epoch` (false on time-out)
-__device__ __forceinline__ bool peer_wait(const PeerArgs& pa, unsigned long long epoch, int* flag_smem) {
-    if (threadIdx.x == 0) *flag_smem = 1;
-    __syncthreads();
-    if (threadIdx.x < pa.world) {
-        const unsigned long long* f = pa.flags[pa.rank] + threadIdx.x;
-        const unsigned long long t0 = dglobal_timer_ns();
-        while (dld_acquire_sys(f) < epoch) {
-            if (dglobal_timer_ns() - t0 > 10000000000ull) {
-                *flag_smem = 0;
-                break;
-            }
-        }
-    }
-    __syncthreads();
-    __threadfence_system();
-    return *flag_smem != 0;
-}
-
-// fixed rank-order sum of slot i of `epoch` (my own slot array)
-__device__ __forceinline__ double peer_sum(const PeerArgs& pa, unsigned long long epoch, int i) {
-    const double* mine = pa.slots[pa.rank] + (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
-    double s = 0.0;
-    for (int r = 0; r < pa.world; ++r) s += dld_volatile_f64(mine + (size_t)r * PEER_SLOT + i);
-    return s;
-}
-
-__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
-
 // ---------------------------------------------------------------------------
 // K1: local block dot + publish
 // ---------------------------------------------------------------------------
@@ -105,7 +29,7 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(KRY_THREADS, 2)
 dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, const T* q, double* partials,
                 unsigned int* ticket, PeerArgs pa) {
-    __shared__ double sm[32];
+    __shared__ double red[DD_JT * 8];
     __shared__ double fin[PEER_SLOT];
     __shared__ bool last;
     const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
@@ -139,11 +63,23 @@ dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, con
                     if (jb + t < nv) acc[t] = fma((double)V[(long long)(jb + t) * ldv + i], qe, acc[t]);
             }
         }
+        // CTA reduction of all DD_JT accumulators with ONE barrier pair (at the per-rank sizes of an
+        // 8-GPU run the per-accumulator barriers were ~15 % of the kernel)
+        {
+            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
 #pragma unroll
-        for (int t = 0; t < DD_JT; ++t) {
-            double s = kry_block_sum(acc[t], sm);
-            if (threadIdx.x == 0 && jb + t < nv)
-                partials[(long long)(jb + t) * KRY_MAX_PARTIAL_BLOCKS + blockIdx.x] = s;
+            for (int t = 0; t < DD_JT; ++t) acc[t] = kry_warp_sum(acc[t]);
+            __syncthreads();
+            if (lane == 0) {
+#pragma unroll
+                for (int t = 0; t < DD_JT; ++t) red[t * 8 + w] = acc[t];
+            }
+            __syncthreads();
+            if (threadIdx.x < DD_JT && jb + threadIdx.x < nv) {
+                double s = 0.0;
+                for (int ww = 0; ww < nw; ++ww) s += red[threadIdx.x * 8 + ww];     // fixed warp order
+                partials[(long long)(jb + threadIdx.x) * KRY_MAX_PARTIAL_BLOCKS + blockIdx.x] = s;
+            }
         }
     }
     __threadfence();
@@ -299,6 +235,71 @@ dist_scale_kernel(long long n, const T* q, T* vnext, double* nrm_out, PeerArgs p
 }
 
 // ---------------------------------------------------------------------------
+// K3+K4 fused: acquire ||q||^2, v_next = q / nrm, publish "my segment of v_next is complete",
+// acquire the peers' flags, gather the halo of v_next -- the next SpMV starts without any
+// further handshake.  All CTAs are co-resident (grid <= 4 CTAs/SM), so waiting on the peers
+// inside the kernel cannot starve the local publisher.
+// ---------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 4)
+dist_scale_halo_kernel(long long n, const T* q, T* vnext, double* nrm_out, long long nhalo,
+                       const T* const* peer_bases, long long elem_offset, const int* __restrict__ halo_peer,
+                       const int* __restrict__ halo_off, T* halo_dst, unsigned int* ticket, PeerArgs pa) {
+    __shared__ int okflag;
+    __shared__ double nrm_s;
+    __shared__ bool last;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
+    const bool ok = peer_wait(pa, E, &okflag);
+    if (threadIdx.x == 0) nrm_s = ok ? sqrt(fabs(peer_sum(pa, E, 0))) : nan_f64();
+    __syncthreads();
+    const double nrm = nrm_s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) nrm_out[0] = nrm;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] = nrm > 0.0 ? qv[u] / nrm : 0.0;
+        VecIO<T, VEC>::store(vnext, i, qv);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x)
+            vnext[i] = (T)(nrm > 0.0 ? (double)q[i] / nrm : 0.0);
+    // my segment is complete once every CTA is here: the last one releases the flag to all peers
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x < pa.world) dst_release_sys(pa.flags[threadIdx.x] + pa.rank, E + 1ull);
+    }
+    const bool ok2 = peer_wait(pa, E + 1ull, &okflag);
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhalo; i += stride) {
+        const T* src = peer_bases[__ldg(halo_peer + i)] + elem_offset;
+        const T v = *(const volatile T*)(src + __ldg(halo_off + i));
+        halo_dst[i] = ok2 ? v : (T)nan_f64();
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket + 1, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last && threadIdx.x == 0) {
+        *pa.epoch_dev = E + 1ull;
+        ticket[0] = 0u;
+        ticket[1] = 0u;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // K4: handshake + halo gather
 // ---------------------------------------------------------------------------
 template <typename T>
@@ -444,6 +445,48 @@ int kry_dist_scale(kry_ctx* ctx, int dtype, long long n, const void* q, void* vn
     if (dtype == KRY_F32) return dist_scale_launch<float>(ctx, n, (const float*)q, (float*)vnext, nrm_out_dev, pa);
     kry_set_error("kry_dist_scale: unsupported dtype %d", dtype);
     return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_dist_scale_halo(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext, double* nrm_out_dev,
+                        long long nhalo, const void* const* peer_bases_dev, long long elem_offset,
+                        const int* halo_peer, const int* halo_off, void* halo_dst, int world, int rank,
+                        unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                        unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && q && vnext && nrm_out_dev && nhalo >= 0, "bad arguments");
+    KRY_REQUIRE(nhalo == 0 || (peer_bases_dev && halo_peer && halo_off && halo_dst), "NULL halo argument");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    unsigned int* tk = ctx->d_ticket + 8;
+    if (dtype == KRY_F64) {
+        const double* qq = (const double*)q;
+        double* vn = (double*)vnext;
+        if (kry_aligned16(qq) && kry_aligned16(vn))
+            dist_scale_halo_kernel<double, 2><<<dgrid(ctx, n / 2, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const double* const*)peer_bases_dev, elem_offset, halo_peer, halo_off,
+                (double*)halo_dst, tk, pa);
+        else
+            dist_scale_halo_kernel<double, 1><<<dgrid(ctx, n, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const double* const*)peer_bases_dev, elem_offset, halo_peer, halo_off,
+                (double*)halo_dst, tk, pa);
+    } else if (dtype == KRY_F32) {
+        const float* qq = (const float*)q;
+        float* vn = (float*)vnext;
+        if (kry_aligned16(qq) && kry_aligned16(vn))
+            dist_scale_halo_kernel<float, 4><<<dgrid(ctx, n / 4, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const float* const*)peer_bases_dev, elem_offset, halo_peer, halo_off,
+                (float*)halo_dst, tk, pa);
+        else
+            dist_scale_halo_kernel<float, 1><<<dgrid(ctx, n, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const float* const*)peer_bases_dev, elem_offset, halo_peer, halo_off,
+                (float*)halo_dst, tk, pa);
+    } else {
+        kry_set_error("kry_dist_scale_halo: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
 }
 
 int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev, long long elem_offset,

@@ -34,6 +34,7 @@ struct OrthArgs {
     double* nrm;
     T* vnext;
     double* partials;   // [2][KRY_MAX_SLOTS][KRY_MAX_PARTIAL_BLOCKS]
+    PeerArgs peer;      // world == 1: single GPU; otherwise the reductions are completed over NVLink
 };
 
 __device__ __forceinline__ double* partial_slot(double* partials, int buf, int slot) {
@@ -61,11 +62,35 @@ __device__ __forceinline__ void reduce_slots(double* partials, int buf, int cnt,
     __syncthreads();
 }
 
-template <typename T, int VEC>
+// Row-partitioned run: turn the local sums c_s[0..cnt) (identical in every CTA) into global sums.
+// CTA 0 stores them into every peer's slot array and releases its flag; every CTA acquires all
+// flags and sums the per-rank partials in rank order (bitwise identical on all ranks).
+__device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned long long epoch, double* c_s, int cnt,
+                                              double* stage, int* okflag) {
+    if (blockIdx.x == 0) peer_publish(pa, epoch, c_s, cnt);
+    const bool ok = peer_wait(pa, epoch, okflag);
+    const double* mine = pa.slots[pa.rank] + (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
+    for (int idx = threadIdx.x; idx < pa.world * cnt; idx += blockDim.x) {
+        const int r = idx / cnt, j = idx - r * cnt;
+        stage[r * PEER_SLOT + j] = dld_volatile_f64(mine + (size_t)r * PEER_SLOT + j);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < pa.world; ++r) sum += stage[r * PEER_SLOT + j];
+        c_s[j] = ok ? sum : nan_f64();
+    }
+    __syncthreads();
+}
+
+template <typename T, int VEC, bool PEER>
 __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[32];
     __shared__ double c_s[KRY_MAX_SLOTS];
+    __shared__ double stage[PEER ? PEER_MAX_RANKS * PEER_SLOT : 1];
+    __shared__ int okflag;
+    unsigned long long epoch = PEER ? dld_volatile_u64(a.peer.epoch_dev) : 0ull;
     const long long n = a.n, ldv = a.ldv;
     const long long nvec = n / VEC;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -142,6 +167,7 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
             }
             grid.sync();
             reduce_slots(a.partials, buf, cnt, c_s);
+            if (PEER && cnt > 0) peer_exchange(a.peer, ++epoch, c_s, cnt, stage, &okflag);
             if (blockIdx.x == 0)
                 for (int s = threadIdx.x; s < cnt; s += blockDim.x) a.h[a.j0 + s] += c_s[s];
             buf ^= 1;
@@ -237,6 +263,14 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
                 if (threadIdx.x == 0) partial_slot(a.partials, buf, 0)[blockIdx.x] = s;
                 grid.sync();
                 c_prev = reduce_slot(a.partials, buf, 0, sm);
+                if (PEER) {
+                    __syncthreads();
+                    if (threadIdx.x == 0) c_s[0] = c_prev;
+                    __syncthreads();
+                    peer_exchange(a.peer, ++epoch, c_s, 1, stage, &okflag);
+                    c_prev = c_s[0];
+                    __syncthreads();
+                }
                 j_prev = j;
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.h[j] += c_prev;
                 buf ^= 1;
@@ -291,7 +325,15 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
         double s = kry_block_sum(nrm2_part, sm);
         if (threadIdx.x == 0) partial_slot(a.partials, buf, 0)[blockIdx.x] = s;
         grid.sync();
-        const double nrm = sqrt(reduce_slot(a.partials, buf, 0, sm));
+        double nrm2 = reduce_slot(a.partials, buf, 0, sm);
+        if (PEER) {
+            __syncthreads();
+            if (threadIdx.x == 0) c_s[0] = nrm2;
+            __syncthreads();
+            peer_exchange(a.peer, ++epoch, c_s, 1, stage, &okflag);
+            nrm2 = c_s[0];
+        }
+        const double nrm = sqrt(nrm2);
         if (blockIdx.x == 0 && threadIdx.x == 0) a.nrm[0] = nrm;
         if (a.vnext != nullptr) {
             for (long long i = i0; i < nvec; i += stride) {
@@ -305,6 +347,12 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
                 for (long long i = tail0; i < n; i += blockDim.x)
                     a.vnext[i] = (T)(nrm > 0.0 ? (double)q[i] / nrm : 0.0);
         }
+    }
+    if (PEER) {
+        // every CTA read epoch_dev before the first grid.sync; one more grid-wide sync orders the
+        // write-back after all of those reads (also when no reduction was needed)
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.peer.epoch_dev = epoch;
     }
 }
 
@@ -459,11 +507,11 @@ static int max_blocks_of(K kern, int* out) {
 int kry_orth_max_blocks(int dtype, int* out) {
     int a = 0, b = 0, rc;
     if (dtype == KRY_F64) {
-        if ((rc = max_blocks_of(orth_kernel<double, 2>, &a))) return rc;
-        if ((rc = max_blocks_of(orth_kernel<double, 1>, &b))) return rc;
+        if ((rc = max_blocks_of(orth_kernel<double, 2, true>, &a))) return rc;
+        if ((rc = max_blocks_of(orth_kernel<double, 1, true>, &b))) return rc;
     } else {
-        if ((rc = max_blocks_of(orth_kernel<float, 4>, &a))) return rc;
-        if ((rc = max_blocks_of(orth_kernel<float, 1>, &b))) return rc;
+        if ((rc = max_blocks_of(orth_kernel<float, 4, true>, &a))) return rc;
+        if ((rc = max_blocks_of(orth_kernel<float, 1, true>, &b))) return rc;
     }
     *out = a < b ? a : b;
     KRY_REQUIRE(*out >= 1, "orth kernel does not fit");
@@ -497,14 +545,15 @@ static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
     bool al = kry_aligned16(a.Vdot) && kry_aligned16(a.Vsub) && kry_aligned16(a.q) && (a.ldv % W == 0) &&
               (!a.pre_vec || kry_aligned16(a.pre_vec)) && (!a.vnext || kry_aligned16(a.vnext));
     void* args[] = {&a};
+    const bool peer = a.peer.world > 1;
     if (al) {
         int g = coop_grid(a.n / W, max_blocks);
-        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)orth_kernel<T, W>, dim3(g), dim3(KRY_THREADS), args, 0,
-                                                   ctx->stream));
+        void* k = peer ? (void*)orth_kernel<T, W, true> : (void*)orth_kernel<T, W, false>;
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
     } else {
         int g = coop_grid(a.n, max_blocks);
-        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel((void*)orth_kernel<T, 1>, dim3(g), dim3(KRY_THREADS), args, 0,
-                                                   ctx->stream));
+        void* k = peer ? (void*)orth_kernel<T, 1, true> : (void*)orth_kernel<T, 1, false>;
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
     }
     KRY_LAUNCHED(ctx);
     return KRY_OK;
@@ -530,9 +579,9 @@ static int proj_launch(kry_ctx* ctx, ProjArgs<T>& p, int max_blocks) {
 
 extern "C" {
 
-int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub, long long ldv, int j0,
-                   int nv, void* q, int passes, int algo, const void* pre_vec, const double* pre_coef_dev,
-                   double* h_dev, double* nrm_dev, void* vnext) {
+static int orth_fused_impl(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub, long long ldv,
+                           int j0, int nv, void* q, int passes, int algo, const void* pre_vec,
+                           const double* pre_coef_dev, double* h_dev, double* nrm_dev, void* vnext, PeerArgs peer) {
     KRY_ENTER(ctx);
     KRY_REQUIRE(n >= 0 && q, "bad arguments");
     KRY_REQUIRE(j0 >= 0 && nv >= j0, "bad basis range");
@@ -546,16 +595,45 @@ int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const
     if (!Vsub) Vsub = q;
     if (dtype == KRY_F64) {
         OrthArgs<double> a = {n, (const double*)Vdot, (const double*)Vsub, ldv, j0, nv, passes, algo, (double*)q,
-                              (const double*)pre_vec, pre_coef_dev, h_dev, nrm_dev, (double*)vnext, ctx->d_partials};
+                              (const double*)pre_vec, pre_coef_dev, h_dev, nrm_dev, (double*)vnext, ctx->d_partials,
+                              peer};
         return orth_launch<double>(ctx, a, ctx->orth_blocks_f64);
     }
     if (dtype == KRY_F32) {
         OrthArgs<float> a = {n, (const float*)Vdot, (const float*)Vsub, ldv, j0, nv, passes, algo, (float*)q,
-                             (const float*)pre_vec, pre_coef_dev, h_dev, nrm_dev, (float*)vnext, ctx->d_partials};
+                             (const float*)pre_vec, pre_coef_dev, h_dev, nrm_dev, (float*)vnext, ctx->d_partials,
+                             peer};
         return orth_launch<float>(ctx, a, ctx->orth_blocks_f32);
     }
     kry_set_error("kry_orth_fused: unsupported dtype %d", dtype);
     return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub, long long ldv, int j0,
+                   int nv, void* q, int passes, int algo, const void* pre_vec, const double* pre_coef_dev,
+                   double* h_dev, double* nrm_dev, void* vnext) {
+    PeerArgs peer;
+    memset(&peer, 0, sizeof(peer));
+    peer.world = 1;
+    return orth_fused_impl(ctx, dtype, n, Vdot, Vsub, ldv, j0, nv, q, passes, algo, pre_vec, pre_coef_dev, h_dev,
+                           nrm_dev, vnext, peer);
+}
+
+int kry_orth_fused_dist(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const void* Vsub, long long ldv,
+                        int j0, int nv, void* q, int passes, int algo, const void* pre_vec,
+                        const double* pre_coef_dev, double* h_dev, double* nrm_dev, void* vnext, int world, int rank,
+                        unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                        unsigned long long* const* peer_flags_dev) {
+    KRY_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "bad world/rank");
+    KRY_REQUIRE(epoch_dev && peer_slots_dev && peer_flags_dev, "NULL peer argument");
+    PeerArgs peer;
+    peer.world = world;
+    peer.rank = rank;
+    peer.epoch_dev = epoch_dev;
+    peer.slots = peer_slots_dev;
+    peer.flags = peer_flags_dev;
+    return orth_fused_impl(ctx, dtype, n, Vdot, Vsub, ldv, j0, nv, q, passes, algo, pre_vec, pre_coef_dev, h_dev,
+                           nrm_dev, vnext, peer);
 }
 
 int kry_project(kry_ctx* ctx, int dtype, long long n, const void* W, long long ldw, const void* V, long long ldv,

@@ -1230,6 +1230,10 @@ class Arnoldi(object):
         else:
             self._Vs = ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A))
         self._ld = self._Vs.stride(0)
+        rf = _rightmost_factor(self.A)
+        self._halo_op = rf if (ctx.comm is not None and hasattr(rf, "_halo_args")) else None
+        if ctx.comm is not None:
+            ctx.comm.halo_ready = None
         self._Vd = self._Vs[:, :N]
         self._Pd = None
         if self.M is not None:
@@ -1333,7 +1337,7 @@ class Arnoldi(object):
                 ctx.orth_fused(V, Vsub, start, k + 1, q0, self._passes, self._algo, None,
                                nrm=nrm if fused_tail else None,
                                vnext=V[k + 1] if fused_tail else None,
-                               pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr)
+                               pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr, halo_op=self._halo_op)
         else:
             # generic inner product: the reference's loop, one reduction at a time
             if pre_vec is not None:
