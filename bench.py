@@ -171,7 +171,8 @@ def run_reference(args, rank, world):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    sys.stdout.write("\n" + json.dumps(line) + "\n")
+    sys.stdout.flush()
 
 
 def config_dict(args, world):
@@ -375,7 +376,8 @@ def run_b200(args, rank, world, local_rank):
             "final_resnorm": float(hist[-1][-1]),
         }
         line.update(extra)
-        print(json.dumps(line))
+        sys.stdout.write("\n" + json.dumps(line) + "\n")
+        sys.stdout.flush()
     if dist is not None:
         dist.destroy_process_group()
 
@@ -430,6 +432,7 @@ def run_e2e(args, kp, torch, A, b, x_dev):
 
 
 def main():
+    os.environ.setdefault("NCCL_DEBUG", "WARN")     # keep NCCL's version banner off stdout (one JSON line only)
     args = parse()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
