@@ -284,7 +284,10 @@ class DistCsrOperator(utils._DeviceOperator):
         self.plan = HaloPlan(A_rows, part)
         self.N_global = part.N
         super(DistCsrOperator, self).__init__((part.nloc, part.nloc), A_rows.dtype)
-        self._ext_len = self.plan.ext
+        # peers address each other's basis rows with ONE element offset (row index * leading
+        # dimension), so the leading dimension must be identical on every rank: size the halo part
+        # of a row for the largest halo of any rank
+        self._ext_len = part.block + max(self.comm.all_gather_object(int(self.plan.nhalo)))
         self._devcache = {}
         self._xbuf = {}
         self._napply = 0
@@ -310,7 +313,7 @@ class DistCsrOperator(utils._DeviceOperator):
         key = (td, self._napply & 1)
         buf = self._xbuf.get(key)
         if buf is None:
-            buf = self.comm.shared_basis(1, _roundup(self.plan.ext, 32), td)
+            buf = self.comm.shared_basis(1, _roundup(self._ext_len, 32), td)
             self._xbuf[key] = buf
         return buf
 

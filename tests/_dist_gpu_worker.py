@@ -15,8 +15,16 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 def main():
     lr = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(lr)
-    dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    ws = int(os.environ.get("WORLD_SIZE", "1"))
+    if torch.cuda.device_count() >= ws:
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+    else:
+        # fewer GPUs than ranks: all ranks share the available device(s) (CUDA IPC works between
+        # processes on one GPU; the driver time-slices the spinning kernels) -- slow, but it
+        # exercises the >2-rank protocol (middle ranks with two-sided halos) on a 1-GPU box
+        torch.cuda.set_device(lr % torch.cuda.device_count())
+        dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
     import krypy_b200 as kp
     from krypy_b200 import dist as kd, problems, _device
@@ -101,6 +109,7 @@ def main():
 
     torch.cuda.synchronize()
     dist.barrier()
+    kd.shutdown()
     dist.destroy_process_group()
     print("rank %d ok" % rank)
 
