@@ -283,7 +283,6 @@ def run_b200(args, rank, world, local_rank):
         torch.cuda.synchronize()
         ctx.timer = None
         launches = ctx.launch_count() * args.steps
-        prof_ms = None
     if dist is not None:
         tms = torch.tensor([ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tms, op=dist.ReduceOp.MAX)

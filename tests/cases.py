@@ -125,8 +125,6 @@ def case_inputs(name):
         c["ls"] = dict(self_adjoint=True, positive_definite=True)
         c["solver"] = "cg"
         c["kw"] = dict(tol=1e-9, maxiter=80, explicit_residual=True)
-    elif name == "convdiff_defl_minres_cg":
-        raise KeyError(name)
     elif name in ("lap2d_defl_cg", "lap2d_defl_minres"):
         n = 14
         c["A"] = problems.laplace2d(n)
