@@ -147,6 +147,10 @@ class Context(object):
     def sync(self):
         check(self.lib.kry_sync(self.h))
 
+    def event(self):
+        """a CUDA event on the context's stream (record() / synchronize())"""
+        return torch().cuda.Event()
+
     def launch_count(self):
         return int(self.lib.kry_launch_count(self.h))
 

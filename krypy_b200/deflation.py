@@ -136,7 +136,7 @@ class _DeflationMixin(object):
         """host (d, ncols) array of the raw first-application coefficients."""
         if self._d == 0 or self._ncols == 0:
             return numpy.zeros((self._d, self._ncols))
-        raw = self._Craw[: self._ncols].cpu().numpy().T              # (d, ncols)
+        raw = self._Craw[: self._ncols].cpu().numpy().T.copy()       # (d, ncols)
         WR = self.projection.WR
         return WR.T.conj().dot(raw) if WR is not None else raw       # Ya = WR^H c, utils.py:544-545
 

@@ -587,7 +587,7 @@ class Minres(_KrylovSolver):
                 resid = float(mb[0])
                 lz._finish(k, mb[6:8].copy())
             else:
-                hc = lz._hcol[: k + 2].cpu().numpy()                 # synchronises
+                hc = lz._hcol[: k + 2].cpu().numpy().copy()          # synchronises
                 lz._hcol[: k + 2].zero_()
                 resid = float(mb[0])
                 lz._finish(k, hc)
@@ -697,7 +697,7 @@ class Gmres(_KrylovSolver):
         is_lanczos = self.ortho == "lanczos"
         t = _device.torch()
         HALF = 8192                          # two mailbox halves: step k uses half k & 1
-        events = (t.cuda.Event(), t.cuda.Event())
+        events = (ctx.event(), ctx.event())
         # Look-ahead: step k+1 is enqueued BEFORE the host waits for step k, so the device
         # never idles on the host's convergence test.  An Arnoldi step does not depend on the
         # host's decision; if the loop ends at k the speculative step is simply discarded

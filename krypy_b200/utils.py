@@ -868,7 +868,7 @@ def _qr_dev(Xd, ip_B=None, reorthos=1):
                     ctx.axpy_dev(tmp, -1.0, Q[j], qi)
             _ip_coef(Q[i:i + 1], Q[i:i + 1], ip_B, Rrows[i][i:], post=1)
         ctx.sync()
-        col = Rrows[i][: i + 1].cpu().numpy()
+        col = Rrows[i][: i + 1].cpu().numpy().copy()
         R[: i + 1, i] = col
         if R[i, i] >= 1e-15:                                        # utils.py:705-706
             ctx.scale_dev(Rrows[i][i:], 1, 1.0, qi, qi)
@@ -1397,7 +1397,7 @@ class Arnoldi(object):
             ctx.sync()
             self._finish(k, ctx.mailbox[6:8].copy())
         else:
-            hc = self._hcol[: k + 2].cpu().numpy()                   # synchronising D2H of k+2 doubles
+            hc = self._hcol[: k + 2].cpu().numpy().copy()            # synchronising D2H of k+2 doubles
             self._hcol[: k + 2].zero_()
             self._finish(k, hc)
 

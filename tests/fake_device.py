@@ -1,0 +1,302 @@
+"""TEST DOUBLE of the device layer -- test infrastructure, never part of the product.
+
+``krypy_b200`` has no CPU path: every N-sized operation is a CUDA kernel behind the C ABI.  To
+exercise the HOST logic (solver control flow, restart/deflation bookkeeping, attribute semantics,
+exception policy) in the CPU-only test tier, the tests in ``tests/test_host_logic_cpu.py`` swap
+``krypy_b200._device.Context`` for the ``FakeContext`` below, whose methods restate the CONTRACT of
+each C-ABI entry point (include/krypy_b200.h) in numpy on torch CPU tensors -- including the
+mailbox layouts, the "+=" accumulation into h and the zeroing done by the device recurrences.
+
+Nothing under ``krypy_b200/`` imports this file, and no GPU-marked test uses it: the parity tests
+proper run the real kernels.  What a green run here proves is that the Python host layer drives the
+C ABI consistently; it says nothing about the kernels.
+"""
+import ctypes
+
+import numpy as np
+import scipy.sparse as sp
+import torch
+
+from krypy_b200 import _device
+from krypy_b200._lib import KRY_ORTH_CGS
+
+
+def _view(x, n=None):
+    """numpy float64 view of a CPU tensor or of a raw address (ints come from pointer arithmetic)"""
+    if x is None:
+        return None
+    if isinstance(x, int):
+        assert n is not None
+        return np.ctypeslib.as_array(ctypes.cast(x, ctypes.POINTER(ctypes.c_double)), shape=(n,))
+    return x.detach().numpy()
+
+
+def _drotg(a, b):
+    """csrc/kry_small.cu: kry_drotg"""
+    an, bn = abs(a), abs(b)
+    if bn == 0.0:
+        return 1.0, 0.0
+    if an == 0.0:
+        return 0.0, 1.0
+    scl = min(4.4942328371557898e+307, max(2.2250738585072014e-308, an, bn))
+    sigma = np.copysign(1.0, a) if an > bn else np.copysign(1.0, b)
+    r = sigma * (scl * np.sqrt((a / scl) ** 2 + (b / scl) ** 2))
+    return a / r, b / r
+
+
+def _rot(c, s, x0, x1):
+    return c * x0 + s * x1, -s * x0 + c * x1
+
+
+class _Event(object):
+    def record(self):
+        pass
+
+    def synchronize(self):
+        pass
+
+
+class FakeContext(object):
+    def __init__(self):
+        self.device = torch.device("cpu")
+        self.mailbox = np.zeros(16384)
+        self.timer = None
+        self.comm = None
+        self.sm_count = 148
+        self.calls = {}
+
+    def _count(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    # ---- plumbing ----
+    def use_current_stream(self):
+        pass
+
+    def sync(self):
+        pass
+
+    def event(self):
+        return _Event()
+
+    def launch_count(self):
+        return sum(self.calls.values())
+
+    def reset_launch_count(self):
+        self.calls = {}
+
+    def empty(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def zeros(self, shape, dtype):
+        return torch.zeros(shape, dtype=dtype)
+
+    def scalars(self, n):
+        return torch.zeros(n, dtype=torch.float64)
+
+    def alloc_basis(self, rows, N, dtype, op=None):
+        ld = (int(N) + 31) // 32 * 32
+        return torch.zeros((int(rows), ld), dtype=dtype)
+
+    def to_block(self, X, dtype):
+        if isinstance(X, torch.Tensor):
+            Xt = X.detach().to(dtype=dtype)
+            Xt = Xt.reshape(1, -1) if Xt.dim() == 1 else Xt.t()
+            return Xt.contiguous().clone()
+        X = np.asarray(X)
+        if np.iscomplexobj(X):
+            raise NotImplementedError("complex vectors are not supported by the device path")
+        if X.ndim == 1:
+            X = X.reshape(-1, 1)
+        return torch.from_numpy(np.ascontiguousarray(X.T, dtype=_device.torch_to_np_dtype(dtype))).clone()
+
+    def to_numpy(self, Xd):
+        return np.ascontiguousarray(Xd.detach().numpy().T)
+
+    def upload_csr(self, A, dtype):
+        A = sp.csr_matrix(A)
+        npdt = _device.torch_to_np_dtype(dtype)
+        return _device.CsrDev(torch.from_numpy(A.indptr.astype(np.int32)), torch.from_numpy(A.indices.astype(np.int32)),
+                              torch.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)), A.shape)
+
+    # ---- operators (kry_spmv_csr, kry_gemv_dense, kry_diag_mul) ----
+    def spmv(self, A, x, y, w=None, dot_out=None):
+        self._count("spmv")
+        M = sp.csr_matrix((A.vals.numpy().astype(np.float64), A.colidx.numpy(), A.rowptr.numpy()), shape=A.shape)
+        r = M @ x.numpy().astype(np.float64)
+        if y is not None:
+            y.copy_(torch.from_numpy(r).to(y.dtype))
+        if w is not None:
+            dot_out[0] = float(w.numpy().astype(np.float64) @ r)
+
+    def gemv(self, A, x, y):
+        self._count("gemv")
+        y.copy_(torch.from_numpy(A.numpy().astype(np.float64) @ x.numpy().astype(np.float64)).to(y.dtype))
+
+    def diag_mul(self, d, x, y):
+        self._count("diag_mul")
+        y.copy_((d.double() * x.double()).to(y.dtype))
+
+    # ---- elementwise (kry_axpby, kry_axpy_dev, kry_scale_dev) ----
+    def axpby(self, a, x, b, y, z):
+        self._count("axpby")
+        r = float(a) * x.double()
+        if y is not None:
+            r = r + float(b) * y.double()
+        z.copy_(r.to(z.dtype))
+
+    def axpy_dev(self, coef, sign, x, y):
+        self._count("axpy_dev")
+        y.copy_((y.double() + float(sign) * float(coef[0]) * x.double()).to(y.dtype))
+
+    def scale_dev(self, s, divide, mul, x, out):
+        self._count("scale_dev")
+        v = float(mul) * x.double()
+        out.copy_((v / float(s[0]) if divide else v * float(s[0])).to(out.dtype))
+
+    # ---- tall-skinny (kry_block_dot, kry_block_axpy, kry_block_combine) ----
+    def block_dot(self, V, nv, q, out, post=0, acc=None):
+        self._count("block_dot")
+        o = _view(out, nv)
+        a = _view(acc, nv)
+        qq = q.numpy().astype(np.float64)
+        for j in range(int(nv)):
+            s = float(V[j].numpy().astype(np.float64) @ qq)
+            if post == 1:
+                s = float(np.sqrt(abs(s)))
+            o[j] = s
+            if a is not None:
+                a[j] += s
+
+    def block_axpy(self, V, nv, coef, sign, q):
+        self._count("block_axpy")
+        r = q.double()
+        for j in range(int(nv)):
+            r = r + float(sign) * float(coef[j]) * V[j].double()
+        q.copy_(r.to(q.dtype))
+
+    def block_combine(self, V, nv, coef, x0, out):
+        self._count("block_combine")
+        s = torch.zeros(out.shape, dtype=torch.float64)
+        for j in range(int(nv)):
+            s = s + float(coef[j]) * V[j].double()
+        if x0 is not None:
+            s = x0.double() + s
+        out.copy_(s.to(out.dtype))
+
+    # ---- kry_orth_fused ----
+    def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
+                   pre_coef=None, h_ptr=None, halo_op=None):
+        self._count("orth_fused")
+        hv = _view(h_ptr if h_ptr is not None else h, max(int(nv), 1)) if (h is not None or h_ptr is not None) else None
+        qq = q.double()
+        if pre_vec is not None:
+            qq = (qq - float(pre_coef[0]) * pre_vec.double()).to(q.dtype).double()
+        for _ in range(int(passes)):
+            if algo == KRY_ORTH_CGS:
+                cs = [float(Vdot[j].double() @ qq) for j in range(int(j0), int(nv))]
+                for j, c in zip(range(int(j0), int(nv)), cs):
+                    hv[j] += c
+                    qq = qq - c * Vsub[j].double()
+                qq = qq.to(q.dtype).double()
+            else:
+                for j in range(int(j0), int(nv)):
+                    c = float(Vdot[j].double() @ qq)
+                    hv[j] += c
+                    qq = (qq - c * Vsub[j].double()).to(q.dtype).double()
+        q.copy_(qq.to(q.dtype))
+        if nrm is not None:
+            n2 = float(np.sqrt(float(qq @ qq)))
+            nrm[0] = n2
+            if vnext is not None:
+                vnext.copy_((qq / n2 if n2 > 0 else torch.zeros_like(qq)).to(vnext.dtype))
+
+    # ---- kry_project ----
+    def project(self, W, V, d, a, Q, R, iterations, c_first):
+        import scipy.linalg
+        self._count("project")
+        aa = a.double()
+        Wn = W[: int(d)].double().numpy()
+        Vn = V[: int(d)].double().numpy()
+        for it in range(int(iterations)):
+            c = Wn @ aa.numpy()
+            if it == 0 and c_first is not None:
+                c_first[: int(d)] = torch.from_numpy(c)
+            if Q is not None:
+                c = scipy.linalg.solve_triangular(R.numpy(), Q.numpy().T @ c)
+            aa = aa - torch.from_numpy(Vn.T @ c)
+        a.copy_(aa.to(a.dtype))
+
+    # ---- small recurrences ----
+    def givens_update(self, k, hcol, rcol, cs, y, off=0):
+        self._count("givens")
+        h = hcol.numpy()
+        r = h[: k + 2].copy()
+        mb = self.mailbox
+        mb[off + 1: off + k + 3] = r
+        h[: k + 2] = 0.0
+        c_ = cs.numpy()
+        for i in range(k):
+            r[i], r[i + 1] = _rot(c_[2 * i], c_[2 * i + 1], r[i], r[i + 1])
+        c, s = _drotg(r[k], r[k + 1])
+        c_[2 * k], c_[2 * k + 1] = c, s
+        r[k], r[k + 1] = _rot(c, s, r[k], r[k + 1])
+        yy = y.numpy()
+        yy[k], yy[k + 1] = _rot(c, s, yy[k], yy[k + 1])
+        mb[off] = abs(yy[k + 1])
+        rcol.numpy()[: k + 2] = r
+        mb[off + k + 3: off + 2 * k + 5] = r
+
+    def tri_solve(self, k, R, y, out):
+        import scipy.linalg
+        self._count("tri_solve")
+        out[: int(k)] = torch.from_numpy(scipy.linalg.solve_triangular(R.numpy()[:k, :k], y.numpy()[:k]))
+
+    def minres_recur(self, k, h3, st, shift=1, off=0):
+        self._count("minres_recur")
+        h = h3.numpy()
+        s_ = st.numpy()
+        R0, R1 = 0.0, (h[0] if k > 0 else 0.0)
+        if s_[2] != 0.0:
+            R0, R1 = _rot(s_[0], s_[1], R0, R1)
+        R2, R3 = h[1], h[2]
+        if s_[5] != 0.0:
+            R1, R2 = _rot(s_[3], s_[4], R1, R2)
+        s_[0:3] = s_[3:6]
+        c, s = _drotg(R2, R3)
+        s_[3], s_[4], s_[5] = c, s, 1.0
+        R2 = c * R2 + s * R3
+        y0, y1 = _rot(c, s, s_[6], 0.0)
+        s_[8:12] = [R0, R1, R2, y0]
+        s_[6] = y1
+        mb = self.mailbox
+        mb[off: off + 8] = [abs(y1), R0, R1, R2, y0, h[0], h[1], h[2]]
+        if shift:
+            h[0] = h[2]
+            h[1] = 0.0
+
+    def minres_update(self, v, w0, w1, yk, st):
+        self._count("minres_update")
+        s_ = st.numpy()
+        z = ((v.double() - s_[8] * w0.double() - s_[9] * w1.double()) / s_[10]).to(w0.dtype)
+        w0.copy_(z)
+        yk.copy_((yk.double() + s_[11] * z.double()).to(yk.dtype))
+
+    def cg_update(self, Ap, p, yk, r, z, dinv, rho, pAp, off=0):
+        self._count("cg_update")
+        pap = float(pAp[0])
+        alpha = float(rho) / pap
+        yk.copy_((yk.double() + alpha * p.double()).to(yk.dtype))
+        r.copy_((r.double() - alpha * Ap.double()).to(r.dtype))
+        if dinv is not None:
+            z.copy_((dinv.double() * r.double()).to(z.dtype))
+            rz = float(r.double() @ z.double())
+        else:
+            rz = float(r.double() @ r.double())
+        self.mailbox[off: off + 3] = [rz, alpha, pap]
+
+
+def install(monkeypatch):
+    """swap the product's device context for the test double (pytest monkeypatch fixture)"""
+    fake = FakeContext()
+    monkeypatch.setattr(_device.Context, "get", classmethod(lambda cls, device=None: fake))
+    return fake

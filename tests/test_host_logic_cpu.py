@@ -1,0 +1,109 @@
+"""CPU tier: the product's HOST logic (krypy_b200/{utils,linsys,deflation,_convenience}.py) driven
+end to end over a numpy test double of the device layer (tests/fake_device.py) and compared with the
+reference fixtures.  This validates the control flow, bookkeeping and attribute semantics of the
+Python layer without a GPU; the kernels themselves are covered by the -m gpu tests."""
+import warnings
+
+import numpy as np
+import pytest
+
+import cases
+import fake_device
+import runners
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    return fake_device.install(monkeypatch)
+
+
+def _check_history(got, ref, rtol=1e-10, atol=5e-13):   # explicit entries of the kappa=1e5 case: cancellation noise
+    assert got.shape == ref.shape, (got.shape, ref.shape)
+    err = np.abs(got - ref)
+    bound = rtol * np.abs(ref) + atol
+    assert np.all(err <= bound), (int(np.argmax(err / bound)), float((err / bound).max()))
+
+
+@pytest.mark.parametrize("name", cases.ALL_CASES)
+def test_host_logic_reproduces_reference_fixtures(fake, name):
+    gold = runners.load_golden(name)
+    got = runners.run_product(name)
+    assert bool(got["converged"]) == bool(gold["converged"])
+    rtol = 1e-5 if name == "shifted_minres_ipB" else 1e-10      # fp32 INPUTS: see test_solvers_gpu.py
+    _check_history(got["resnorms"], gold["resnorms"], rtol=rtol)
+    scale = np.abs(gold["xk"]).max() + 1e-300
+    assert np.abs(got["xk"] - gold["xk"]).max() <= max(1e-8, rtol) * scale
+    for k in ("iter", "V_shape"):
+        if k in gold:
+            assert np.array_equal(got[k], gold[k]), k
+    rn = gold["resnorms"]
+    ngood = int(np.argmax(rn < 1e-7)) if np.any(rn < 1e-7) else len(rn)
+    for k in ("H", "C", "V_colsum_abs"):
+        if k in gold:
+            assert got[k].shape == gold[k].shape, k
+            nc = min(max(ngood - 1, 0), gold[k].shape[-1])
+            a, b = got[k][..., :nc], gold[k][..., :nc]
+            if a.size:
+                assert np.abs(a - b).max() <= 1e-6 * (np.abs(b).max() + 1e-300), k
+    for k in ("E", "UMlr", "rhos"):
+        if k in gold:
+            np.testing.assert_allclose(got[k], gold[k], rtol=1e-8, atol=1e-13 * (np.abs(gold[k]).max() + 1e-300))
+    # the host layer went through the device entry points, not around them
+    assert fake.launch_count() > 0
+
+
+def test_host_logic_block_variants_and_lookahead(fake):
+    gold = runners.load_golden("lap2d_gmres30")
+    for ortho in ("cgs", "cgs2", "dmgs"):
+        got = runners.run_product("lap2d_gmres30", ortho=ortho)
+        _check_history(got["resnorms"], gold["resnorms"])
+    # explicit_residual=True disables the look-ahead: same history
+    got = runners.run_product("lap2d_gmres30", explicit_residual=True)
+    assert got["resnorms"].shape == gold["resnorms"].shape
+    np.testing.assert_allclose(got["resnorms"], gold["resnorms"], rtol=1e-6)
+
+
+def test_host_logic_known_answers_and_semantics(fake):
+    """reference test/test_convenience_wrappers.py numbers + SURVEY 3.6 traps on the CPU tier"""
+    import krypy_b200 as kp
+    A = np.diag([1.0e-3] + list(range(2, 101))).astype(float)
+    b = np.ones(100)
+    ref = {kp.cg: [1004.1873775173957, 1000.0003174916551, 999.9999999997555],
+           kp.gmres: [1004.1873724888546, 1000.0003124630923, 999.999994971191],
+           kp.minres: [1004.187372488912, 1000.0003124632159, 999.9999949713145]}
+    for fn, r in ref.items():
+        sol, _ = fn(A, b, inner_product=np.dot)
+        assert sol.shape == b.shape
+        assert abs(np.sum(np.abs(sol)) - r[0]) < 1e-11 * r[0]
+        assert abs(np.sqrt(sol @ sol) - r[1]) < 1e-11 * r[1]
+        assert abs(np.max(np.abs(sol)) - r[2]) < 1e-11 * r[2]
+    sol, _ = kp.cg(A, b, inner_product=lambda x, y: np.dot(x, y))     # callable ip_B path
+    assert abs(np.sum(np.abs(sol)) - 1004.1873775173957) < 1e-11 * 1004.1873775173957
+    ls = kp.linsys.LinearSystem(A, b, self_adjoint=True, positive_definite=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for cls, it in ((kp.linsys.Cg, 55), (kp.linsys.Minres, 54), (kp.linsys.Gmres, 54)):
+            s = cls(ls, store_arnoldi=True)
+            assert s.iter == it and s.V.shape == (100, 56) and s.H.shape == (56, 55)
+        for cls, vs, hs in ((kp.linsys.Cg, (100, 10), (10, 9)), (kp.linsys.Minres, (100, 11), (11, 10)),
+                            (kp.linsys.Gmres, (100, 11), (11, 10))):
+            with pytest.raises(kp.utils.ConvergenceError) as ei:
+                cls(ls, maxiter=10, store_arnoldi=True)
+            s = ei.value.solver
+            assert len(s.resnorms) - 1 == 10 and s.iter == 9 and s.V.shape == vs and s.H.shape == hs
+    z = kp.linsys.Gmres(kp.linsys.LinearSystem(A, np.zeros((100, 1))))
+    assert z.resnorms == [0.0] and np.all(z.xk == 0)
+    d = kp.deflation.DeflatedGmres(kp.linsys.LinearSystem(A, b), U=np.eye(100, 2), store_arnoldi=True)
+    n = d.H.shape[1]
+    assert d.C.shape == (2, n) and d.E.shape == (2, 2) and d.B_.shape == (n + 1, 2)
+    # restart loop hands the residual over and reuses the workspace
+    r = kp.linsys.RestartedGmres(ls, maxiter=30, max_restarts=10)
+    assert r.resnorms[-1] <= 1e-5
+    with pytest.raises(kp.utils.ConvergenceError):
+        kp.linsys.RestartedGmres(ls, maxiter=5, max_restarts=1)
+    with pytest.raises(NotImplementedError):
+        kp.linsys.LinearSystem(A.astype(complex), b)
+    with pytest.raises(NotImplementedError):
+        kp.linsys.Gmres(ls, ortho="house")
+    with pytest.raises(kp.utils.ArgumentError):
+        kp.linsys.Gmres(ls, ortho="nope")
