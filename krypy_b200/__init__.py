@@ -7,8 +7,8 @@ the ``cg / minres / gmres`` convenience functions.  All N-sized arithmetic runs
 in hand-written CUDA kernels (krypy_b200/csrc, C ABI in include/krypy_b200.h);
 there is no CPU fallback.
 """
-from . import deflation, linsys, problems, utils
+from . import deflation, linsys, problems, recycling, utils
 from ._convenience import cg, gmres, minres
 
 __version__ = "0.1.0"
-__all__ = ["linsys", "deflation", "utils", "problems", "cg", "minres", "gmres", "__version__"]
+__all__ = ["linsys", "deflation", "utils", "recycling", "problems", "cg", "minres", "gmres", "__version__"]

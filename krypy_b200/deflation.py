@@ -13,7 +13,7 @@ from . import _device, linsys, utils
 from .utils import _ctx, _is_dev
 
 __all__ = ["DeflatedCg", "DeflatedMinres", "DeflatedGmres", "_DeflationMixin",
-           "ObliqueProjection", "_Projection"]
+           "ObliqueProjection", "_Projection", "Ritz"]
 
 
 class _Projection(utils.Projection):
@@ -27,11 +27,12 @@ class ObliqueProjection(_Projection):
         """Oblique projection for left deflation (krypy/deflation.py:32-56)."""
         ctx = _ctx()
         self.linear_system = ls = linear_system
-        if _is_dev(U):
-            d = U.shape[0]
-            Ud = U.to(ls._td)
+        if isinstance(U, utils.DeviceBlock):
+            Ud = U.block.to(ls._td)                # vector-major (d, N) block already in HBM
+            d = Ud.shape[0]
         else:
-            U = numpy.asarray(U)
+            if not _is_dev(U):
+                U = numpy.asarray(U)
             (N, d) = U.shape
             Ud = ctx.to_block(U, ls._td)
         # orthogonalize U in the Minv-inner-product (deflation.py:40)
@@ -104,7 +105,7 @@ class _DeflationMixin(object):
             U = numpy.zeros((linear_system.N, 0))
         if projection_kwargs is None:
             projection_kwargs = {}
-        if not _is_dev(U):
+        if not _is_dev(U) and not isinstance(U, utils.DeviceBlock):
             U = numpy.asarray(U)
             if U.ndim == 1:
                 U = U.reshape(-1, 1)
@@ -126,7 +127,7 @@ class _DeflationMixin(object):
         self._Craw = None      # device (maxcols, d): raw W^H (MlAMr v) of each application
         self._C_cache = None
         self._B_ = None
-        udtype = _device.torch_to_np_dtype(U.dtype) if _is_dev(U) else U.dtype
+        udtype = _device.torch_to_np_dtype(U.dtype) if _is_dev(U) else U.dtype    # DeviceBlock.dtype is numpy
         if numpy.dtype(udtype).kind not in "fc":
             udtype = numpy.float64
         super(_DeflationMixin, self).__init__(linear_system, dtype=udtype, *args, **kwargs)
@@ -203,14 +204,24 @@ class _DeflationMixin(object):
         (n_, n) = self.H.shape
         ls = self.linear_system
         if self._B_ is None or self._B_.shape[1] < n_:
+            Vd = self._basis_dev()[:n_]                      # the basis is still in HBM: no PCIe round trip
+            AUd = self.projection._AUd
             if ls.self_adjoint:
                 self._B_ = self.C.T.conj()
                 if n_ > n:
-                    self._B_ = numpy.vstack(
-                        [self._B_, utils.inner(self.V[:, [-1]], self.projection.AU, ip_B=ls.ip_B)])
+                    last = utils._inner_dev(Vd[n_ - 1:n_], AUd, ls.ip_B).cpu().numpy().copy()
+                    self._B_ = numpy.vstack([self._B_, last])
             else:
-                self._B_ = utils.inner(self.V, self.projection.AU, ip_B=ls.ip_B)
+                self._B_ = utils._inner_dev(Vd, AUd, ls.ip_B).cpu().numpy().copy()
         return self._B_
+
+    def _basis_dev(self):
+        """device block of the Arnoldi/Lanczos basis of the finished solve"""
+        if hasattr(self, "arnoldi"):
+            return self.arnoldi._Vd
+        if hasattr(self, "lanczos"):
+            return self.lanczos._Vd
+        return self._Vd
 
     def estimate_time(self, nsteps, ndefl, deflweight=1.0):
         """krypy/deflation.py:191-233."""
@@ -267,3 +278,141 @@ class DeflatedMinres(_DeflationMixin, linsys.Minres):
 
 class DeflatedGmres(_DeflationMixin, linsys.Gmres):
     """Deflated preconditioned GMRES (krypy/deflation.py:276-283)."""
+
+
+class Ritz(object):
+    """Ritz / harmonic Ritz pairs of a deflated solve (krypy/deflation.py:737-869).
+
+    The (n+m)-sized eigenproblem is host algebra on the small matrices the solve left behind
+    (``H``, ``B_``, ``C``, ``E``; ``F = <AU, M AU>`` is one device block product); the N-sized part --
+    the Ritz vectors ``[V_n, U] coeffs`` and the explicit residuals -- runs on the device.
+    ``get_vectors`` returns an ``(N, k)`` numpy array like the reference; ``get_vectors_dev`` keeps
+    the block in HBM (``utils.DeviceBlock``) so a recycled deflation space never crosses PCIe."""
+
+    def __init__(self, deflated_solver, mode="ritz"):
+        import scipy.linalg
+        self._solver = sv = deflated_solver
+        ls = sv.linear_system
+        self.values = None
+        self.coeffs = None
+        Hx = numpy.asarray(sv.H)
+        (n1, n) = Hx.shape
+        Hn = Hx[:n, :n]
+        pr = sv.projection
+        if not isinstance(pr, ObliqueProjection):
+            raise utils.ArgumentError("Invalid projection used in deflated_solver. Valid are ObliqueProjection")
+        m = pr._k
+        if n + m == 0:                                           # deflation.py:766-770
+            self.values = numpy.zeros((0,))
+            self.coeffs = numpy.zeros((0,))
+            self.resnorms = numpy.zeros((0,))
+            return
+        E, C = sv.E, sv.C
+        EiC = numpy.linalg.solve(E, C) if m > 0 else C          # deflation.py:775-778
+        Bx = sv.B_
+        Bn = Bx[:n, :]
+        eye, zer = numpy.eye, numpy.zeros
+        Mmat = numpy.block([[Hn + Bn.dot(EiC), Bn], [C, E]])      # deflation.py:783
+        if m > 0:
+            MAUd = ls.M._apply_dev(pr._AUd)
+            F = utils._inner_dev(pr._AUd, MAUd, ls.ip_B).cpu().numpy().copy()
+        else:
+            F = zer((0, 0))
+        S = numpy.block([[eye(n1), Bx, zer((n1, m))],
+                         [Bx.T.conj(), F, E],
+                         [zer((m, n1)), E.T.conj(), eye(m)]])    # deflation.py:785-791
+        eig = scipy.linalg.eigh if ls.self_adjoint else scipy.linalg.eig
+        if mode == "ritz":
+            self.values, self.coeffs = eig(Mmat)
+        elif mode == "harmonic":
+            L = numpy.block([[Hx, zer((n1, m))], [EiC, eye(m)]])
+            K = numpy.block([[eye(n1), Bx], [Bx.T.conj(), F]])
+            sig, self.coeffs = eig(Mmat.T.conj(), L.T.conj().dot(K.dot(L)))
+            self.values = numpy.zeros(m + n, dtype=sig.dtype)
+            tiny = numpy.abs(sig) < numpy.finfo(float).eps
+            self.values[~tiny] = 1.0 / sig[~tiny]
+            self.values[tiny] = numpy.inf
+        else:
+            raise utils.ArgumentError("Invalid value  '%s' for 'mode'. Valid are ritz and harmonic." % mode)
+        self.coeffs = self.coeffs / numpy.linalg.norm(self.coeffs, 2, axis=0, keepdims=True)   # :814-815
+        # residual norms of the Ritz pairs from the small matrices (deflation.py:817-834)
+        self.resnorms = numpy.zeros(m + n)
+        for i in range(n + m):
+            mu = self.values[i]
+            y = self.coeffs[:, [i]]
+            G = numpy.block([[Hx - mu * eye(n1, n), zer((n1, m))],
+                             [EiC, eye(m)],
+                             [zer((m, n)), -mu * eye(m)]])
+            Gy = G.dot(y)
+            self.resnorms[i] = numpy.sqrt(numpy.abs((Gy.T.conj().dot(S.dot(Gy)))[0, 0]))
+
+    # -- N-sized parts on the device -------------------------------------------------------
+    def _real_coeffs(self, indices, realify):
+        co = self.coeffs if indices is None else self.coeffs[:, indices]
+        if co.ndim == 1:
+            co = co.reshape(-1, 1)
+        if numpy.iscomplexobj(co):
+            if numpy.abs(co.imag).max() <= 1e-14 * max(numpy.abs(co).max(), 1e-300):
+                return numpy.ascontiguousarray(co.real)
+            if not realify:
+                raise NotImplementedError(
+                    "complex Ritz vectors are not supported by the (real) device path; pass realify=True to "
+                    "get a real basis of the same space (select conjugate pairs together; SURVEY F10)")
+            # [Re, Im] spans the same space as the selected vectors when conjugate pairs are selected
+            # together; a pivoted QR of the coefficients keeps the k most independent combinations
+            import scipy.linalg
+            k = co.shape[1]
+            RI = numpy.hstack([co.real, co.imag])
+            _, _, piv = scipy.linalg.qr(RI, mode="economic", pivoting=True)
+            return numpy.ascontiguousarray(RI[:, piv[:k]])
+        return numpy.ascontiguousarray(co)
+
+    def get_vectors_dev(self, indices=None, realify=False):
+        """Ritz vectors as a vector-major device block wrapped in ``utils.DeviceBlock``."""
+        sv = self._solver
+        ctx = _ctx()
+        t = _device.torch()
+        (n1, n) = numpy.asarray(sv.H).shape
+        pr = sv.projection
+        m = pr._k
+        co = self._real_coeffs(indices, realify)
+        k = co.shape[1]
+        Vd = sv._basis_dev()
+        N = sv.linear_system.N
+        out = ctx.empty((k, N), sv._td)
+        cd = t.from_numpy(numpy.ascontiguousarray(co.T, dtype=numpy.float64)).to(ctx.device)   # (k, n+m)
+        for j in range(k):
+            ctx.block_combine(Vd, n, cd[j][:n] if n else None, None, out[j])                 # V[:, :n] y
+            if m:
+                ctx.block_axpy(pr._Ud, m, cd[j][n:], 1.0, out[j])                             # + U z
+        return utils.DeviceBlock(out)
+
+    def get_vectors(self, indices=None, realify=False):
+        """krypy/deflation.py:840-847."""
+        blk = self.get_vectors_dev(indices, realify)
+        return _ctx().to_numpy(blk.block).astype(self._solver.dtype, copy=False)
+
+    def get_explicit_residual(self, indices=None):
+        """krypy/deflation.py:849-855 (real Ritz pairs)."""
+        ctx = _ctx()
+        blk = self.get_vectors_dev(indices).block
+        vals = self.values if indices is None else self.values[indices]
+        vals = numpy.atleast_1d(vals)
+        if numpy.iscomplexobj(vals):
+            if numpy.abs(vals.imag).max() > 0:
+                raise NotImplementedError("complex Ritz values are not supported by the (real) device path")
+            vals = vals.real
+        res = self._solver.linear_system.MlAMr._apply_dev(blk)
+        for j in range(blk.shape[0]):
+            ctx.axpby(1.0, res[j], -float(vals[j]), blk[j], res[j])
+        return res
+
+    def get_explicit_resnorms(self, indices=None):
+        """krypy/deflation.py:857-869."""
+        ls = self._solver.linear_system
+        res = self.get_explicit_residual(indices)
+        out = numpy.zeros(res.shape[0])
+        for j in range(res.shape[0]):
+            rj = res[j:j + 1]
+            out[j] = linsys._norm_dev(rj, ls.M._apply_dev(rj), ls.ip_B)
+        return out

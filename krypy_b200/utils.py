@@ -27,7 +27,7 @@ __all__ = [
     "MatrixLinearOperator", "DiagonalLinearOperator", "TimedLinearOperator", "Projection",
     "Timer", "Timings", "arnoldi", "arnoldi_res", "get_linearoperator", "inner", "ip_euclid",
     "norm", "norm_squared", "orthonormality", "qr", "shape_vec", "shape_vecs",
-    "find_common_dtype",
+    "find_common_dtype", "DeviceBlock", "SolverWorkspace",
 ]
 
 
@@ -1147,6 +1147,22 @@ _ORTHO = {
     "cgs2": (KRY_ORTH_CGS, 2),       # new: CGS with re-orthogonalisation
 }
 _CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
+
+
+class DeviceBlock(object):
+    """A block of k vectors that already lives in HBM in the internal vector-major layout
+    ``(k, N)``; accepted wherever the public API takes an ``(N, k)`` array of deflation vectors."""
+
+    def __init__(self, block):
+        self.block = block
+
+    @property
+    def shape(self):
+        return (self.block.shape[1], self.block.shape[0])
+
+    @property
+    def dtype(self):
+        return _device.torch_to_np_dtype(self.block.dtype)
 
 
 class SolverWorkspace(object):

@@ -107,3 +107,16 @@ def test_host_logic_known_answers_and_semantics(fake):
         kp.linsys.Gmres(ls, ortho="house")
     with pytest.raises(kp.utils.ArgumentError):
         kp.linsys.Gmres(ls, ortho="nope")
+
+
+@pytest.mark.parametrize("name", ["convdiff_defl_gmres", "lap2d_defl_minres", "lap2d_defl_cg", "c1_gmres_defl"])
+def test_ritz_pairs_host_logic(fake, name):
+    import ritz_checks
+    ritz_checks.check_ritz_pairs(name)
+
+
+@pytest.mark.parametrize("sname", ["cg", "minres", "gmres"])
+@pytest.mark.parametrize("which", ["lm", "sm", "lr", "sr", "li", "si", "smallest_res"])
+def test_recycling_host_logic(fake, sname, which):
+    import ritz_checks
+    ritz_checks.check_recycling(sname, which)

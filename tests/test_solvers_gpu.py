@@ -241,3 +241,18 @@ def test_arnoldi_relation(ortho, with_M, ipB):
     np.testing.assert_allclose(V.T @ ipM @ V, np.eye(n + 1), atol=1e-11)
     if with_M:
         np.testing.assert_allclose(M @ res[2], V, atol=1e-13)
+
+
+@pytest.mark.parametrize("name", ["convdiff_defl_gmres", "lap2d_defl_minres", "lap2d_defl_cg", "c1_gmres_defl"])
+def test_ritz_pairs_match_reference(name):
+    """deflation.Ritz against the reference's values / residual norms"""
+    import ritz_checks
+    ritz_checks.check_ritz_pairs(name)
+
+
+@pytest.mark.parametrize("sname", ["cg", "minres", "gmres"])
+@pytest.mark.parametrize("which", ["sm", "lm", "smallest_res"])
+def test_recycling_ritz_factory_simple(sname, which):
+    """reference test/test_recycling.py: three recycled solves, iteration counts as the reference"""
+    import ritz_checks
+    ritz_checks.check_recycling(sname, which)
