@@ -962,14 +962,17 @@ class Projection(object):
             return scipy.linalg.solve_triangular(self.R, self.Q.T.conj().dot(c_host))
         return c_host
 
-    def _apply_dev(self, ad, return_Ya=False, adj=False):
+    def _apply_dev(self, ad, return_Ya=False, adj=False, c_first=None):
         """single application on a device block (m, N) -> Pa (m, N) [, Ya numpy (k, m)]
-        (krypy/utils.py:522-564)."""
+        (krypy/utils.py:522-564).  ``c_first`` (device, k doubles per column) receives the raw
+        ``<W, a>`` like the fused kernel's ``c_first_dev``."""
         ctx = _ctx()
         t = _device.torch()
         m = ad.shape[0]
         Wd, Vd = (self._Vd, self._Wd) if adj else (self._Wd, self._Vd)
-        c = _inner_dev(Wd, ad, self.ip_B).cpu().numpy()          # (k, m), small
+        c = _inner_dev(Wd, ad, self.ip_B).cpu().numpy().copy()   # (k, m), small
+        if c_first is not None:
+            c_first[: self._k * m].copy_(t.from_numpy(numpy.ascontiguousarray(c.T.reshape(-1))).to(ctx.device))
         Ya = None
         if return_Ya:
             Ya = c.copy()
@@ -1009,7 +1012,7 @@ class Projection(object):
                 return out, Ya
             return out
         # generic inner product: one application at a time
-        res = self._apply_dev(out, return_Ya=return_Ya)
+        res = self._apply_dev(out, return_Ya=return_Ya, c_first=c_first)
         x, Ya = res if return_Ya else (res, None)
         ctx.axpby(1.0, out, -1.0, x, out)
         for _ in range(self.iterations - 1):

@@ -1,0 +1,82 @@
+"""Build-container check (needs /root/reference; NOT used by the GPU tests, smoke() or bench.py):
+run the REFERENCE's own test files against krypy_b200's host layer, with the package aliased as
+``krypy`` and the device layer replaced by the numpy test double (tests/fake_device.py).
+
+Only the real-valued cases can run (the device path is real); complex cases are filtered out of the
+scratch copies / reported as skipped.  Result recorded in DESIGN.md section 8:
+  test_convenience_wrappers.py 7 passed | test_recycling.py 21 passed |
+  test_linsys.py (real subset) 5167 passed | test_deflation.py::test_deflation_solver 492 passed |
+  test_utils.py -k "arnoldi or givens or projection or qr" 1529 passed, 68 skipped (house, complex)
+usage: python tools/reference_suite_on_host_layer.py
+"""
+import os
+import shutil
+import subprocess
+import sys
+
+REF = "/root/reference/test"
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SCRATCH = "/tmp/krypy_b200_reftest"
+
+CONFTEST = '''
+import sys
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy
+numpy.complex = complex; numpy.float = float; numpy.int = int; numpy.Inf = numpy.Infinity = numpy.inf
+import krypy_b200
+from krypy_b200 import _device
+import fake_device
+_fake = fake_device.FakeContext()
+_device.Context.get = classmethod(lambda cls, device=None: _fake)
+for name, mod in (("krypy", krypy_b200), ("krypy.utils", krypy_b200.utils), ("krypy.linsys", krypy_b200.linsys),
+                  ("krypy.deflation", krypy_b200.deflation), ("krypy.recycling", krypy_b200.recycling)):
+    sys.modules[name] = mod
+import pytest
+
+@pytest.hookimpl(hookwrapper=True)
+def pytest_runtest_call(item):
+    outcome = yield
+    exc = outcome.excinfo
+    if exc is not None and issubclass(exc[0], NotImplementedError):
+        outcome.force_exception(pytest.skip.Exception("device path: " + str(exc[1])[:80]))
+''' % (ROOT, os.path.join(ROOT, "tests"))
+
+REAL_CASES = '''cases = [
+    {"A": test_utils.get_matrix_spd(), "normal": True, "self_adjoint": True, "positive_definite": True},
+    {"A": test_utils.get_matrix_symm_indef(), "normal": True, "self_adjoint": True},
+    {"A": test_utils.get_matrix_nonsymm()},
+]
+
+
+'''
+
+
+def main():
+    if not os.path.isdir(REF):
+        raise SystemExit("reference tests not present at " + REF)
+    shutil.rmtree(SCRATCH, ignore_errors=True)
+    os.makedirs(SCRATCH)
+    for f in os.listdir(REF):
+        if f.endswith(".py"):
+            shutil.copy(os.path.join(REF, f), SCRATCH)
+    open(os.path.join(SCRATCH, "conftest.py"), "w").write(CONFTEST)
+    # scratch copies only: drop the complex right-hand side / matrix classes, and the Arnoldifyer part
+    p = os.path.join(SCRATCH, "test_linsys.py")
+    s = open(p).read().replace("        (1 + 1j) * numpy.ones((10, 1)),\n", "")
+    a, b = s.index("cases = ["), s.index("def generate_cases():")
+    open(p, "w").write(s[:a] + REAL_CASES + s[b:])
+    p = os.path.join(SCRATCH, "test_deflation.py")
+    s = open(p).read()
+    open(p, "w").write(s[: s.index("def generate_Arnoldifyer_cases():")])
+    runs = [["test_convenience_wrappers.py", "test_recycling.py"], ["test_linsys.py"], ["test_deflation.py"],
+            ["test_utils.py", "-k", "arnoldi or givens or projection or qr"]]
+    rc = 0
+    for r in runs:
+        print("==", " ".join(r))
+        rc |= subprocess.call([sys.executable, "-m", "pytest", "-q", "-p", "no:cacheprovider", "-W", "ignore"] + r,
+                              cwd=SCRATCH)
+    sys.exit(rc)
+
+
+if __name__ == "__main__":
+    main()
