@@ -89,6 +89,11 @@ int kry_axpy_dev(kry_ctx* ctx, int dtype, long long n, const double* coef_dev, d
 int kry_scale_dev(kry_ctx* ctx, int dtype, long long n, const double* s_dev, int divide,
                   double mul, const void* x, void* out);
 
+/* y = i*x for n interleaved complex numbers (2n reals; x != y).  Complex systems are run on
+ * the real kernels by real embedding: a complex vector is 2n reals, every basis vector v is
+ * stored next to its twin i*v, and <v,q>_C = <v,q>_R + i<iv,q>_R (krypy/utils.py:157). */
+int kry_rot90(kry_ctx* ctx, int dtype, long long n, const void* x, void* y);
+
 /* ---- tall-skinny reductions / updates ----------------------------------- */
 /* out_dev[j] = sum_i V_j[i]*q[i], j < nv (deterministic two-stage reduction).
  * post: 0 none, 1 out = sqrt(out).  acc_dev (may be NULL): acc_dev[j] += out[j].

@@ -241,6 +241,10 @@ class Context(object):
         check(self.lib.kry_scale_dev(self.h, code(x), x.numel(), s.data_ptr(), int(divide), float(mul),
                                      x.data_ptr(), out.data_ptr()))
 
+    def rot90(self, x, y):
+        """y = i*x for interleaved complex data held in real tensors (len(x) = 2 * #complex)"""
+        check(self.lib.kry_rot90(self.h, code(x), x.numel() // 2, x.data_ptr(), y.data_ptr()))
+
     # ---- tall-skinny -----------------------------------------------------
     def block_dot(self, V, nv, q, out, post=0, acc=None):
         """out[j] = <V[j], q>, j < nv.  V: (>=nv, N) tensor (row stride = ld)."""

@@ -41,6 +41,7 @@ PROTOTYPES = {
     "kry_axpby": (c_int, [c_void_p, c_int, c_ll, c_double, c_void_p, c_double, c_void_p, c_void_p]),
     "kry_axpy_dev": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_double, c_void_p, c_void_p]),
     "kry_scale_dev": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_int, c_double, c_void_p, c_void_p]),
+    "kry_rot90": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p]),
     "kry_block_dot": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p,
                               c_int, c_void_p]),
     "kry_block_axpy": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_double,

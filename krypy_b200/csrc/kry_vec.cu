@@ -123,6 +123,19 @@ __global__ void __launch_bounds__(KRY_THREADS) diag_mul_kernel(long long n, cons
             y[i] = (T)((double)d[i] * (double)x[i]);
 }
 
+// y = i * x for interleaved complex data (x, y: n complex numbers = 2n reals, may not alias):
+// y[2k] = -x[2k+1], y[2k+1] = x[2k].  Complex systems run on the real kernels with every basis
+// vector v stored next to its twin i*v ("complex by real embedding").
+template <typename T>
+__global__ void __launch_bounds__(KRY_THREADS) rot90_kernel(long long n, const T* __restrict__ x, T* y) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < n; k += stride) {
+        const T re = x[2 * k], im = x[2 * k + 1];
+        y[2 * k] = -im;
+        y[2 * k + 1] = re;
+    }
+}
+
 // ---------------------------------------------------------------------------
 // block dot: out[j] = <V_j, q>, j < nv.  JT basis vectors per register tile.
 // ---------------------------------------------------------------------------
@@ -412,6 +425,23 @@ int kry_diag_mul(kry_ctx* ctx, int dtype, long long n, const void* d, const void
         kry_set_error("kry_diag_mul: unsupported dtype %d", dtype);
         return KRY_ERR_UNSUPPORTED;
     }
+    return KRY_OK;
+}
+
+int kry_rot90(kry_ctx* ctx, int dtype, long long n, const void* x, void* y) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && x && y && x != y, "bad arguments (x and y must not alias)");
+    if (n == 0) return KRY_OK;
+    int g = stream_grid(ctx, n, 8);
+    if (dtype == KRY_F64)
+        rot90_kernel<double><<<g, KRY_THREADS, 0, ctx->stream>>>(n, (const double*)x, (double*)y);
+    else if (dtype == KRY_F32)
+        rot90_kernel<float><<<g, KRY_THREADS, 0, ctx->stream>>>(n, (const float*)x, (float*)y);
+    else {
+        kry_set_error("kry_rot90: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
     return KRY_OK;
 }
 

@@ -153,6 +153,12 @@ class FakeContext(object):
         v = float(mul) * x.double()
         out.copy_((v / float(s[0]) if divide else v * float(s[0])).to(out.dtype))
 
+    def rot90(self, x, y):
+        self._count("rot90")
+        xv = x.detach().clone()
+        y[0::2] = -xv[1::2]
+        y[1::2] = xv[0::2]
+
     # ---- tall-skinny (kry_block_dot, kry_block_axpy, kry_block_combine) ----
     def block_dot(self, V, nv, q, out, post=0, acc=None):
         self._count("block_dot")
