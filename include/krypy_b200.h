@@ -151,6 +151,15 @@ int kry_givens_update(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev,
  * (scipy.linalg.solve_triangular, linsys.py:946) */
 int kry_tri_solve(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const double* y_dev,
                   double* out_dev);
+/* Complex twins (complex numbers interleaved re/im in double arrays; krypy/utils.py:419-427:
+ * drotg when both entries are real-valued, zrotg otherwise).  hcol_dev, rcol_dev, y_dev hold
+ * k+2 complex numbers; cs_dev 4 doubles per rotation [c, flag, s_re, s_im].
+ * Mailbox at off: [ |y[k+1]|, H[0..k+1,k] (2(k+2) doubles), R[0..k+1,k] (2(k+2) doubles) ].
+ * kry_tri_solve_z: R complex row-major, ldr in complex elements. */
+int kry_givens_update_z(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev,
+                        double* cs_dev, double* y_dev, int mailbox_off);
+int kry_tri_solve_z(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const double* y_dev,
+                    double* out_dev);
 /* MINRES sliding QR (krypy/linsys.py:827-847).  st_dev: 16 doubles of state
  * [G1c,G1s,G1valid,G2c,G2s,G2valid,y0,-, R0,R1,R2,ycoef, ...] (zero-initialised,
  * st[6] = ||r0||); h3_dev: [H[k-1,k], H[k,k], H[k+1,k]] as left by

@@ -33,9 +33,11 @@ def np_to_torch_dtype(dt):
         return t.float64
     if dt == np.float32:
         return t.float32
+    if dt.kind == "c":
+        return t.complex128
     raise NotImplementedError(
-        "krypy_b200: dtype %s is not supported by the device path (float32/float64 only; "
-        "complex arithmetic is not implemented and there is no CPU fallback)" % dt)
+        "krypy_b200: dtype %s is not supported by the device path (float32/float64/complex128; "
+        "there is no CPU fallback)" % dt)
 
 
 def torch_to_np_dtype(dt):
@@ -44,11 +46,46 @@ def torch_to_np_dtype(dt):
         return np.dtype(np.float64)
     if dt == t.float32:
         return np.dtype(np.float32)
+    if dt == t.complex128:
+        return np.dtype(np.complex128)
     raise NotImplementedError("unsupported torch dtype %s" % dt)
 
 
 def code(t):
-    return KRY_F64 if t.dtype == torch().float64 else KRY_F32
+    if t.dtype == torch().float64:
+        return KRY_F64
+    if t.dtype == torch().float32:
+        return KRY_F32
+    raise TypeError("kernel argument of dtype %s (complex blocks are passed as real views)" % t.dtype)
+
+
+def is_complex(t):
+    return t is not None and not isinstance(t, int) and t.dtype == torch().complex128
+
+
+def rview(t):
+    """Real view of a complex128 tensor: (..., N) complex -> (..., 2N) float64, re/im interleaved
+    (same memory).  Real tensors, ints (raw addresses) and None pass through."""
+    if t is None or isinstance(t, int) or t.dtype != torch().complex128:
+        return t
+    return t.view(torch().float64)
+
+
+def realviews(fn):
+    """Kernel wrappers see complex blocks as their interleaved real views: the kernels are real
+    (krypy_b200/_cplx.py: complex arithmetic by real embedding + twin storage)."""
+    import functools
+    T = torch
+
+    @functools.wraps(fn)
+    def wrapper(self, *args, **kwargs):
+        tens = T().Tensor
+        args = [rview(a) if isinstance(a, tens) else a for a in args]
+        for k, v in kwargs.items():
+            if isinstance(v, tens):
+                kwargs[k] = rview(v)
+        return fn(self, *args, **kwargs)
+    return wrapper
 
 
 def _p(t):
@@ -172,14 +209,14 @@ class Context(object):
         """numpy/torch array (N,) or (N,k) -> contiguous device tensor (k, N)."""
         t = torch()
         if isinstance(X, t.Tensor):
-            if X.is_complex():
-                raise NotImplementedError("complex vectors are not supported by the device path")
+            if X.is_complex() and dtype != t.complex128:
+                raise NotImplementedError("complex vectors need a complex linear system / solver dtype")
             Xt = X.detach().to(device=self.device, dtype=dtype)
             Xt = Xt.reshape(1, -1) if Xt.dim() == 1 else Xt.t()
             return Xt.contiguous().clone()   # inputs are never mutated (SURVEY 8b, ownership)
         X = np.asarray(X)
-        if np.iscomplexobj(X):
-            raise NotImplementedError("complex vectors are not supported by the device path")
+        if np.iscomplexobj(X) and dtype != t.complex128:
+            raise NotImplementedError("complex vectors need a complex linear system / solver dtype")
         if X.ndim == 1:
             X = X.reshape(-1, 1)
         if X.shape[1] > 1 and X.shape[0] * X.shape[1] > (1 << 20):
@@ -209,6 +246,7 @@ class Context(object):
         return CsrDev(rowptr, colidx, vals, A.shape)
 
     # ---- operators -------------------------------------------------------
+    @realviews
     def spmv(self, A, x, y, w=None, dot_out=None):
         if self.timer is not None:
             tm, self.timer = self.timer, None
@@ -221,31 +259,38 @@ class Context(object):
         if self.comm is not None and dot_out is not None:
             self.comm.allreduce(dot_out, 1)
 
+    @realviews
     def gemv(self, A, x, y):
         check(self.lib.kry_gemv_dense(self.h, code(A), A.shape[0], A.shape[1], A.data_ptr(),
                                       A.stride(0), x.data_ptr(), y.data_ptr()))
 
+    @realviews
     def diag_mul(self, d, x, y):
         check(self.lib.kry_diag_mul(self.h, code(x), x.numel(), d.data_ptr(), x.data_ptr(), y.data_ptr()))
 
     # ---- elementwise -------------------------------------------------------
+    @realviews
     def axpby(self, a, x, b, y, z):
         check(self.lib.kry_axpby(self.h, code(x), x.numel(), float(a), x.data_ptr(), float(b), _p(y),
                                  z.data_ptr()))
 
+    @realviews
     def axpy_dev(self, coef, sign, x, y):
         check(self.lib.kry_axpy_dev(self.h, code(x), x.numel(), coef.data_ptr(), float(sign),
                                     x.data_ptr(), y.data_ptr()))
 
+    @realviews
     def scale_dev(self, s, divide, mul, x, out):
         check(self.lib.kry_scale_dev(self.h, code(x), x.numel(), s.data_ptr(), int(divide), float(mul),
                                      x.data_ptr(), out.data_ptr()))
 
+    @realviews
     def rot90(self, x, y):
         """y = i*x for interleaved complex data held in real tensors (len(x) = 2 * #complex)"""
         check(self.lib.kry_rot90(self.h, code(x), x.numel() // 2, x.data_ptr(), y.data_ptr()))
 
     # ---- tall-skinny -----------------------------------------------------
+    @realviews
     def block_dot(self, V, nv, q, out, post=0, acc=None):
         """out[j] = <V[j], q>, j < nv.  V: (>=nv, N) tensor (row stride = ld)."""
         if self.comm is not None:
@@ -257,15 +302,18 @@ class Context(object):
         check(self.lib.kry_block_dot(self.h, code(q), q.numel(), _p(V), V.stride(0) if V is not None else 0,
                                      int(nv), q.data_ptr(), _p(out), int(post), _p(acc)))
 
+    @realviews
     def block_axpy(self, V, nv, coef, sign, q):
         check(self.lib.kry_block_axpy(self.h, code(q), q.numel(), V.data_ptr(), V.stride(0), int(nv),
                                       coef.data_ptr(), float(sign), q.data_ptr()))
 
+    @realviews
     def block_combine(self, V, nv, coef, x0, out):
         check(self.lib.kry_block_combine(self.h, code(out), out.numel(), _p(V),
                                          V.stride(0) if V is not None else 0, int(nv), _p(coef), _p(x0),
                                          out.data_ptr()))
 
+    @realviews
     def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
                    pre_coef=None, h_ptr=None, halo_op=None):
         if self.timer is not None:
@@ -377,6 +425,7 @@ class Context(object):
         ld = (int(N) + 31) // 32 * 32
         return self.empty((int(rows), ld), dtype)
 
+    @realviews
     def project(self, W, V, d, a, Q, R, iterations, c_first):
         if self.comm is not None:
             if self._tmpc is None:
@@ -407,13 +456,26 @@ class Context(object):
     def tri_solve(self, k, R, y, out):
         check(self.lib.kry_tri_solve(self.h, int(k), R.data_ptr(), R.stride(0), y.data_ptr(), out.data_ptr()))
 
+    def givens_update_z(self, k, hcol, rcol, cs, y, off=0):
+        """complex twin of givens_update: hcol/rcol/y hold k+2 interleaved complex numbers,
+        cs 4 doubles per rotation"""
+        check(self.lib.kry_givens_update_z(self.h, int(k), hcol.data_ptr(), rcol.data_ptr(), cs.data_ptr(),
+                                           y.data_ptr(), int(off)))
+
+    def tri_solve_z(self, k, R, y, out):
+        """R: (k, 2k) float64 = k x k complex row-major, interleaved"""
+        check(self.lib.kry_tri_solve_z(self.h, int(k), R.data_ptr(), R.stride(0) // 2, y.data_ptr(),
+                                       out.data_ptr()))
+
     def minres_recur(self, k, h3, st, shift=1, off=0):
         check(self.lib.kry_minres_recur(self.h, int(k), h3.data_ptr(), st.data_ptr(), int(shift), int(off)))
 
+    @realviews
     def minres_update(self, v, w0, w1, yk, st):
         check(self.lib.kry_minres_update(self.h, code(v), v.numel(), v.data_ptr(), w0.data_ptr(),
                                          w1.data_ptr(), yk.data_ptr(), st.data_ptr()))
 
+    @realviews
     def cg_update(self, Ap, p, yk, r, z, dinv, rho, pAp, off=0):
         check(self.lib.kry_cg_update(self.h, code(p), p.numel(), Ap.data_ptr(), p.data_ptr(), yk.data_ptr(),
                                      r.data_ptr(), _p(z), _p(dinv), float(rho), pAp.data_ptr(), int(off)))

@@ -3,6 +3,7 @@
 // memory in parallel, one thread runs the (inherently serial) recurrence, the
 // results go to device state and to the pinned host mailbox in parallel.
 #include "kry_common.cuh"
+#include "kry_small_core.h"
 
 #define KRY_ENTER(ctx)                                                         \
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
@@ -144,6 +145,51 @@ __global__ void __launch_bounds__(128) small_qr_apply_kernel(int d, const double
     for (int i = threadIdx.x; i < d; i += blockDim.x) c_out[i] = t[i];
 }
 
+// Complex twins of givens_kernel / tri_solve_kernel (complex numbers interleaved re/im in
+// double arrays; the serial cores live in kry_small_core.h and are unit-tested on the host).
+// cs: 4 doubles per rotation [c, flag, s_re, s_im].
+// mailbox: [ |y[k+1]|, H[0..k+1,k] (2(k+2) doubles), R[0..k+1,k] (2(k+2) doubles) ].
+__global__ void __launch_bounds__(128) givens_z_kernel(int k, double* hcol, double* rcol, double* cs, double* y,
+                                                       double* mailbox) {
+    extern __shared__ double sh[];
+    const int nr = 2 * (k + 2);
+    double* r = sh;           // 2(k+2)
+    double* rot = sh + nr;    // 4k
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) r[i] = hcol[i];
+    for (int i = threadIdx.x; i < 4 * k; i += blockDim.x) rot[i] = cs[i];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+        mailbox[1 + i] = r[i];
+        hcol[i] = 0.0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double yy[4] = {y[2 * k], y[2 * k + 1], y[2 * k + 2], y[2 * k + 3]};
+        double rn[4];
+        const double res = kryc_givens_step(k, r, rot, rn, yy);
+        for (int i = 0; i < 4; ++i) {
+            cs[4 * k + i] = rn[i];
+            y[2 * k + i] = yy[i];
+        }
+        mailbox[0] = res;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < nr; i += blockDim.x) {
+        rcol[i] = r[i];
+        mailbox[1 + nr + i] = r[i];
+    }
+}
+
+__global__ void tri_solve_z_kernel(int k, const double* R, long long ldr, const double* y, double* out) {
+    extern __shared__ double sh[];
+    double* x = sh;   // 2k
+    for (int i = threadIdx.x; i < 2 * k; i += blockDim.x) x[i] = y[i];
+    __syncthreads();
+    if (threadIdx.x == 0) kryc_tri_solve(k, R, ldr, x);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * k; i += blockDim.x) out[i] = x[i];
+}
+
 extern "C" {
 
 int kry_small_qr_apply(kry_ctx* ctx, int d, const double* Q_dev, const double* R_dev, const double* c_in_dev,
@@ -185,6 +231,29 @@ int kry_minres_recur(kry_ctx* ctx, int k, double* h3_dev, double* st_dev, int sh
     KRY_REQUIRE(k >= 0 && h3_dev && st_dev, "bad arguments");
     KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 8 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
     minres_recur_kernel<<<1, 32, 0, ctx->stream>>>(k, h3_dev, st_dev, shift, ctx->d_mailbox + mailbox_off);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_givens_update_z(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev, double* cs_dev, double* y_dev,
+                        int mailbox_off) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(k >= 0 && hcol_dev && rcol_dev && cs_dev && y_dev, "bad arguments");
+    KRY_REQUIRE(k <= 1000, "k too large for the single-CTA Givens update (use restarts)");
+    KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 4 * k + 9 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
+    size_t smem = sizeof(double) * (size_t)(2 * (k + 2) + 4 * k);
+    givens_z_kernel<<<1, 128, smem, ctx->stream>>>(k, hcol_dev, rcol_dev, cs_dev, y_dev, ctx->d_mailbox + mailbox_off);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_tri_solve_z(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const double* y_dev, double* out_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(k >= 0 && ldr >= k, "bad arguments");
+    if (k == 0) return KRY_OK;
+    KRY_REQUIRE(R_dev && y_dev && out_dev, "NULL argument");
+    KRY_REQUIRE(k <= 3000, "k too large");
+    tri_solve_z_kernel<<<1, 128, sizeof(double) * 2 * (size_t)k, ctx->stream>>>(k, R_dev, ldr, y_dev, out_dev);
     KRY_LAUNCHED(ctx);
     return KRY_OK;
 }

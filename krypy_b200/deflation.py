@@ -9,7 +9,7 @@ reference's layout when the attribute is read.
 """
 import numpy
 
-from . import _device, linsys, utils
+from . import _cplx, _device, linsys, utils
 from .utils import _ctx, _is_dev
 
 __all__ = ["DeflatedCg", "DeflatedMinres", "DeflatedGmres", "_DeflationMixin",
@@ -74,10 +74,9 @@ class ObliqueProjection(_Projection):
         ctx.axpby(1.0, ls._b_dev[0], -1.0, Az[0], r[0])
         c = ls.Ml._apply_dev(r)
         c = utils._inner_dev(self._Wd, c, self.ip_B).cpu().numpy()       # (d, 1); synchronises
-        c = numpy.ascontiguousarray(self._small_correct(c).reshape(-1), dtype=numpy.float64)
-        cd = _device.torch().from_numpy(c).to(ctx.device)
+        c = self._small_correct(c).reshape(-1)
         out = ctx.empty(zd.shape, zd.dtype)
-        ctx.block_combine(self._Wd, self._k, cd, zd[0], out[0])          # z + W c
+        utils._combine(ctx, self._Wd, self._k, c, zd[0], out[0])         # z + W c
         return out
 
     def correct(self, z):
@@ -137,7 +136,10 @@ class _DeflationMixin(object):
         """host (d, ncols) array of the raw first-application coefficients."""
         if self._d == 0 or self._ncols == 0:
             return numpy.zeros((self._d, self._ncols))
-        raw = self._Craw[: self._ncols].cpu().numpy().T.copy()       # (d, ncols)
+        raw = self._Craw[: self._ncols].cpu().numpy()                # (ncols, d doubles | 2d interleaved)
+        if self._td == _device.torch().complex128:
+            raw = _cplx.from_pairs(raw)
+        raw = raw.T.copy()                                           # (d, ncols)
         WR = self.projection.WR
         return WR.T.conj().dot(raw) if WR is not None else raw       # Ya = WR^H c, utils.py:544-545
 
@@ -152,8 +154,9 @@ class _DeflationMixin(object):
         """krypy/deflation.py:127-133."""
         N = self.linear_system.N
         ctx = _ctx()
-        self._Craw = ctx.scalars(max((self.maxiter + 2) * max(self._d, 1), 1)).reshape(
-            self.maxiter + 2, max(self._d, 1))
+        nr = 2 if self._td == _device.torch().complex128 else 1
+        self._Craw = ctx.scalars(max((self.maxiter + 2) * nr * max(self._d, 1), 1)).reshape(
+            self.maxiter + 2, nr * max(self._d, 1))
         P = utils._FunctionDeviceOperator((N, N), self.linear_system.dtype, self._apply_projection)
         self.MlAMr = P * self.linear_system.MlAMr
         super(_DeflationMixin, self)._solve()
@@ -375,10 +378,23 @@ class Ritz(object):
         (n1, n) = numpy.asarray(sv.H).shape
         pr = sv.projection
         m = pr._k
-        co = self._real_coeffs(indices, realify)
-        k = co.shape[1]
         Vd = sv._basis_dev()
         N = sv.linear_system.N
+        if sv._td == t.complex128:
+            # complex system: complex coefficients over the twin storage of V_n and U
+            co = self.coeffs if indices is None else self.coeffs[:, indices]
+            co = co.reshape(-1, 1) if co.ndim == 1 else co
+            k = co.shape[1]
+            out = ctx.empty((k, N), sv._td)
+            tmp = ctx.empty((1, N), sv._td)
+            for j in range(k):
+                utils._combine(ctx, Vd, n, co[:n, j], None, out[j])
+                if m:
+                    utils._combine(ctx, pr._Ud, m, co[n:, j], out[j], tmp[0])
+                    out[j].copy_(tmp[0])
+            return utils.DeviceBlock(out)
+        co = self._real_coeffs(indices, realify)
+        k = co.shape[1]
         out = ctx.empty((k, N), sv._td)
         cd = t.from_numpy(numpy.ascontiguousarray(co.T, dtype=numpy.float64)).to(ctx.device)   # (k, n+m)
         for j in range(k):
@@ -398,13 +414,13 @@ class Ritz(object):
         blk = self.get_vectors_dev(indices).block
         vals = self.values if indices is None else self.values[indices]
         vals = numpy.atleast_1d(vals)
-        if numpy.iscomplexobj(vals):
-            if numpy.abs(vals.imag).max() > 0:
-                raise NotImplementedError("complex Ritz values are not supported by the (real) device path")
-            vals = vals.real
         res = self._solver.linear_system.MlAMr._apply_dev(blk)
+        if numpy.iscomplexobj(vals) and not utils._is_cplx(blk):
+            if numpy.abs(vals.imag).max() > 0:
+                raise NotImplementedError("complex Ritz values of a real system (use realify / a complex system)")
+            vals = vals.real
         for j in range(blk.shape[0]):
-            ctx.axpby(1.0, res[j], -float(vals[j]), blk[j], res[j])
+            utils._caxpby(ctx, -vals[j], blk[j], 1.0, res[j], res[j])
         return res
 
     def get_explicit_resnorms(self, indices=None):

@@ -10,7 +10,7 @@ import warnings
 
 import numpy
 
-from . import _device, utils
+from . import _cplx, _device, utils
 from .utils import _ctx, _is_dev
 
 __all__ = ["LinearSystem", "Cg", "Minres", "Gmres", "RestartedGmres", "TimedLinearSystem",
@@ -400,7 +400,9 @@ class _KrylovSolver(object):
 
 
 def _diag_of(op):
-    return op if isinstance(op, utils.DiagonalLinearOperator) else None
+    if isinstance(op, utils.DiagonalLinearOperator) and numpy.dtype(op._d.dtype).kind != "c":
+        return op
+    return None
 
 
 class Cg(_KrylovSolver):
@@ -570,6 +572,7 @@ class Minres(_KrylovSolver):
         W1 = ctx.zeros((1, N), td)
         yk = ctx.zeros((1, N), td)
         st = ctx.scalars(16)
+        h3 = ctx.scalars(3)
         st[6:7].fill_(float(self.MMlr0_norm))                       # y = [||r0||, 0], linsys.py:809
         mb = ctx.mailbox
         is_lanczos = self.ortho == "lanczos"
@@ -578,6 +581,11 @@ class Minres(_KrylovSolver):
             lz._enqueue(k)                                           # linsys.py:823
             if is_lanczos:
                 ctx.minres_recur(k, lz._lz, st, 1, 0)                # linsys.py:827-841, 847
+            elif lz._cplx:
+                # the recurrence takes the real parts (linsys.py:828-833): gather them from the
+                # interleaved column
+                h3.copy_(lz._hcol_store[2 * k:2 * k + 6:2])
+                ctx.minres_recur(k, h3, st, 0, 0)
             else:
                 ctx.minres_recur(k, lz._hcol_store[k:], st, 0, 0)    # [H[k-1,k], H[k,k], H[k+1,k]]
             ctx.minres_update(lz._Vd[k], W0[0], W1[0], yk[0], st)    # linsys.py:844-846
@@ -587,8 +595,7 @@ class Minres(_KrylovSolver):
                 resid = float(mb[0])
                 lz._finish(k, mb[6:8].copy())
             else:
-                hc = lz._hcol[: k + 2].cpu().numpy().copy()          # synchronises
-                lz._hcol[: k + 2].zero_()
+                hc = lz._read_hcol(k)                                # synchronises
                 resid = float(mb[0])
                 lz._finish(k, hc)
             self._finalize_iteration(yk, resid)                      # linsys.py:849
@@ -651,16 +658,23 @@ class Gmres(_KrylovSolver):
         k = self.arnoldi.iter
         if k > 0:
             t = _device.torch()
-            Rk = t.from_numpy(numpy.ascontiguousarray(self.R[:k, :k], dtype=numpy.float64)).to(ctx.device)
-            yy = ctx.scalars(k)
-            ctx.tri_solve(k, Rk, y, yy)                                    # linsys.py:946
+            ar = self.arnoldi
+            nr = ar._nr
+            yy = ctx.scalars(nr * k)
+            if ar._cplx:
+                Rk = t.from_numpy(_cplx.to_pairs(self.R[:k, :k])).to(ctx.device)   # (k, 2k) interleaved
+                ctx.tri_solve_z(k, Rk, y, yy)
+            else:
+                Rk = t.from_numpy(numpy.ascontiguousarray(self.R[:k, :k], dtype=numpy.float64)).to(ctx.device)
+                ctx.tri_solve(k, Rk, y, yy)                                # linsys.py:946
             out = ctx.empty(x0d.shape, x0d.dtype)
             Mr = self.linear_system.Mr
+            # (complex: the interleaved yy are the real coefficients over the twin rows v_j, i v_j)
             if isinstance(Mr, utils.IdentityLinearOperator):
-                ctx.block_combine(self.arnoldi._Vd, k, yy, x0d[0], out[0])  # x0 + V[:, :k] yy
+                ctx.block_combine(ar._Vt, nr * k, yy, x0d[0], out[0])      # x0 + V[:, :k] yy
             else:
                 yk = ctx.empty(x0d.shape, x0d.dtype)
-                ctx.block_combine(self.arnoldi._Vd, k, yy, None, yk[0])     # linsys.py:947
+                ctx.block_combine(ar._Vt, nr * k, yy, None, yk[0])         # linsys.py:947
                 Mry = Mr._apply_dev(yk)
                 ctx.axpby(1.0, x0d[0], 1.0, Mry[0], out[0])                 # linsys.py:948
             return out
@@ -677,15 +691,17 @@ class Gmres(_KrylovSolver):
         m = self.maxiter
         ws = self._ws
         self.R = numpy.zeros([m + 1, m], dtype=utils._common_type([self.dtype, numpy.float64]))
+        cplx, nr = ar._cplx, ar._nr            # complex: every small quantity is an interleaved pair
         if ws is not None:
-            self._y_dev = y = ws.tensor("y", (m + 2,), lambda: ctx.scalars(m + 2))
-            cs = ws.tensor("cs", (2 * m + 2,), lambda: ctx.scalars(2 * m + 2))
-            rcol = ws.tensor("rcol", (m + 2,), lambda: ctx.scalars(m + 2))
+            self._y_dev = y = ws.tensor("y", (nr * (m + 2),), lambda: ctx.scalars(nr * (m + 2)))
+            cs = ws.tensor("cs", (2 * nr * (m + 1),), lambda: ctx.scalars(2 * nr * (m + 1)))
+            rcol = ws.tensor("rcol", (nr * (m + 2),), lambda: ctx.scalars(nr * (m + 2)))
             y.zero_()
         else:
-            self._y_dev = y = ctx.scalars(m + 2)
-            cs = ctx.scalars(2 * m + 2)
-            rcol = ctx.scalars(m + 2)
+            self._y_dev = y = ctx.scalars(nr * (m + 2))
+            cs = ctx.scalars(2 * nr * (m + 1))
+            rcol = ctx.scalars(nr * (m + 2))
+        givens = ctx.givens_update_z if cplx else ctx.givens_update
         y[0:1].fill_(float(self.MMlr0_norm))                               # linsys.py:969
         # CUDA graphs: from the second cycle over the same workspace on, step k is one graph launch
         use_graphs = (ws is not None and type(self) is Gmres and ws.graphs_enabled(ctx)
@@ -703,7 +719,7 @@ class Gmres(_KrylovSolver):
         # host's decision; if the loop ends at k the speculative step is simply discarded
         # (it only touched V[k+2], y[k+1:], cs[2k+2:], which nothing reads afterwards).
         lookahead = (not self.explicit_residual and ls.exact_solution is None and not is_lanczos
-                     and 2 * m + 5 <= HALF)
+                     and 2 * nr * (m + 2) + 1 <= HALF)
 
         def off_of(k):
             return (k & 1) * HALF if lookahead else 0
@@ -715,14 +731,14 @@ class Gmres(_KrylovSolver):
                 with t.cuda.graph(g):
                     ctx.use_current_stream()
                     ar._enqueue(k)
-                    ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))
+                    givens(k, ar._hcol, rcol, cs, y, off_of(k))
                 ctx.use_current_stream()
                 ws.graphs[k] = g
             if g is not None:
                 g.replay()
             else:
                 ar._enqueue(k)                                             # linsys.py:978
-                ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))     # linsys.py:982-991
+                givens(k, ar._hcol, rcol, cs, y, off_of(k))                # linsys.py:982-991
             events[k & 1].record()
 
         launched = -1
@@ -737,12 +753,12 @@ class Gmres(_KrylovSolver):
                 # tridiagonal column from the three Lanczos entries
                 ctx.minres_recur(k, ar._lz, ar._lz_st, 1, 16)
                 ctx.sync()
-                hcol = numpy.zeros(k + 2)
+                hcol = numpy.zeros(nr * (k + 2))
                 if k > 0:
-                    hcol[k - 1] = mb[16 + 5]
-                hcol[k], hcol[k + 1] = mb[16 + 6], mb[16 + 7]
-                ar._hcol[: k + 2].copy_(t.from_numpy(hcol))
-                ctx.givens_update(k, ar._hcol, rcol, cs, y, off_of(k))
+                    hcol[nr * (k - 1)] = mb[16 + 5]
+                hcol[nr * k], hcol[nr * (k + 1)] = mb[16 + 6], mb[16 + 7]
+                ar._hcol[: nr * (k + 2)].copy_(t.from_numpy(hcol))
+                givens(k, ar._hcol, rcol, cs, y, off_of(k))
                 events[k & 1].record()
                 launched = k
             if launched < k:
@@ -754,10 +770,15 @@ class Gmres(_KrylovSolver):
             events[k & 1].synchronize()
             off = off_of(k)
             resid = float(mb[off])
-            hcol = mb[off + 1:off + k + 3].copy()
-            self.R[: k + 2, k] = mb[off + k + 3:off + 2 * k + 5]
+            nh = nr * (k + 2)
+            hcol = mb[off + 1:off + 1 + nh].copy()
+            rk = mb[off + 1 + nh:off + 1 + 2 * nh].copy()
+            if cplx:
+                hcol = _cplx.from_pairs(hcol.reshape(1, -1))[0]
+                rk = _cplx.from_pairs(rk.reshape(1, -1))[0]
+            self.R[: k + 2, k] = rk
             if is_lanczos:
-                ar._finish(k, hcol[k:k + 2])
+                ar._finish(k, numpy.real(hcol[k:k + 2]))
             else:
                 ar._finish(k, hcol)
             self._finalize_iteration(y, resid)                             # linsys.py:993

@@ -8,8 +8,14 @@ reference; internally blocks live in HBM as ``(k, N)`` torch tensors
 ("vector-major") and the solver classes call the ``*_dev`` methods
 directly so nothing N-sized crosses PCIe inside an iteration.
 
-There is no CPU fallback: anything the device path cannot do (complex dtypes,
-``ortho='house'``) raises ``NotImplementedError``.
+Complex systems run on the same (real) kernels by real embedding: a complex block is a
+``torch.complex128`` tensor whose interleaved real view is what the kernels see, and every block
+that is the left operand of inner products or a combination basis is kept in *twin storage*
+(``_Twin``: rows ``v_0, i v_0, v_1, i v_1, ...``), which turns complex Gram-Schmidt against k
+vectors into real Gram-Schmidt against 2k vectors (krypy_b200/_cplx.py).
+
+There is no CPU fallback: anything the device path cannot do (``ortho='house'``, complex
+row-partitioned runs) raises ``NotImplementedError``.
 """
 import time
 import warnings
@@ -17,7 +23,7 @@ from collections import defaultdict
 
 import numpy
 
-from . import _device
+from . import _cplx, _device
 from ._lib import KRY_ORTH_CGS, KRY_ORTH_MGS
 
 __all__ = [
@@ -104,12 +110,10 @@ def find_common_dtype(*args):
 
 
 def _compute_dtype(npdtype):
-    """numpy dtype -> torch dtype of the device path (raises for complex)."""
+    """numpy dtype -> torch dtype of the device path (complex64 promotes to complex128)."""
     npdtype = numpy.dtype(npdtype)
     if npdtype.kind == "c":
-        raise NotImplementedError(
-            "krypy_b200: complex systems are not implemented on the device path "
-            "(real float32/float64 only; no CPU fallback)")
+        return _device.np_to_torch_dtype(numpy.complex128)
     if npdtype == numpy.float32:
         return _device.np_to_torch_dtype(numpy.float32)
     return _device.np_to_torch_dtype(numpy.float64)   # ints, bools, float16 promote to fp64
@@ -139,6 +143,109 @@ def _isintlike(x):
         return bool(int(x) == x) and numpy.ndim(x) == 0
     except (TypeError, ValueError):
         return False
+
+
+# --------------------------------------------------------------------------
+# complex blocks: twin storage (krypy_b200/_cplx.py)
+# --------------------------------------------------------------------------
+def _is_cplx(x):
+    return _device.is_complex(x)
+
+
+class _Twin(object):
+    """Twin storage of k complex vectors of length N: a real ``(2k, ld)`` tensor whose row ``2j``
+    is the interleaved ``v_j`` and whose row ``2j+1`` is ``i v_j``.
+
+    ``T``: real ``(2k, 2N)`` view for the kernels (real Gram-Schmidt / block dots / combinations
+    against these 2k rows ARE the complex operations against the k vectors, with interleaved
+    complex coefficients); ``C``: complex ``(k, N)`` view of the even rows (the block itself)."""
+
+    def __init__(self, ctx, k, N, op=None):
+        t = _device.torch()
+        self.k, self.N = int(k), int(N)
+        store = ctx.alloc_basis(2 * max(self.k, 1), 2 * self.N, t.float64, None)
+        self.store = store
+        self.T = store[: 2 * self.k, : 2 * self.N]
+        self.C = store[0::2].view(t.complex128)[: self.k, : self.N]
+        self.C._kry_twin = self       # _twin_for(C) finds its own storage
+
+    def refresh(self, ctx, j):
+        """row 2j+1 <- i * row 2j (after vector j was written)"""
+        ctx.rot90(self.T[2 * j], self.T[2 * j + 1])
+
+    @classmethod
+    def of(cls, ctx, Xc):
+        """twin storage holding a copy of the complex block Xc (k, N)"""
+        tw = cls(ctx, Xc.shape[0], Xc.shape[1])
+        if tw.k:
+            tw.C.copy_(Xc)
+            for j in range(tw.k):
+                tw.refresh(ctx, j)
+        return tw
+
+
+def _twin_for(ctx, Xc):
+    """the twin storage behind a complex block: the one it is a view of (blocks produced by
+    ``_qr_dev``, Arnoldi bases), else a freshly built one cached on the tensor object.  Only for
+    blocks that are no longer modified."""
+    tw = getattr(Xc, "_kry_twin", None)
+    if tw is None:
+        tw = _Twin.of(ctx, Xc)
+        try:
+            Xc._kry_twin = tw
+        except Exception:
+            pass
+    return tw
+
+
+def _coefs_dev(ctx, c):
+    """host coefficient vector (real or complex) -> device doubles (complex: interleaved)"""
+    t = _device.torch()
+    c = numpy.asarray(c).reshape(-1)
+    if numpy.iscomplexobj(c):
+        c = _cplx.to_pairs(c.reshape(1, -1)).reshape(-1)
+    return t.from_numpy(numpy.ascontiguousarray(c, dtype=numpy.float64)).to(ctx.device)
+
+
+def _combine(ctx, Vd, nv, coef_host, x0, out):
+    """out = x0 + sum_j coef[j] V_j for a device block Vd and HOST coefficients (real block: real
+    coefficients; complex block: complex coefficients over its twin storage)."""
+    if _is_cplx(Vd):
+        tw = _twin_for(ctx, Vd)
+        c = numpy.zeros(nv, dtype=numpy.complex128)
+        c[:] = numpy.asarray(coef_host).reshape(-1)[:nv]
+        ctx.block_combine(tw.T, 2 * nv, _coefs_dev(ctx, c), x0, out)
+    else:
+        c = numpy.asarray(coef_host).reshape(-1)[:nv]
+        if numpy.iscomplexobj(c):
+            raise NotImplementedError("complex coefficients on a real block")
+        ctx.block_combine(Vd, nv, _coefs_dev(ctx, c), x0, out)
+
+
+def _caxpby(ctx, a, x, b, y, z):
+    """z = a*x + b*y with possibly complex scalars on (real or complex) device vectors"""
+    a, b = complex(a), complex(b)
+    if (a.imag == 0.0 and b.imag == 0.0) or not _is_cplx(x):
+        if a.imag != 0.0 or b.imag != 0.0:
+            raise NotImplementedError("complex scaling of a real block")
+        ctx.axpby(a.real, x, b.real, y, z)
+        return
+    t = _device.torch()
+    ix = t.empty_like(x)
+    ctx.rot90(x, ix)
+    if y is None or b == 0:
+        ctx.axpby(a.real, x, a.imag, ix, z)
+        return
+    if z.data_ptr() == y.data_ptr() and b == 1.0:
+        ctx.axpby(a.real, x, 1.0, y, z)
+        ctx.axpby(a.imag, ix, 1.0, z, z)
+        return
+    iy = t.empty_like(y)
+    ctx.rot90(y, iy)
+    tmp = t.empty_like(x)
+    ctx.axpby(a.real, x, a.imag, ix, tmp)
+    ctx.axpby(b.real, y, b.imag, iy, z)
+    ctx.axpby(1.0, tmp, 1.0, z, z)
 
 
 # --------------------------------------------------------------------------
@@ -346,12 +453,15 @@ class _ScaledLinearOperator(_DeviceOperator):
     def _apply_dev(self, Xd, out=None, adj=False):
         ctx = _ctx()
         alpha = self.args[1]
-        if numpy.iscomplexobj(alpha):
-            raise NotImplementedError("complex scaling is not supported by the device path")
         Y = self.args[0]._apply_dev(Xd, adj=adj)
         if out is None:
             out = Y if Y is not Xd else ctx.empty(Xd.shape, Xd.dtype)
-        ctx.axpby(float(alpha), Y, 0.0, None, out)
+        if numpy.iscomplexobj(alpha) and complex(alpha).imag != 0.0:
+            alpha = numpy.conj(alpha) if adj else alpha          # utils.py:1516-1519
+            for j in range(Y.shape[0]):
+                _caxpby(ctx, alpha, Y[j], 0.0, None, out[j])
+            return out
+        ctx.axpby(float(numpy.real(alpha)), Y, 0.0, None, out)
         return out
 
 
@@ -458,14 +568,21 @@ class MatrixLinearOperator(_DeviceOperator):
             if adj and self._A_adj is None:
                 self._A_adj = self._A.T.conj()
             A = self._A_adj if adj else self._A
-            if numpy.dtype(A.dtype).kind == "c":
-                raise NotImplementedError("complex matrices are not supported by the device path")
-            if _isspmatrix(A):
+            t = _device.torch()
+            if tdtype == t.complex128:
+                # complex vectors: the real kernels apply the 2N x 2N real embedding of A to the
+                # interleaved real views (entry a+ib -> [[a, -b], [b, a]], krypy_b200/_cplx.py)
+                if _isspmatrix(A):
+                    obj = ctx.upload_csr(_cplx.expand_sparse(A), t.float64)
+                else:
+                    obj = t.from_numpy(_cplx.expand_dense(numpy.asarray(A))).to(ctx.device)
+            elif numpy.dtype(A.dtype).kind == "c":
+                raise NotImplementedError("complex matrix applied to a real block")
+            elif _isspmatrix(A):
                 obj = ctx.upload_csr(A, tdtype)
             else:
                 npdt = _device.torch_to_np_dtype(tdtype)
-                obj = _device.torch().from_numpy(
-                    numpy.ascontiguousarray(numpy.asarray(A), dtype=npdt)).to(ctx.device)
+                obj = t.from_numpy(numpy.ascontiguousarray(numpy.asarray(A), dtype=npdt)).to(ctx.device)
             self._devcache[key] = obj
         return obj
 
@@ -474,7 +591,7 @@ class MatrixLinearOperator(_DeviceOperator):
         A = self._dev(Xd.dtype, adj)
         k = Xd.shape[0]
         if out is None:
-            out = ctx.empty((k, A.shape[0]), Xd.dtype)
+            out = ctx.empty((k, self.shape[1] if adj else self.shape[0]), Xd.dtype)
         sparse = isinstance(A, _device.CsrDev)
         for j in range(k):
             if sparse:
@@ -497,18 +614,28 @@ class DiagonalLinearOperator(_DeviceOperator):
         super(DiagonalLinearOperator, self).__init__((d.shape[0], d.shape[0]), d.dtype)
         self._d = d
         self._devcache = {}
+        self._as_matrix = None
 
     def _dev(self, tdtype):
         obj = self._devcache.get(tdtype)
         if obj is None:
-            if numpy.dtype(self._d.dtype).kind == "c":
-                raise NotImplementedError("complex diagonal not supported by the device path")
-            obj = _ctx().to_block(self._d, tdtype)[0]
+            t = _device.torch()
+            if tdtype == t.complex128:
+                # real diagonal acting on interleaved complex data: every entry twice
+                obj = _ctx().to_block(numpy.repeat(self._d.astype(numpy.float64), 2), t.float64)[0]
+            else:
+                obj = _ctx().to_block(self._d, tdtype)[0]
             self._devcache[tdtype] = obj
         return obj
 
     def _apply_dev(self, Xd, out=None, adj=False):
         ctx = _ctx()
+        if numpy.dtype(self._d.dtype).kind == "c":
+            # complex diagonal: the general (embedded sparse) path
+            if self._as_matrix is None:
+                import scipy.sparse as sp
+                self._as_matrix = MatrixLinearOperator(sp.diags(self._d).tocsr())
+            return self._as_matrix._apply_dev(Xd, out=out, adj=adj)
         d = self._dev(Xd.dtype)
         if out is None:
             out = ctx.empty(Xd.shape, Xd.dtype)
@@ -667,61 +794,89 @@ def _is_identity_ip(ip_B):
 
 
 def _inner_dev(Xd, Yd, ip_B=None, out=None):
-    """<X, Y> for device blocks X (m, N), Y (n, N) -> device (m, n) fp64 tensor
-    (krypy/utils.py:160-193).  Column j of the result is one kry_block_dot."""
+    """<X, Y> for device blocks X (m, N), Y (n, N) -> device (m, n) tensor, fp64 (complex128 for
+    complex blocks) (krypy/utils.py:160-193).  Column j of the result is one kry_block_dot; for
+    complex blocks two: Re = <X, y>_R and Im = -<X, i y>_R on the interleaved real views."""
     ctx = _ctx()
+    t = _device.torch()
     m, n = Xd.shape[0], Yd.shape[0]
-    if out is None:
+    cplx = _is_cplx(Xd) or _is_cplx(Yd)
+    if cplx and not (_is_cplx(Xd) and _is_cplx(Yd)):
+        Xd = Xd if _is_cplx(Xd) else Xd.to(t.complex128)
+        Yd = Yd if _is_cplx(Yd) else Yd.to(t.complex128)
+    if out is None or cplx:
         out = ctx.scalars(max(m * n, 1))[: m * n].reshape(n, m)
     if m == 0 or n == 0:
-        return out.t()
+        return out.t().to(t.complex128) if cplx else out.t()
     if not _is_identity_ip(ip_B):
         try:
             B = get_linearoperator((Xd.shape[1], Xd.shape[1]), ip_B)
         except TypeError:
             # callable inner product on host arrays (utils.py:186-189)
             G = numpy.asarray(ip_B(ctx.to_numpy(Xd), ctx.to_numpy(Yd)))
-            if numpy.iscomplexobj(G):
-                raise NotImplementedError("complex inner products are not supported")
-            res = _device.torch().from_numpy(numpy.ascontiguousarray(G, dtype=numpy.float64)).to(ctx.device)
-            return res
+            if numpy.iscomplexobj(G) and not cplx:
+                if numpy.abs(G.imag).max() > 0:
+                    raise NotImplementedError("complex-valued inner product of real blocks")
+                G = G.real
+            gdt = numpy.complex128 if cplx else numpy.float64
+            return t.from_numpy(numpy.ascontiguousarray(G, dtype=gdt)).to(ctx.device)
         if m > n:
-            # (B X)^H Y: for a real self-adjoint B this equals X^T (B Y) up to round-off;
+            # (B X)^H Y: for a self-adjoint B this equals X^H (B Y) up to round-off;
             # follow the reference's choice of which side gets B (utils.py:190-193)
-            BX = B._apply_dev(Xd)
-            for j in range(n):
-                ctx.block_dot(BX, m, Yd[j], out[j])
-            return out.t()
-        Yd = B._apply_dev(Yd)
+            Xd = B._apply_dev(Xd)
+        else:
+            Yd = B._apply_dev(Yd)
+    if not cplx:
+        for j in range(n):
+            ctx.block_dot(Xd, m, Yd[j], out[j])
+        return out.t()
+    out_im = ctx.scalars(m * n).reshape(n, m)
+    iy = ctx.empty((1, Yd.shape[1]), Yd.dtype)
     for j in range(n):
         ctx.block_dot(Xd, m, Yd[j], out[j])
-    return out.t()
+        ctx.rot90(Yd[j], iy[0])
+        ctx.block_dot(Xd, m, iy[0], out_im[j])
+    return t.complex(out, -out_im).t()
 
 
-def _ip_coef(Xd, Yd, ip_B, out, acc=None, post=0):
+def _ip_coef(Xd, Yd, ip_B, out, acc=None, post=0, x_twin=None):
     """out[0] = <x, y>_B for single-vector device blocks (1, N) without leaving the
     device (post=1: sqrt(|.|) as numpy.sqrt(numpy.linalg.norm(ip, 2)) gives for a
-    1x1 matrix, utils.py:238); acc[0] += out[0] when given."""
+    1x1 matrix, utils.py:238); acc[0] += out[0] when given.
+
+    Complex blocks: out[0] is the REAL part (all a norm, CG and Lanczos need, linsys.py:634-641,
+    utils.py:1003-1009); with ``x_twin`` (the real row ``i x`` of x's twin storage) the imaginary
+    part ``<i x, y>_R`` goes to out[1] (acc[1])."""
     ctx = _ctx()
+    want_im = x_twin is not None and _is_cplx(Xd) and not post
     if _is_identity_ip(ip_B):
         ctx.block_dot(Xd, 1, Yd[0], out, post, acc)
+        if want_im:
+            ctx.block_dot(x_twin.reshape(1, -1), 1, Yd[0], out[1:], 0, None if acc is None else acc[1:])
         return
     try:
         B = get_linearoperator((Xd.shape[1], Xd.shape[1]), ip_B)
     except TypeError:
         val = numpy.asarray(ip_B(ctx.to_numpy(Xd), ctx.to_numpy(Yd)))[0, 0]
-        if numpy.iscomplexobj(val):
+        im = float(numpy.imag(val))
+        if numpy.iscomplexobj(val) and not _is_cplx(Xd):
             if abs(val.imag) > 1e-10 * max(abs(val), 1e-300):
-                raise NotImplementedError("complex inner products are not supported")
-            val = val.real
-        val = float(val)
+                raise NotImplementedError("complex-valued inner product of real blocks")
+        val = float(numpy.real(val))
         if post:
             val = float(numpy.sqrt(abs(val)))
         out[0:1].fill_(val)
         if acc is not None:
             acc[0:1].add_(val)
+        if want_im:
+            out[1:2].fill_(im)
+            if acc is not None:
+                acc[1:2].add_(im)
         return
-    ctx.block_dot(Xd, 1, B._apply_dev(Yd)[0], out, post, acc)
+    BY = B._apply_dev(Yd)
+    ctx.block_dot(Xd, 1, BY[0], out, post, acc)
+    if want_im:
+        ctx.block_dot(x_twin.reshape(1, -1), 1, BY[0], out[1:], 0, None if acc is None else acc[1:])
 
 
 def ip_euclid(X, Y):
@@ -806,10 +961,30 @@ def _drotg(a, b):
     return a / r, b / r
 
 
+def _zrotg(a, b):
+    """BLAS zrotg (LAPACK 3.10 semantics), the host twin of kryc_zrotg in
+    csrc/kry_small_core.h; returns (c real, s complex)."""
+    a, b = complex(a), complex(b)
+    if b == 0:
+        return 1.0, 0j
+    if a == 0:
+        u = max(abs(b.real), abs(b.imag))
+        bs = b / u
+        return 0.0, numpy.conj(bs) / abs(bs)
+    u = max(abs(a.real), abs(a.imag), abs(b.real), abs(b.imag))
+    as_, bs = a / u, b / u
+    f2 = as_.real ** 2 + as_.imag ** 2
+    g2 = bs.real ** 2 + bs.imag ** 2
+    if f2 == 0.0:
+        return (abs(a) / u) / numpy.sqrt(g2), (a / abs(a)) * numpy.conj(bs) / numpy.sqrt(g2)
+    h2 = f2 + g2
+    return float(numpy.sqrt(f2 / h2)), numpy.conj(bs) * (as_ / numpy.sqrt(f2 * h2))
+
+
 class Givens:
-    """krypy/utils.py:405-436 for a real (2,1) vector.  This 2x2 helper is scalar
-    host arithmetic; inside the solvers the rotations are generated and applied
-    on the device (kry_givens_update / kry_minres_recur)."""
+    """krypy/utils.py:405-436 for a (2,1) vector (drotg for real-valued input, zrotg otherwise).
+    This 2x2 helper is scalar host arithmetic; inside the solvers the rotations are generated
+    and applied on the device (kry_givens_update[_z] / kry_minres_recur)."""
 
     def __init__(self, x):
         if x.shape != (2, 1):
@@ -821,7 +996,7 @@ class Givens:
             b = float(numpy.real(b))
             c, s = _drotg(a, b)
         else:
-            raise NotImplementedError("complex Givens rotations are not supported")
+            c, s = _zrotg(a, b)
         self.c = c
         self.s = s
         self.r = c * a + s * b
@@ -848,6 +1023,8 @@ def _qr_dev(Xd, ip_B=None, reorthos=1):
     product (krypy/utils.py:695-707).  Returns (Q (k, N) device, R numpy (k,k))."""
     ctx = _ctx()
     k, N = Xd.shape
+    if _is_cplx(Xd):
+        return _qr_dev_z(ctx, Xd, ip_B, reorthos)
     ld = (N + 31) // 32 * 32
     store = ctx.empty((max(k, 1), ld), Xd.dtype)
     Q = store[:k, :N]
@@ -875,6 +1052,37 @@ def _qr_dev(Xd, ip_B=None, reorthos=1):
     return Q, R
 
 
+def _qr_dev_z(ctx, Xd, ip_B, reorthos):
+    """complex ``_qr_dev``: the same MGS over twin storage (column i against the 2i real rows
+    ``q_0, i q_0, ...`` = complex MGS against i columns; coefficients come out interleaved)."""
+    k, N = Xd.shape
+    tw = _Twin.of(ctx, Xd)
+    Q, T = tw.C, tw.T
+    Rdev = ctx.scalars(max(2 * k * (k + 1), 2))
+    Rrows = Rdev[: 2 * k * (k + 1)].reshape(k, 2 * (k + 1)) if k else None
+    euclid = _is_identity_ip(ip_B)
+    tmp = ctx.scalars(2)
+    R = numpy.zeros((k, k), dtype=numpy.complex128)
+    for i in range(k):
+        qi = T[2 * i]
+        if euclid:
+            ctx.orth_fused(T, T, 0, 2 * i, qi, reorthos + 1, KRY_ORTH_MGS, Rrows[i], nrm=Rrows[i][2 * i:])
+        else:
+            for _ in range(reorthos + 1):
+                for j in range(i):
+                    _ip_coef(Q[j:j + 1], Q[i:i + 1], ip_B, tmp, acc=Rrows[i][2 * j:], x_twin=T[2 * j + 1])
+                    ctx.axpy_dev(tmp, -1.0, T[2 * j], qi)
+                    ctx.axpy_dev(tmp[1:], -1.0, T[2 * j + 1], qi)
+            _ip_coef(Q[i:i + 1], Q[i:i + 1], ip_B, Rrows[i][2 * i:], post=1)
+        ctx.sync()
+        col = _cplx.from_pairs(Rrows[i][: 2 * (i + 1)].cpu().numpy().reshape(1, -1))[0]
+        R[: i + 1, i] = col
+        if R[i, i].real >= 1e-15:                                   # utils.py:705-706
+            ctx.scale_dev(Rrows[i][2 * i:], 1, 1.0, qi, qi)
+        tw.refresh(ctx, i)
+    return Q, R
+
+
 def qr(X, ip_B=None, reorthos=1):
     """krypy/utils.py:680-707.  Always (re-orthogonalised) modified Gram-Schmidt
     on the device; the reference's LAPACK shortcut for ``ip_B is None`` (:692-693)
@@ -887,7 +1095,7 @@ def qr(X, ip_B=None, reorthos=1):
     if X.shape[1] == 0:
         return X.copy(), numpy.zeros((0, 0), dtype=X.dtype)
     Qd, R = _qr_dev(ctx.to_block(X, dt), ip_B, reorthos)
-    return ctx.to_numpy(Qd), R.astype(_common_type([X.dtype, numpy.float64]) if X.dtype.kind != "f" else X.dtype)
+    return ctx.to_numpy(Qd), R.astype(_common_type([X.dtype, numpy.float64]) if X.dtype.kind not in "fc" else X.dtype)
 
 
 class Projection(object):
@@ -942,8 +1150,16 @@ class Projection(object):
             M = _inner_dev(self._Wd, self._Vd, ip_B).cpu().numpy()
             self.Q, self.R = scipy.linalg.qr(M)           # k x k host algebra (utils.py:520)
             t = _device.torch()
-            self._Q_dev = t.from_numpy(numpy.ascontiguousarray(self.Q, dtype=numpy.float64)).to(ctx.device)
-            self._R_dev = t.from_numpy(numpy.ascontiguousarray(self.R, dtype=numpy.float64)).to(ctx.device)
+            if _is_cplx(Xd):
+                # kry_project computes R_dev^-1 (Q_dev^T c) on the 2k interleaved coefficients; the
+                # embedding of a triangular complex R is only BLOCK triangular, so the kernel gets
+                # the embedded product  T = R^-1 Q^H  as its "Q^T" and the identity as its "R"
+                Tm = scipy.linalg.solve_triangular(self.R, self.Q.T.conj())
+                self._Q_dev = t.from_numpy(numpy.ascontiguousarray(_cplx.expand_dense(Tm).T)).to(ctx.device)
+                self._R_dev = t.from_numpy(numpy.eye(2 * self._k)).to(ctx.device)
+            else:
+                self._Q_dev = t.from_numpy(numpy.ascontiguousarray(self.Q, dtype=numpy.float64)).to(ctx.device)
+                self._R_dev = t.from_numpy(numpy.ascontiguousarray(self.R, dtype=numpy.float64)).to(ctx.device)
 
     @property
     def V(self):
@@ -967,22 +1183,21 @@ class Projection(object):
         (krypy/utils.py:522-564).  ``c_first`` (device, k doubles per column) receives the raw
         ``<W, a>`` like the fused kernel's ``c_first_dev``."""
         ctx = _ctx()
-        t = _device.torch()
         m = ad.shape[0]
         Wd, Vd = (self._Vd, self._Wd) if adj else (self._Wd, self._Vd)
         c = _inner_dev(Wd, ad, self.ip_B).cpu().numpy().copy()   # (k, m), small
         if c_first is not None:
-            c_first[: self._k * m].copy_(t.from_numpy(numpy.ascontiguousarray(c.T.reshape(-1))).to(ctx.device))
+            cf = _coefs_dev(ctx, c.T.reshape(-1))                # complex: interleaved, 2k per column
+            c_first[: cf.numel()].copy_(cf)
         Ya = None
         if return_Ya:
             Ya = c.copy()
             if self.WR is not None:
                 Ya = self.WR.T.conj().dot(Ya)
-        c = numpy.ascontiguousarray(self._coef_transform(c, adj=adj).T, dtype=numpy.float64)  # (m, k)
-        cd = t.from_numpy(c).to(ctx.device)
+        c = self._coef_transform(c, adj=adj)                     # (k, m)
         Pa = ctx.empty(ad.shape, ad.dtype)
         for j in range(m):
-            ctx.block_combine(Vd, self._k, cd[j], None, Pa[j])
+            _combine(ctx, Vd, self._k, c[:, j], None, Pa[j])
         return (Pa, Ya) if return_Ya else Pa
 
     def _complement_dev(self, ad, return_Ya=False, c_first=None, out=None):
@@ -997,16 +1212,22 @@ class Projection(object):
         if self._k == 0:
             return (out, numpy.zeros((0, ad.shape[0]))) if return_Ya else out
         m = ad.shape[0]
-        if _is_identity_ip(self.ip_B):
+        cplx = _is_cplx(ad)
+        kk = 2 * self._k if cplx else self._k            # real rows / coefficients per vector
+        if _is_identity_ip(self.ip_B) and kk <= _CGS_CHUNK:
             own = c_first is None and return_Ya
             if own:
-                c_first = ctx.scalars(self._k * m)
+                c_first = ctx.scalars(kk * m)
+            if cplx:
+                Wb, Vb = _twin_for(ctx, self._Wd).T, _twin_for(ctx, self._Vd).T
+            else:
+                Wb, Vb = self._Wd, self._Vd
             for j in range(m):
-                cf = None if c_first is None else c_first[j * self._k:(j + 1) * self._k]
-                ctx.project(self._Wd, self._Vd, self._k, out[j], self._Q_dev, self._R_dev,
-                            self.iterations, cf)
+                cf = None if c_first is None else c_first[j * kk:(j + 1) * kk]
+                ctx.project(Wb, Vb, kk, out[j], self._Q_dev, self._R_dev, self.iterations, cf)
             if return_Ya:
-                Ya = c_first[: self._k * m].reshape(m, self._k).t().cpu().numpy()
+                Ya = c_first[: kk * m].reshape(m, kk).cpu().numpy()
+                Ya = (_cplx.from_pairs(Ya) if cplx else Ya).T
                 if self.WR is not None:
                     Ya = self.WR.T.conj().dot(Ya)
                 return out, Ya
@@ -1241,23 +1462,43 @@ class Arnoldi(object):
                 "(and cgs, cgs2 on the device path)." % ortho)
         self._algo, self._passes = _ORTHO[ortho]
         td = self._td = _compute_dtype(self.dtype)
+        self._cplx = cplx = td == t.complex128
+        self._nr = nr = 2 if cplx else 1          # real rows per basis vector / doubles per coefficient
         self.iter = 0
         self.invariant = False
         m1 = self.maxiter + 1
-        if ws is not None:
-            self._Vs = ws.tensor("V", (m1, N, td), lambda: ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A)))
-        else:
-            self._Vs = ctx.alloc_basis(m1, N, td, _rightmost_factor(self.A))
-        self._ld = self._Vs.stride(0)
         rf = _rightmost_factor(self.A)
         self._halo_op = rf if (ctx.comm is not None and hasattr(rf, "_halo_args")) else None
         if ctx.comm is not None:
             ctx.comm.halo_ready = None
-        self._Vd = self._Vs[:, :N]
         self._Pd = None
-        if self.M is not None:
-            self._Ps = ctx.alloc_basis(m1, N, td)
-            self._Pd = self._Ps[:, :N]
+        if cplx:
+            # twin storage: rows 2j, 2j+1 = v_j, i v_j; the kernels work on the real rows
+            if ctx.comm is not None:
+                raise NotImplementedError("complex row-partitioned runs are not implemented")
+            if ws is not None:
+                self._Vtw = ws.tensor("Vtw", (m1, N), lambda: _Twin(ctx, m1, N))
+            else:
+                self._Vtw = _Twin(ctx, m1, N)
+            self._Vs = self._Vtw.store
+            self._Vd, self._Vt = self._Vtw.C, self._Vtw.T
+            self._Pt = None
+            if self.M is not None:
+                self._Ptw = _Twin(ctx, m1, N)
+                self._Pd, self._Pt = self._Ptw.C, self._Ptw.T
+        else:
+            if ws is not None:
+                self._Vs = ws.tensor("V", (m1, N, td), lambda: ctx.alloc_basis(m1, N, td, rf))
+            else:
+                self._Vs = ctx.alloc_basis(m1, N, td, rf)
+            self._Vd = self._Vs[:, :N]
+            self._Vt = self._Vd
+            self._Pt = None
+            if self.M is not None:
+                self._Ps = ctx.alloc_basis(m1, N, td)
+                self._Pd = self._Ps[:, :N]
+                self._Pt = self._Pd
+        self._ld = self._Vs.stride(0)
         # small quantities are always >= fp64 on the device path (also in fp32 storage mode)
         self.H = numpy.zeros((self.maxiter + 1, self.maxiter), dtype=_common_type([self.dtype, numpy.float64]))
         self._euclid = _is_identity_ip(ip_B)
@@ -1265,7 +1506,8 @@ class Arnoldi(object):
             # buffers persist across restart cycles so that a step's launch arguments are stable
             # (CUDA-graph replay); everything that must start from zero is re-zeroed here
             self._q = ws.tensor("q", (1, N, td), lambda: ctx.empty((1, N), td))
-            self._hcol_store = ws.tensor("hcol", (self.maxiter + 10,), lambda: ctx.scalars(self.maxiter + 2 + 8))
+            self._hcol_store = ws.tensor("hcol", (nr * (self.maxiter + 10),),
+                                         lambda: ctx.scalars(nr * (self.maxiter + 2 + 8)))
             self._tmp = ws.tensor("tmp", (4,), lambda: ctx.scalars(4))
             self._lz = ws.tensor("lz", (3,), lambda: ctx.scalars(3))
             self._lz_st = ws.tensor("lz_st", (16,), lambda: ctx.scalars(16))
@@ -1273,12 +1515,12 @@ class Arnoldi(object):
                 buf.zero_()
         else:
             self._q = ctx.empty((1, N), td)
-            self._hcol_store = ctx.scalars(self.maxiter + 2 + 8)
+            self._hcol_store = ctx.scalars(nr * (self.maxiter + 2 + 8))
             self._tmp = ctx.scalars(4)
             self._lz = ctx.scalars(3)          # Lanczos: [H[k-1,k], H[k,k], H[k+1,k]]
             self._lz_st = ctx.scalars(16)
         self._t = None if (self._euclid and self.M is None) else ctx.empty((1, N), td)
-        self._hcol = self._hcol_store[1:]       # one leading zero: H[-1, 0] of linsys.py:828
+        self._hcol = self._hcol_store[nr:]      # one leading zero: H[-1, 0] of linsys.py:828
         self._hfro2 = 0.0
 
         # first basis vector: utils.py:923-952
@@ -1297,6 +1539,8 @@ class Arnoldi(object):
                 self.vnorm = Mv_norm
             if self.vnorm > 0:
                 self._set_scaled(self._Pd[0], pd[0], self.vnorm)
+                if cplx:
+                    self._Ptw.refresh(ctx, 0)
         else:
             if Mv_norm is None:
                 self.vnorm = self._norm_dev(vd, None)
@@ -1304,6 +1548,8 @@ class Arnoldi(object):
                 self.vnorm = Mv_norm
         if self.vnorm > 0:
             self._set_scaled(self._Vd[0], vd[0], self.vnorm)
+            if cplx:
+                self._Vtw.refresh(ctx, 0)
         else:
             self.invariant = True
 
@@ -1325,47 +1571,57 @@ class Arnoldi(object):
         self._lz for Lanczos), H[k+1,k] in hcol[k+1] (lz[2]), V[k+1] (P[k+1]) stored."""
         ctx = self._ctx
         V, P = self._Vd, self._Pd
+        # Vt/Pt: the rows the kernels work on.  Real: the basis itself.  Complex: twin storage,
+        # rows nr*j (+1) = v_j (i v_j); coefficients are nr doubles each (interleaved re/im).
+        Vt, Pt, nr, cplx = self._Vt, self._Pt, self._nr, self._cplx
         q = self._q
         self.A._apply_dev(V[k:k + 1], out=q)                       # utils.py:968
         q0 = q[0]
         lanczos = self.ortho == "lanczos"
-        start = k if lanczos else 0
-        Vsub = P if P is not None else V
+        Vsub = Pt if Pt is not None else Vt
         if lanczos:
-            h_ptr = self._lz.data_ptr() + 8 * (1 - k)               # h[k] -> lz[1]
+            # three-term recurrence with REAL coefficients (alpha.real, utils.py:1003-1009): also for
+            # complex data only the real row of v_k takes part
+            r0, r1 = nr * k, nr * k + 1
+            h_ptr = self._lz.data_ptr() + 8 * (1 - r0)              # h[k] -> lz[1]
             nrm = self._lz[2:]
-            pre_vec = Vsub[k - 1] if k > 0 else None
+            pre_vec = Vsub[nr * (k - 1)] if k > 0 else None
             pre_coef = self._lz if k > 0 else None
         else:
+            r0, r1 = 0, nr * (k + 1)
             h_ptr = self._hcol.data_ptr()
-            nrm = self._hcol[k + 1:]
+            nrm = self._hcol[nr * (k + 1):]
             pre_vec = pre_coef = None
+        vnext = Vt[nr * (k + 1)]
         if self._euclid:
             fused_tail = self.M is None
-            if self._algo == KRY_ORTH_CGS and (k + 1 - start) > _CGS_CHUNK:
+            if self._algo == KRY_ORTH_CGS and (r1 - r0) > _CGS_CHUNK:
                 # more basis vectors than reduction slots: block-wise CGS
-                j0 = start
-                while j0 < k + 1:
-                    j1 = min(j0 + _CGS_CHUNK, k + 1)
-                    last = j1 == k + 1
-                    ctx.orth_fused(V, Vsub, j0, j1, q0, self._passes, self._algo, None,
+                j0 = r0
+                while j0 < r1:
+                    j1 = min(j0 + _CGS_CHUNK, r1)
+                    last = j1 == r1
+                    ctx.orth_fused(Vt, Vsub, j0, j1, q0, self._passes, self._algo, None,
                                    nrm=nrm if (last and fused_tail) else None,
-                                   vnext=V[k + 1] if (last and fused_tail) else None, h_ptr=h_ptr)
+                                   vnext=vnext if (last and fused_tail) else None, h_ptr=h_ptr)
                     j0 = j1
             else:
-                ctx.orth_fused(V, Vsub, start, k + 1, q0, self._passes, self._algo, None,
+                ctx.orth_fused(Vt, Vsub, r0, r1, q0, self._passes, self._algo, None,
                                nrm=nrm if fused_tail else None,
-                               vnext=V[k + 1] if fused_tail else None,
+                               vnext=vnext if fused_tail else None,
                                pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr, halo_op=self._halo_op)
         else:
             # generic inner product: the reference's loop, one reduction at a time
             if pre_vec is not None:
                 ctx.axpy_dev(pre_coef, -1.0, pre_vec, q0)
             for _ in range(self._passes):
-                for j in range(start, k + 1):
-                    hslot = self._lz[1:] if lanczos else self._hcol[j:]
-                    _ip_coef(V[j:j + 1], q, self.ip_B, self._tmp, acc=hslot)     # utils.py:1015, 1025
-                    ctx.axpy_dev(self._tmp, -1.0, Vsub[j], q0)                    # utils.py:1026-1029
+                for j in range(k if lanczos else 0, k + 1):
+                    hslot = self._lz[1:] if lanczos else self._hcol[nr * j:]
+                    tw = Vt[nr * j + 1] if (cplx and not lanczos) else None
+                    _ip_coef(V[j:j + 1], q, self.ip_B, self._tmp, acc=hslot, x_twin=tw)   # utils.py:1015, 1025
+                    ctx.axpy_dev(self._tmp, -1.0, Vsub[nr * j], q0)                       # utils.py:1026-1029
+                    if tw is not None:
+                        ctx.axpy_dev(self._tmp[1:], -1.0, Vsub[nr * j + 1], q0)
             fused_tail = False
         if not fused_tail:
             # utils.py:1030-1045: M apply, norm, scaled stores
@@ -1374,9 +1630,13 @@ class Arnoldi(object):
                 _ip_coef(q, MAv, self.ip_B, nrm, post=1)
                 ctx.scale_dev(nrm, 1, 1.0, q0, P[k + 1])
                 ctx.scale_dev(nrm, 1, 1.0, MAv[0], V[k + 1])
+                if cplx:
+                    self._Ptw.refresh(ctx, k + 1)
             else:
                 _ip_coef(q, q, self.ip_B, nrm, post=1)
                 ctx.scale_dev(nrm, 1, 1.0, q0, V[k + 1])
+        if cplx:
+            self._Vtw.refresh(ctx, k + 1)
 
     def _finish(self, k, hcol_host):
         """Host bookkeeping of step k given H[0..k+1, k] (utils.py:1025, 1032-1039, 1048)."""
@@ -1386,12 +1646,12 @@ class Arnoldi(object):
                 H[k - 1, k] = H[k, k - 1]                         # utils.py:1003
             H[k, k] = hcol_host[0]
             H[k + 1, k] = hcol_host[1]
-            col2 = hcol_host[0] ** 2 + hcol_host[1] ** 2 + (H[k - 1, k] ** 2 if k > 0 else 0.0)
+            col2 = hcol_host[0] ** 2 + hcol_host[1] ** 2 + (abs(H[k - 1, k]) ** 2 if k > 0 else 0.0)
         else:
             H[: k + 2, k] = hcol_host[: k + 2]
-            col2 = float(numpy.dot(hcol_host[: k + 2], hcol_host[: k + 2]))
+            col2 = float(numpy.sum(numpy.abs(hcol_host[: k + 2]) ** 2))
         self._hfro2 += col2
-        hk = H[k + 1, k]
+        hk = float(numpy.real(H[k + 1, k]))
         # invariant-subspace test H[k+1,k]/||H[:k+2,:k+1]||_2 <= 1e-14 (utils.py:1035-1039).
         # ||H||_2 <= ||H||_F, so the SVD is only needed when the cheap bound cannot decide.
         if not numpy.isfinite(hk):
@@ -1416,9 +1676,14 @@ class Arnoldi(object):
             ctx.sync()
             self._finish(k, ctx.mailbox[6:8].copy())
         else:
-            hc = self._hcol[: k + 2].cpu().numpy().copy()            # synchronising D2H of k+2 doubles
-            self._hcol[: k + 2].zero_()
-            self._finish(k, hc)
+            self._finish(k, self._read_hcol(k))
+
+    def _read_hcol(self, k):
+        """synchronising D2H of column k of H (k+2 coefficients); re-zeroes the accumulator"""
+        n = self._nr * (k + 2)
+        hc = self._hcol[:n].cpu().numpy().copy()
+        self._hcol[:n].zero_()
+        return _cplx.from_pairs(hc.reshape(1, -1))[0] if self._cplx else hc
 
     # -- accessors ------------------------------------------------------------------
     def _block_np(self, Bd, ncols):

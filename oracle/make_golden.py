@@ -82,13 +82,16 @@ def main():
     krypy = refshim.import_reference()
     outdir = os.path.join(ROOT, "tests", "golden")
     os.makedirs(outdir, exist_ok=True)
-    for name in cases.ALL_CASES:
+    # python oracle/make_golden.py [name ...]: only the named cases (default: all)
+    names = sys.argv[1:] or (cases.ALL_CASES + cases.COMPLEX_CASES)
+    for name in names:
         out = run_reference(krypy, name)
         np.savez_compressed(os.path.join(outdir, name + ".npz"), **out)
         print("%-28s its=%3d last=%.6e conv=%s" % (
             name, len(out["resnorms"]) - 1, out["resnorms"][-1], bool(out["converged"])))
-    np.savez_compressed(os.path.join(outdir, "givens_table.npz"), table=givens_table(krypy))
-    print("givens table written")
+    if not sys.argv[1:]:
+        np.savez_compressed(os.path.join(outdir, "givens_table.npz"), table=givens_table(krypy))
+        print("givens table written")
 
 
 if __name__ == "__main__":

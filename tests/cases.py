@@ -133,9 +133,96 @@ def case_inputs(name):
         c["solver"] = name.rsplit("_", 1)[1]
         c["kw"] = dict(U=rng.standard_normal((n * n, 3)), tol=1e-9, maxiter=60,
                        store_arnoldi=True)
+    elif name.startswith("z_"):
+        _complex_case(name, c, rng)
     else:
         raise KeyError(name)
     return c
+
+
+def _herm_sparse(n, theta=0.3):
+    """Hermitian positive definite sparse test matrix: the 2-D 5-point Laplacian with complex hopping
+    phases exp(+-i*theta) on the x-bonds (a "magnetic" Laplacian)."""
+    T = sp.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(n, n))
+    Tp = sp.diags([-np.exp(-1j * theta), 2.0, -np.exp(1j * theta)], [-1, 0, 1], shape=(n, n))
+    I = sp.identity(n)
+    return sp.csr_matrix(sp.kron(I, Tp) + sp.kron(T, I))
+
+
+def _complex_case(name, c, rng):
+    """complex128 cases (half of the reference's own test matrix is complex, test/test_linsys.py:118-141)"""
+    def crandn(*shape):
+        return rng.standard_normal(shape) + 1j * rng.standard_normal(shape)
+
+    if name in ("z_gmres_helmholtz", "z_gmres_helmholtz_dmgs", "z_restarted_gmres"):
+        # damped Helmholtz: (L - sigma I) + i*delta I, complex symmetric, non-Hermitian
+        n = 20
+        A = problems.laplace2d(n).astype(np.complex128) + (-0.4 + 0.35j) * sp.identity(n * n)
+        c["A"] = sp.csr_matrix(A)
+        c["b"] = crandn(n * n, 1)
+        if name == "z_restarted_gmres":
+            c["solver"] = "restarted_gmres"
+            c["kw"] = dict(maxiter=15, max_restarts=3, tol=1e-12)
+        else:
+            c["solver"] = "gmres"
+            c["kw"] = dict(maxiter=40, tol=1e-12, store_arnoldi=True,
+                           ortho="dmgs" if name.endswith("dmgs") else "mgs")
+    elif name == "z_gmres_realA_complexb":
+        n = 16
+        c["A"] = problems.convdiff2d(n, c=0.1)
+        c["b"] = crandn(n * n)
+        c["solver"] = "gmres"
+        c["kw"] = dict(maxiter=40, tol=1e-11, x0=crandn(n * n, 1))
+    elif name in ("z_cg_hpd", "z_minres_herm", "z_minres_herm_mgs", "z_defl_cg", "z_defl_minres"):
+        n = 14
+        A = _herm_sparse(n)
+        c["b"] = crandn(n * n, 1)
+        if "minres" in name:
+            A = sp.csr_matrix(A - 1.1 * sp.identity(n * n))         # Hermitian indefinite
+            c["ls"] = dict(self_adjoint=True)
+            c["solver"] = "minres"
+            c["kw"] = dict(tol=1e-9, maxiter=30, store_arnoldi=True)
+            if name.endswith("mgs"):
+                c["kw"]["ortho"] = "mgs"
+        else:
+            c["ls"] = dict(self_adjoint=True, positive_definite=True)
+            c["solver"] = "cg"
+            c["kw"] = dict(tol=1e-9, maxiter=60, store_arnoldi=True)
+        c["A"] = A
+        if "defl" in name:
+            c["kw"]["U"] = crandn(n * n, 3)
+    elif name in ("z_defl_gmres", "z_defl_gmres_ipB"):
+        n = 16
+        A = problems.convdiff2d(n, c=0.1).astype(np.complex128) + 0.25j * sp.identity(n * n)
+        c["A"] = sp.csr_matrix(A)
+        c["b"] = crandn(n * n, 1)
+        c["solver"] = "gmres"
+        c["kw"] = dict(U=crandn(n * n, 4), maxiter=30, tol=1e-10, store_arnoldi=True)
+        if name.endswith("ipB"):
+            c["ls"] = dict(ip_B=sp.diags(np.linspace(1.0, 2.0, n * n)).tocsr())
+    elif name in ("z_dense_gmres_M_ipB", "z_dense_minres_M_ipB", "z_dense_cg_M_ipB"):
+        N = 30
+        S = crandn(N, N)
+        S = S + S.conj().T
+        Bs = crandn(N, N)
+        Bm = np.eye(N) * 1.5 + 0.02 * (Bs + Bs.conj().T)          # Hermitian positive definite
+        K = np.diag(np.linspace(1, 4, N)) + 0.05 * S + 2 * np.eye(N)
+        c["A"] = np.linalg.solve(Bm, K)                            # self-adjoint in <.,.>_B
+        c["b"] = crandn(N, 1)
+        c["ls"] = dict(M=0.5 * np.eye(N), Minv=2.0 * np.eye(N), ip_B=Bm, self_adjoint=True,
+                       positive_definite=True)
+        c["solver"] = name.split("_")[2]
+        c["kw"] = dict(tol=1e-11, maxiter=40, store_arnoldi=True)
+    elif name == "z_dense_gmres_MlMr":
+        N = 40
+        c["A"] = np.diag(np.linspace(1, 10, N)) + 0.3 * crandn(N, N)
+        c["b"] = crandn(N)
+        c["ls"] = dict(Ml=np.diag(1.0 / np.linspace(1, 10, N)) * (1 + 0.2j),
+                       Mr=np.diag(np.linspace(0.5, 1.5, N)))
+        c["solver"] = "gmres"
+        c["kw"] = dict(tol=1e-12, maxiter=40, x0=crandn(N, 1), store_arnoldi=True)
+    else:
+        raise KeyError(name)
 
 
 ALL_CASES = [
@@ -146,4 +233,12 @@ ALL_CASES = [
     "dense_gmres_M_ipB", "dense_minres_M_ipB", "dense_cg_M_ipB", "dense_gmres_MlMr",
     "lucky_breakdown", "zero_rhs", "maxiter_noconv", "cg_explicit_residual",
     "lap2d_defl_cg", "lap2d_defl_minres",
+]
+
+# complex128 systems (device path: real embedding + twin storage, krypy_b200/_cplx.py)
+COMPLEX_CASES = [
+    "z_gmres_helmholtz", "z_gmres_helmholtz_dmgs", "z_restarted_gmres", "z_gmres_realA_complexb",
+    "z_cg_hpd", "z_minres_herm", "z_minres_herm_mgs", "z_defl_cg", "z_defl_minres",
+    "z_defl_gmres", "z_defl_gmres_ipB", "z_dense_gmres_M_ipB", "z_dense_minres_M_ipB",
+    "z_dense_cg_M_ipB", "z_dense_gmres_MlMr",
 ]

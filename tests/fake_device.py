@@ -18,6 +18,7 @@ import scipy.sparse as sp
 import torch
 
 from krypy_b200 import _device
+from krypy_b200._device import realviews
 from krypy_b200._lib import KRY_ORTH_CGS
 
 
@@ -99,12 +100,14 @@ class FakeContext(object):
 
     def to_block(self, X, dtype):
         if isinstance(X, torch.Tensor):
+            if X.is_complex() and dtype != torch.complex128:
+                raise NotImplementedError("complex vectors need a complex linear system / solver dtype")
             Xt = X.detach().to(dtype=dtype)
             Xt = Xt.reshape(1, -1) if Xt.dim() == 1 else Xt.t()
             return Xt.contiguous().clone()
         X = np.asarray(X)
-        if np.iscomplexobj(X):
-            raise NotImplementedError("complex vectors are not supported by the device path")
+        if np.iscomplexobj(X) and dtype != torch.complex128:
+            raise NotImplementedError("complex vectors need a complex linear system / solver dtype")
         if X.ndim == 1:
             X = X.reshape(-1, 1)
         return torch.from_numpy(np.ascontiguousarray(X.T, dtype=_device.torch_to_np_dtype(dtype))).clone()
@@ -119,6 +122,7 @@ class FakeContext(object):
                               torch.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)), A.shape)
 
     # ---- operators (kry_spmv_csr, kry_gemv_dense, kry_diag_mul) ----
+    @realviews
     def spmv(self, A, x, y, w=None, dot_out=None):
         self._count("spmv")
         M = sp.csr_matrix((A.vals.numpy().astype(np.float64), A.colidx.numpy(), A.rowptr.numpy()), shape=A.shape)
@@ -128,15 +132,18 @@ class FakeContext(object):
         if w is not None:
             dot_out[0] = float(w.numpy().astype(np.float64) @ r)
 
+    @realviews
     def gemv(self, A, x, y):
         self._count("gemv")
         y.copy_(torch.from_numpy(A.numpy().astype(np.float64) @ x.numpy().astype(np.float64)).to(y.dtype))
 
+    @realviews
     def diag_mul(self, d, x, y):
         self._count("diag_mul")
         y.copy_((d.double() * x.double()).to(y.dtype))
 
     # ---- elementwise (kry_axpby, kry_axpy_dev, kry_scale_dev) ----
+    @realviews
     def axpby(self, a, x, b, y, z):
         self._count("axpby")
         r = float(a) * x.double()
@@ -144,15 +151,18 @@ class FakeContext(object):
             r = r + float(b) * y.double()
         z.copy_(r.to(z.dtype))
 
+    @realviews
     def axpy_dev(self, coef, sign, x, y):
         self._count("axpy_dev")
         y.copy_((y.double() + float(sign) * float(coef[0]) * x.double()).to(y.dtype))
 
+    @realviews
     def scale_dev(self, s, divide, mul, x, out):
         self._count("scale_dev")
         v = float(mul) * x.double()
         out.copy_((v / float(s[0]) if divide else v * float(s[0])).to(out.dtype))
 
+    @realviews
     def rot90(self, x, y):
         self._count("rot90")
         xv = x.detach().clone()
@@ -160,6 +170,7 @@ class FakeContext(object):
         y[1::2] = xv[0::2]
 
     # ---- tall-skinny (kry_block_dot, kry_block_axpy, kry_block_combine) ----
+    @realviews
     def block_dot(self, V, nv, q, out, post=0, acc=None):
         self._count("block_dot")
         o = _view(out, nv)
@@ -173,6 +184,7 @@ class FakeContext(object):
             if a is not None:
                 a[j] += s
 
+    @realviews
     def block_axpy(self, V, nv, coef, sign, q):
         self._count("block_axpy")
         r = q.double()
@@ -180,6 +192,7 @@ class FakeContext(object):
             r = r + float(sign) * float(coef[j]) * V[j].double()
         q.copy_(r.to(q.dtype))
 
+    @realviews
     def block_combine(self, V, nv, coef, x0, out):
         self._count("block_combine")
         s = torch.zeros(out.shape, dtype=torch.float64)
@@ -190,6 +203,7 @@ class FakeContext(object):
         out.copy_(s.to(out.dtype))
 
     # ---- kry_orth_fused ----
+    @realviews
     def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
                    pre_coef=None, h_ptr=None, halo_op=None):
         self._count("orth_fused")
@@ -217,6 +231,7 @@ class FakeContext(object):
                 vnext.copy_((qq / n2 if n2 > 0 else torch.zeros_like(qq)).to(vnext.dtype))
 
     # ---- kry_project ----
+    @realviews
     def project(self, W, V, d, a, Q, R, iterations, c_first):
         import scipy.linalg
         self._count("project")
@@ -252,6 +267,45 @@ class FakeContext(object):
         rcol.numpy()[: k + 2] = r
         mb[off + k + 3: off + 2 * k + 5] = r
 
+    def givens_update_z(self, k, hcol, rcol, cs, y, off=0):
+        """csrc/kry_small.cu: givens_z_kernel (interleaved complex; drotg for real-valued pairs,
+        zrotg otherwise; the serial core itself is tested in tests/test_small_core_cpu.py)"""
+        self._count("givens_z")
+        from krypy_b200.utils import _zrotg
+        h = hcol.numpy()
+        nr = 2 * (k + 2)
+        mb = self.mailbox
+        mb[off + 1: off + 1 + nr] = h[:nr]
+        r = h[:nr].copy().view(np.complex128)
+        h[:nr] = 0.0
+        c_ = cs.numpy()
+
+        def rot(c, s, x0, x1):
+            return c * x0 + s * x1, -np.conj(s) * x0 + c * x1
+        for i in range(k):
+            r[i], r[i + 1] = rot(c_[4 * i], complex(c_[4 * i + 2], c_[4 * i + 3]), r[i], r[i + 1])
+        if r[k].imag == 0.0 and r[k + 1].imag == 0.0:
+            c, s = _drotg(r[k].real, r[k + 1].real)
+            s = complex(s)
+            flag = 1.0
+        else:
+            c, s = _zrotg(r[k], r[k + 1])
+            flag = 0.0
+        c_[4 * k: 4 * k + 4] = [c, flag, s.real, s.imag]
+        r[k], r[k + 1] = rot(c, s, r[k], r[k + 1])
+        yy = y.numpy()[:nr].view(np.complex128)
+        yy[k], yy[k + 1] = rot(c, s, yy[k], yy[k + 1])
+        mb[off] = abs(yy[k + 1])
+        rcol.numpy()[:nr] = r.view(np.float64)
+        mb[off + 1 + nr: off + 1 + 2 * nr] = r.view(np.float64)
+
+    def tri_solve_z(self, k, R, y, out):
+        import scipy.linalg
+        self._count("tri_solve_z")
+        Rc = np.ascontiguousarray(R.numpy()[:k, :2 * k]).view(np.complex128)
+        yc = y.numpy()[:2 * k].copy().view(np.complex128)
+        out.numpy()[:2 * k] = scipy.linalg.solve_triangular(Rc, yc).view(np.float64)
+
     def tri_solve(self, k, R, y, out):
         import scipy.linalg
         self._count("tri_solve")
@@ -280,6 +334,7 @@ class FakeContext(object):
             h[0] = h[2]
             h[1] = 0.0
 
+    @realviews
     def minres_update(self, v, w0, w1, yk, st):
         self._count("minres_update")
         s_ = st.numpy()
@@ -287,6 +342,7 @@ class FakeContext(object):
         w0.copy_(z)
         yk.copy_((yk.double() + s_[11] * z.double()).to(yk.dtype))
 
+    @realviews
     def cg_update(self, Ap, p, yk, r, z, dinv, rho, pAp, off=0):
         self._count("cg_update")
         pap = float(pAp[0])

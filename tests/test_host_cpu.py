@@ -91,8 +91,9 @@ def test_host_operator_dispatch_and_dtype_rules():
     assert (g.c, g.s, g.r) == (-0.6, 0.8, -5.0)
     g = u.Givens(np.array([[0.0], [0.0]]))
     assert (g.c, g.s, g.r) == (1.0, 0.0, 0.0)
-    with pytest.raises(NotImplementedError):
-        u._compute_dtype(np.complex128)
+    import torch
+    assert u._compute_dtype(np.complex64) == torch.complex128        # complex runs by real embedding
+    assert u._compute_dtype(np.int32) == torch.float64 and u._compute_dtype(np.float32) == torch.float32
 
 
 def test_givens_host_twin_matches_reference_table():

@@ -24,7 +24,7 @@ def _check_history(got, ref, rtol=1e-10, atol=5e-13):   # explicit entries of th
     assert np.all(err <= bound), (int(np.argmax(err / bound)), float((err / bound).max()))
 
 
-@pytest.mark.parametrize("name", cases.ALL_CASES)
+@pytest.mark.parametrize("name", cases.ALL_CASES + cases.COMPLEX_CASES)
 def test_host_logic_reproduces_reference_fixtures(fake, name):
     gold = runners.load_golden(name)
     got = runners.run_product(name)
@@ -101,8 +101,9 @@ def test_host_logic_known_answers_and_semantics(fake):
     assert r.resnorms[-1] <= 1e-5
     with pytest.raises(kp.utils.ConvergenceError):
         kp.linsys.RestartedGmres(ls, maxiter=5, max_restarts=1)
-    with pytest.raises(NotImplementedError):
-        kp.linsys.LinearSystem(A.astype(complex), b)
+    zs = kp.linsys.Gmres(kp.linsys.LinearSystem(A.astype(complex), (1 + 1j) * b), tol=1e-8)   # complex: real embedding
+    assert zs.xk.dtype == np.complex128 and zs.resnorms[-1] <= 1e-8
+    assert np.allclose(zs.xk.reshape(-1), (1 + 1j) * np.linalg.solve(A, b).reshape(-1), rtol=1e-6)
     with pytest.raises(NotImplementedError):
         kp.linsys.Gmres(ls, ortho="house")
     with pytest.raises(kp.utils.ArgumentError):

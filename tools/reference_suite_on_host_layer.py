@@ -41,16 +41,6 @@ def pytest_runtest_call(item):
         outcome.force_exception(pytest.skip.Exception("device path: " + str(exc[1])[:80]))
 ''' % (ROOT, os.path.join(ROOT, "tests"))
 
-REAL_CASES = '''cases = [
-    {"A": test_utils.get_matrix_spd(), "normal": True, "self_adjoint": True, "positive_definite": True},
-    {"A": test_utils.get_matrix_symm_indef(), "normal": True, "self_adjoint": True},
-    {"A": test_utils.get_matrix_nonsymm()},
-]
-
-
-'''
-
-
 def main():
     if not os.path.isdir(REF):
         raise SystemExit("reference tests not present at " + REF)
@@ -60,11 +50,7 @@ def main():
         if f.endswith(".py"):
             shutil.copy(os.path.join(REF, f), SCRATCH)
     open(os.path.join(SCRATCH, "conftest.py"), "w").write(CONFTEST)
-    # scratch copies only: drop the complex right-hand side / matrix classes, and the Arnoldifyer part
-    p = os.path.join(SCRATCH, "test_linsys.py")
-    s = open(p).read().replace("        (1 + 1j) * numpy.ones((10, 1)),\n", "")
-    a, b = s.index("cases = ["), s.index("def generate_cases():")
-    open(p, "w").write(s[:a] + REAL_CASES + s[b:])
+    # scratch copies only: drop the Arnoldifyer part (not implemented)
     p = os.path.join(SCRATCH, "test_deflation.py")
     s = open(p).read()
     open(p, "w").write(s[: s.index("def generate_Arnoldifyer_cases():")])
