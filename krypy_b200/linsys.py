@@ -705,7 +705,7 @@ class Gmres(_KrylovSolver):
         y[0:1].fill_(float(self.MMlr0_norm))                               # linsys.py:969
         # CUDA graphs: from the second cycle over the same workspace on, step k is one graph launch
         use_graphs = (ws is not None and type(self) is Gmres and ws.graphs_enabled(ctx)
-                      and self.ortho != "lanczos")
+                      and self.ortho not in ("lanczos", "house"))
         ws_warm = ws is not None and ws.uses >= 1      # buffers and lazy kernel set-up exist already
         if ws is not None:
             ws.uses += 1

@@ -1006,13 +1006,53 @@ class Givens:
         return numpy.dot(self.G, x)
 
 
+def _house_params(gamma, sigma, n):
+    """Scalars of the Householder reflector of a vector with first entry ``gamma`` and
+    ``sigma = ||x[1:]||`` (krypy/utils.py:349-377; Golub/Van Loan Alg. 5.1.1 + section 5.1.13):
+    returns (v0, vscale, xnorm, alpha, beta) with ``v = [v0, x[1:]] / vscale``."""
+    if n == 1 or sigma == 0:
+        xnorm = numpy.abs(gamma)
+        alpha = 1 if gamma == 0 else gamma / xnorm
+        return 1.0, 1.0, xnorm, alpha, 0
+    xnorm = numpy.sqrt(numpy.abs(gamma) ** 2 + sigma ** 2)
+    if gamma == 0:
+        v0, alpha = -sigma, 1
+    else:
+        v0 = gamma + gamma / numpy.abs(gamma) * xnorm
+        alpha = -gamma / numpy.abs(gamma)
+    return v0, numpy.sqrt(numpy.abs(v0) ** 2 + sigma ** 2), xnorm, alpha, 2
+
+
 class House:
-    """krypy/utils.py:332-402 is not on any BASELINE path."""
+    """krypy/utils.py:332-402: Householder reflector ``H = I - beta v v^*`` with
+    ``H x = alpha ||x|| e_1``.  A helper for small host vectors (numpy ``(n,1)``), like ``Givens``;
+    inside ``Arnoldi(ortho='house')`` the reflectors live in HBM and are applied by the block
+    kernels (``Arnoldi._house_*``)."""
 
     def __init__(self, x):
-        raise NotImplementedError(
-            "Householder orthogonalisation is not implemented on the device path "
-            "(use ortho='mgs', 'dmgs', 'cgs', 'cgs2' or 'lanczos')")
+        if len(x.shape) != 2 or x.shape[1] != 1:
+            raise ArgumentError("x is not a vector of dim (N,1)")
+        x = numpy.asarray(x)
+        n = x.shape[0]
+        gamma = x[0].item()
+        sigma = numpy.linalg.norm(x[1:], 2) if n > 1 else 0
+        v0, vscale, self.xnorm, self.alpha, self.beta = _house_params(gamma, sigma, n)
+        v = numpy.array(x, dtype=numpy.result_type(x.dtype, type(v0), numpy.float64))
+        v[0] = v0
+        self.v = v / vscale
+
+    def apply(self, x):
+        """krypy/utils.py:379-389."""
+        if len(x.shape) != 2:
+            raise ArgumentError("x is not a matrix of shape (N,*)")
+        if self.beta == 0:
+            return x
+        return x - self.beta * self.v * numpy.dot(self.v.T.conj(), x)
+
+    def matrix(self):
+        """krypy/utils.py:391-402 (dense; for tests)."""
+        n = self.v.shape[0]
+        return numpy.eye(n, n) - self.beta * numpy.dot(self.v, self.v.T.conj())
 
 
 # --------------------------------------------------------------------------
@@ -1455,12 +1495,13 @@ class Arnoldi(object):
         if ortho == "house":
             if self.M is not None or not _is_identity_ip(ip_B):
                 raise ArgumentError("Only euclidean inner product allowed with Householder orthogonalization")
-            raise NotImplementedError("ortho='house' is not implemented on the device path")
-        if ortho not in _ORTHO:
+            if ctx.comm is not None:
+                raise NotImplementedError("ortho='house' is not implemented for row-partitioned runs")
+        elif ortho not in _ORTHO:
             raise ArgumentError(
                 "Invalid value '%s' for argument 'ortho'. Valid are house, mgs, dmgs, lanczos "
                 "(and cgs, cgs2 on the device path)." % ortho)
-        self._algo, self._passes = _ORTHO[ortho]
+        self._algo, self._passes = _ORTHO.get(ortho, (None, 0))
         td = self._td = _compute_dtype(self.dtype)
         self._cplx = cplx = td == t.complex128
         self._nr = nr = 2 if cplx else 1          # real rows per basis vector / doubles per coefficient
@@ -1527,6 +1568,13 @@ class Arnoldi(object):
         vd = v if v_dev_in else ctx.to_block(numpy.asarray(v), td)
         if vd.dtype != td:
             vd = vd.to(td)
+        if ortho == "house":
+            # utils.py:910-922: reflectors zero-padded to full length in HBM (twin storage if complex)
+            self._Wtw = _Twin(ctx, m1 + 1, N) if cplx else None
+            self._Wt = self._Wtw.T if cplx else ctx.alloc_basis(m1 + 1, N, td)[:, :N]
+            self._houses = []
+            self._house_make(0, vd)
+            Mv_norm = self._houses[0][2]                       # numpy.linalg.norm(v, 2)
         if self.M is not None:
             pd = vd
             if Mv is None:
@@ -1577,6 +1625,8 @@ class Arnoldi(object):
         q = self._q
         self.A._apply_dev(V[k:k + 1], out=q)                       # utils.py:968
         q0 = q[0]
+        if self.ortho == "house":
+            return self._enqueue_house(k)
         lanczos = self.ortho == "lanczos"
         Vsub = Pt if Pt is not None else Vt
         if lanczos:
@@ -1637,6 +1687,73 @@ class Arnoldi(object):
                 ctx.scale_dev(nrm, 1, 1.0, q0, V[k + 1])
         if cplx:
             self._Vtw.refresh(ctx, k + 1)
+
+    # -- Householder orthogonalisation (utils.py:970-994) ------------------------------------
+    def _house_make(self, j, xd):
+        """Reflector j from the device vector xd (1, N), acting on entries j..N-1 (utils.py:332-377):
+        stored zero-padded in row j of the reflector block; (alpha, beta, xnorm) kept on the host.
+        One host synchronisation (gamma and sigma are needed for the branch decisions)."""
+        ctx, t = self._ctx, _device.torch()
+        N, nr = self.N, self._nr
+        w = self._Wtw.C[j] if self._cplx else self._Wt[j]
+        w.copy_(xd[0])
+        if j > 0:
+            w[:j].zero_()
+        gam = t.empty(1, dtype=w.dtype)
+        gam.copy_(w[j:j + 1])                                      # D2H of one entry (synchronises)
+        gamma = gam[0].item()
+        sigma = 0.0
+        if j + 1 < N:
+            w[j:j + 1].zero_()
+            ctx.block_dot(w.reshape(1, -1), 1, w, self._tmp, 1, None)      # ||x[j+1:]||
+            sigma = float(self._tmp[0].item())
+        v0, vscale, xnorm, alpha, beta = _house_params(gamma, sigma, N - j)
+        w[j:j + 1].copy_(t.full((1,), v0, dtype=w.dtype))          # H2D of one entry
+        self._tmp[3:4].fill_(float(vscale))
+        ctx.scale_dev(self._tmp[3:], 1, 1.0, w, w)
+        if self._cplx:
+            self._Wtw.refresh(ctx, j)
+        self._houses.append((alpha, beta, xnorm))
+
+    def _house_apply(self, j, x):
+        """x <- (I - beta_j w_j w_j^*) x on a full-length device vector (utils.py:379-389)"""
+        beta = self._houses[j][1]
+        if beta == 0:
+            return
+        ctx, nr = self._ctx, self._nr
+        W = self._Wt[nr * j:]
+        ctx.block_dot(W, nr, x, self._tmp, 0, None)               # <w_j, x> (complex: re, im over the twin rows)
+        ctx.block_axpy(W, nr, self._tmp, -float(beta), x)
+
+    def _enqueue_house(self, k):
+        """Householder step k (utils.py:970-994); leaves column k of H in the device accumulator
+        like the Gram-Schmidt kernels do and stores V[k+1]."""
+        ctx, t = self._ctx, _device.torch()
+        N, nr, cplx = self.N, self._nr, self._cplx
+        q = self._q
+        for j in range(k + 1):
+            self._house_apply(j, q[0])
+        ncoef = min(k + 2, N)
+        col = numpy.zeros(k + 2, dtype=numpy.complex128 if cplx else numpy.float64)
+        if k + 1 < N:
+            self._house_make(k + 1, q)
+            col[k + 1] = self._houses[k + 1][2]                    # |alpha^* (H_{k+1} q)[k+1]| = ||q[k+1:]||
+        head = q[0][:min(k + 1, N)].cpu().numpy().astype(col.dtype)
+        for j in range(head.shape[0]):
+            col[j] = head[j] * numpy.conj(self._houses[j][0])      # Av[j] *= conj(alpha_j)
+        self._hcol[: nr * (k + 2)].copy_(_coefs_dev(ctx, col))
+        if k + 1 < N:
+            # v_{k+1} = alpha_{k+1} H_0 ... H_{k+1} e_{k+1}
+            v = self._t_house = getattr(self, "_t_house", None)
+            if v is None:
+                v = self._t_house = ctx.empty((1, N), self._td)
+            v.zero_()
+            v[0][k + 1:k + 2].copy_(t.ones(1, dtype=v.dtype))
+            for j in range(k + 1, -1, -1):
+                self._house_apply(j, v[0])
+            _caxpby(ctx, self._houses[k + 1][0], v[0], 0.0, None, self._Vd[k + 1])
+            if cplx:
+                self._Vtw.refresh(ctx, k + 1)
 
     def _finish(self, k, hcol_host):
         """Host bookkeeping of step k given H[0..k+1, k] (utils.py:1025, 1032-1039, 1048)."""

@@ -104,8 +104,11 @@ def test_host_logic_known_answers_and_semantics(fake):
     zs = kp.linsys.Gmres(kp.linsys.LinearSystem(A.astype(complex), (1 + 1j) * b), tol=1e-8)   # complex: real embedding
     assert zs.xk.dtype == np.complex128 and zs.resnorms[-1] <= 1e-8
     assert np.allclose(zs.xk.reshape(-1), (1 + 1j) * np.linalg.solve(A, b).reshape(-1), rtol=1e-6)
-    with pytest.raises(NotImplementedError):
-        kp.linsys.Gmres(ls, ortho="house")
+    hs = kp.linsys.Gmres(ls, ortho="house", maxiter=60)                 # Householder Arnoldi (utils.py:970-994)
+    ms = kp.linsys.Gmres(ls, maxiter=60)
+    assert len(hs.resnorms) == len(ms.resnorms) and np.allclose(hs.resnorms, ms.resnorms, rtol=1e-6)
+    with pytest.raises(kp.utils.ArgumentError):
+        kp.linsys.Gmres(kp.linsys.LinearSystem(A, b, ip_B=np.eye(100) * 2.0), ortho="house")
     with pytest.raises(kp.utils.ArgumentError):
         kp.linsys.Gmres(ls, ortho="nope")
 

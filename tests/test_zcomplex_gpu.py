@@ -247,3 +247,33 @@ def test_complex_convenience_wrappers(ctx):
             x, sol = fn(A, b, tol=1e-9, maxiter=200)
             assert x is not None and x.shape == b.shape and x.dtype == np.complex128
             assert np.linalg.norm(A @ x - b) <= 1e-8 * np.linalg.norm(b)
+
+
+# ------------------------------------------------------------------ Householder Arnoldi (ortho='house')
+@pytest.mark.parametrize("cplx", [False, True])
+def test_householder_arnoldi(ctx, cplx):
+    """krypy/utils.py:970-994 on the device (reflectors in HBM, applied with kry_block_dot/axpy):
+    Arnoldi relation, orthonormality to machine precision, and the same H as modified Gram-Schmidt"""
+    from krypy_b200 import utils
+    rng = np.random.default_rng(11)
+    N = 120
+    A = rng.standard_normal((N, N)) + 6 * np.eye(N)
+    v = rng.standard_normal((N, 1))
+    if cplx:
+        A = A + 1j * rng.standard_normal((N, N))
+        v = v + 1j * rng.standard_normal((N, 1))
+    V, H = utils.arnoldi(A, v, maxiter=15, ortho="house")
+    Vm, Hm = utils.arnoldi(A, v, maxiter=15, ortho="dmgs")
+    assert V.shape == (N, 16) and H.shape == (16, 15)
+    assert np.linalg.norm(A @ V[:, :-1] - V @ H) <= 1e-12 * np.linalg.norm(H)
+    assert np.linalg.norm(V.conj().T @ V - np.eye(16)) <= 1e-13
+    np.testing.assert_allclose(H, Hm, rtol=0, atol=1e-10 * np.abs(Hm).max())
+    np.testing.assert_allclose(V, Vm, rtol=0, atol=1e-10)
+    # small host helper, utils.py:332-402
+    x = v[:7]
+    h = utils.House(x)
+    y = h.apply(x)
+    assert abs(y[0, 0] - h.alpha * np.linalg.norm(x)) <= 1e-13 and np.abs(y[1:]).max() <= 1e-13
+    # full-dimensional run ends with an invariant subspace (k+1 == N branch)
+    Vf, Hf = utils.arnoldi(A[:9, :9], v[:9], ortho="house")
+    assert Vf.shape == (9, 9) and Hf.shape == (9, 9)

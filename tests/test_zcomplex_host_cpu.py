@@ -52,3 +52,8 @@ def test_complex_convenience(fake):
 @pytest.mark.parametrize("name", z.cases.COMPLEX_CASES)
 def test_complex_cases(fake, name):
     z.test_complex_cases_match_reference_fixture_and_oracle(name)
+
+
+@pytest.mark.parametrize("cplx", [False, True])
+def test_householder_arnoldi(fake, cplx):
+    z.test_householder_arnoldi(fake, cplx)

@@ -2,11 +2,11 @@
 run the REFERENCE's own test files against krypy_b200's host layer, with the package aliased as
 ``krypy`` and the device layer replaced by the numpy test double (tests/fake_device.py).
 
-Only the real-valued cases can run (the device path is real); complex cases are filtered out of the
-scratch copies / reported as skipped.  Result recorded in DESIGN.md section 8:
-  test_convenience_wrappers.py 7 passed | test_recycling.py 21 passed |
-  test_linsys.py (real subset) 5167 passed | test_deflation.py::test_deflation_solver 492 passed |
-  test_utils.py -k "arnoldi or givens or projection or qr" 1529 passed, 68 skipped (house, complex)
+Real and complex cases run (complex: real embedding + twin storage).  Result recorded in DESIGN.md
+section 8:
+  test_convenience_wrappers.py + test_recycling.py 28 passed | test_linsys.py 13385 passed |
+  test_deflation.py::test_deflation_solver 7728 passed |
+  test_utils.py -k "arnoldi or givens or projection or qr or house" 1669 passed
 usage: python tools/reference_suite_on_host_layer.py
 """
 import os
@@ -55,7 +55,7 @@ def main():
     s = open(p).read()
     open(p, "w").write(s[: s.index("def generate_Arnoldifyer_cases():")])
     runs = [["test_convenience_wrappers.py", "test_recycling.py"], ["test_linsys.py"], ["test_deflation.py"],
-            ["test_utils.py", "-k", "arnoldi or givens or projection or qr"]]
+            ["test_utils.py", "-k", "arnoldi or givens or projection or qr or house"]]
     rc = 0
     for r in runs:
         print("==", " ".join(r))
