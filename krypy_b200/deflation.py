@@ -13,7 +13,7 @@ from . import _cplx, _device, linsys, utils
 from .utils import _ctx, _is_dev
 
 __all__ = ["DeflatedCg", "DeflatedMinres", "DeflatedGmres", "_DeflationMixin",
-           "ObliqueProjection", "_Projection", "Ritz"]
+           "ObliqueProjection", "_Projection", "Ritz", "Arnoldifyer", "bound_pseudo"]
 
 
 class _Projection(utils.Projection):
@@ -294,7 +294,7 @@ class Ritz(object):
 
     def __init__(self, deflated_solver, mode="ritz"):
         import scipy.linalg
-        self._solver = sv = deflated_solver
+        self._solver = self._deflated_solver = sv = deflated_solver
         ls = sv.linear_system
         self.values = None
         self.coeffs = None
@@ -432,3 +432,6 @@ class Ritz(object):
             rj = res[j:j + 1]
             out[j] = linsys._norm_dev(rj, ls.M._apply_dev(rj), ls.ip_B)
         return out
+
+
+from ._arnoldifyer import Arnoldifyer, bound_pseudo  # noqa: E402,F401  (krypy/deflation.py:286-734)

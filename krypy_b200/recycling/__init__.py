@@ -1,10 +1,8 @@
-"""Recycling Krylov solvers (krypy/recycling/*; SURVEY 8f rank 1): strategy objects on host
+"""Recycling Krylov solvers (krypy/recycling/*; SURVEY 8f ranks 1 and 4): strategy objects on host
 scalars that pick deflation vectors from the last solve and run the deflated device solvers.
-
-Implemented: ``Recycling{Cg,Minres,Gmres}`` and the factories that need only Ritz pairs
-(``RitzFactorySimple``, ``UnionFactory``).  The evaluator-driven ``RitzFactory`` family depends on
-``Arnoldifyer`` / ``bound_pseudo`` (out of scope) and raises."""
-from . import factories
+``Recycling{Cg,Minres,Gmres}``, the factories (``RitzFactorySimple``, ``UnionFactory``, the
+evaluator-driven ``RitzFactory``), subset ``generators`` and ``evaluators``."""
+from . import evaluators, factories, generators
 from .linsys import RecyclingCg, RecyclingGmres, RecyclingMinres
 
-__all__ = ["RecyclingCg", "RecyclingMinres", "RecyclingGmres", "factories"]
+__all__ = ["RecyclingCg", "RecyclingMinres", "RecyclingGmres", "factories", "evaluators", "generators"]

@@ -12,10 +12,67 @@ class _DeflationVectorFactory(object):
 
 
 class RitzFactory(_DeflationVectorFactory):
-    def __init__(self, *args, **kwargs):
-        raise NotImplementedError(
-            "RitzFactory needs the subset evaluators built on Arnoldifyer / bound_pseudo, which are "
-            "outside the hot-path scope (SURVEY section 2); use RitzFactorySimple")
+    """Greedy selection of Ritz vectors: starting from the empty set, a generator proposes index sets
+    to add, an evaluator rates every enlarged set (estimated time of the next solve), the best one is
+    kept; the overall best rated set wins (krypy/recycling/factories.py:20-139)."""
+
+    def __init__(self, subset_evaluator, subsets_generator=None, mode="ritz", print_results=None):
+        from . import generators
+        self.subsets_generator = generators.RitzSmall() if subsets_generator is None else subsets_generator
+        self.subset_evaluator = subset_evaluator
+        self.mode = mode
+        self.print_results = print_results
+
+    def get(self, deflated_solver):
+        ritz = deflation.Ritz(deflated_solver, mode=self.mode)
+        return ritz.get_vectors_dev(self._get_best_subset(ritz), realify=True)
+
+    def _rate(self, ritz, subset, table):
+        try:
+            table[subset] = self.subset_evaluator.evaluate(ritz, subset)
+        except utils.AssumptionError:
+            pass                               # this set cannot be rated: skip it
+
+    def _get_best_subset(self, ritz):
+        rated = {}
+        current = frozenset()
+        self._rate(ritz, current, rated)
+        everything = set(range(len(ritz.values)))
+        while True:
+            proposals = self.subsets_generator.generate(ritz, everything.difference(current))
+            if len(proposals) == 0:
+                break
+            round_ = {}
+            for add in proposals:
+                self._rate(ritz, current.union(add), round_)
+            if round_:
+                current = min(round_, key=round_.get)
+            else:
+                # nothing could be rated: extend by the proposal with the smallest residual norms
+                sums = [numpy.sum(ritz.resnorms[list(add)]) for add in proposals]
+                current = current.union(proposals[int(numpy.argmin(sums))])
+            rated.update(round_)
+        selection = list(min(rated, key=rated.get)) if rated else []
+        self._report(ritz, selection, rated)
+        return selection
+
+    def _report(self, ritz, selection, rated):
+        how = self.print_results
+        if how is None:
+            return
+        if how == "number":
+            print("# of selected deflation vectors: %d" % len(selection))
+        elif how == "values":
+            print("%d Ritz values corresponding to selected deflation vectors: %s"
+                  % (len(selection), ", ".join(str(v) for v in ritz.values[selection])))
+        elif how == "timings":
+            print("Timings for all successfully evaluated choices of deflation vectors with "
+                  "corresponding Ritz values:")
+            for subset, time in sorted(rated.items(), key=lambda kv: kv[1]):
+                print(" %ss: %s" % (time, ", ".join(str(v) for v in ritz.values[list(subset)])))
+        else:
+            raise utils.ArgumentError("Invalid value `%s` for argument `print_result`. Valid are `None`, "
+                                      "`number`, `values` and `timings`." % how)
 
 
 class RitzFactorySimple(_DeflationVectorFactory):

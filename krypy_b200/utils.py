@@ -34,6 +34,10 @@ __all__ = [
     "Timer", "Timings", "arnoldi", "arnoldi_res", "get_linearoperator", "inner", "ip_euclid",
     "norm", "norm_squared", "orthonormality", "qr", "shape_vec", "shape_vecs",
     "find_common_dtype", "DeviceBlock", "SolverWorkspace",
+    # host-side analysis helpers (krypy_b200/_analysis.py)
+    "BoundCG", "BoundMinres", "NormalizedRootsPolynomial", "Interval", "Intervals", "angles",
+    "arnoldi_projected", "bound_perturbed_gmres", "gap", "hegedus", "norm_MMlr", "ritz", "strakos",
+    "get_residual_norms",
 ]
 
 
@@ -1857,3 +1861,9 @@ def arnoldi(*args, **kwargs):
     while _arnoldi.iter < _arnoldi.maxiter and not _arnoldi.invariant:
         _arnoldi.advance()
     return _arnoldi.get()
+
+
+# host-side analysis helpers under the reference's names
+from ._analysis import (BoundCG, BoundMinres, Interval, Intervals, NormalizedRootsPolynomial,  # noqa: E402,F401
+                        angles, arnoldi_projected, bound_perturbed_gmres, gap, get_residual_norms,
+                        hegedus, norm_MMlr, ritz, strakos)
