@@ -1,0 +1,24 @@
+#!/bin/bash
+# One GPU-box session (gpurun -- 'bash tools/gpu_session.sh'): the GPU test tier, the default bench
+# line, the ncu launch list of the same command and the full-size configurations, with everything
+# worth keeping written under gpurun_out/ (copied to profiles/ by hand afterwards).
+# First thing to run in a round: it covers the tests that were written without GPU time
+# (tests/test_zcomplex_gpu.py, tests/test_zz_analysis_gpu.py).
+set -u
+mkdir -p gpurun_out
+python -c "import __graft_entry__ as g; g.build()" > gpurun_out/build.log 2>&1
+timeout 1500 python -m pytest tests -m gpu -q -x -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
+tail -5 gpurun_out/pytest_gpu.log
+# the files that sort last, again without -x, so one failure does not hide the rest
+timeout 900 python -m pytest tests/test_zcomplex_gpu.py tests/test_zz_analysis_gpu.py -m gpu -q -p no:cacheprovider \
+    > gpurun_out/pytest_new.log 2>&1
+tail -15 gpurun_out/pytest_new.log
+timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+timeout 900 python bench.py > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log
+timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 220 --csv \
+    --log-file gpurun_out/launch_list.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e \
+    > gpurun_out/ncu_bench.log 2>&1
+timeout 1200 python tools/run_configs.py c2 c3 c4 c5 > gpurun_out/configs_fullsize.json 2> gpurun_out/configs.err
+tail -3 gpurun_out/configs.err
