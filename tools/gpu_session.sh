@@ -20,5 +20,5 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 220 --csv \
     --log-file gpurun_out/launch_list.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e \
     > gpurun_out/ncu_bench.log 2>&1
-timeout 1200 python tools/run_configs.py c2 c3 c4 c5 > gpurun_out/configs_fullsize.json 2> gpurun_out/configs.err
+timeout 1200 python tools/run_configs.py c2 c3 c4 c4r c5 > gpurun_out/configs_fullsize.json 2> gpurun_out/configs.err
 tail -3 gpurun_out/configs.err

@@ -1,6 +1,6 @@
 """Run BASELINE.json's configurations C2..C5 at FULL size on one B200 through the public API and
 report iterations/s, algorithmic GB/s (SURVEY 8d byte model) and size-independent parity
-properties.  usage: python tools/run_configs.py [c2 c3 c4 c5] > profiles/r1_configs.json"""
+properties.  usage: python tools/run_configs.py [c2 c3 c4 c4r c5] > profiles/r1_configs.json"""
 import json, os, sys, time, warnings
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
@@ -90,6 +90,28 @@ if "c4" in which:
     s0, dt0 = timed(lambda: kp.linsys.Gmres(ls, maxiter=60, tol=1e-10, ortho="cgs"))
     out["c4"]["undeflated_final_resnorm"] = float(s0.resnorms[-1]); out["c4"]["undeflated_it_per_s"] = 60 / dt0
     del ls, s, s0, proj
+
+if "c4r" in which:
+    # SURVEY 8d's C4 workflow end to end on the device: solve 1 (no deflation, store_arnoldi) ->
+    # 20 Ritz vectors of smallest magnitude (RitzFactorySimple, realified, kept in HBM) -> timed solve 2
+    n = 2000; N = n * n; d = 20
+    A = problems.convdiff2d(n, c=0.1); b = np.ones((N, 1))
+    ls = kp.linsys.LinearSystem(A, b)
+    fac = kp.recycling.factories.RitzFactorySimple(n_vectors=d, which="sm")
+    rs = kp.recycling.RecyclingGmres()
+    s1, dt1 = timed(lambda: rs.solve(ls, vector_factory=fac, maxiter=60, tol=1e-10, ortho="cgs"))
+    torch.cuda.synchronize(); t0 = time.perf_counter()
+    Ublk = fac.get(rs.last_solver); torch.cuda.synchronize(); tfac = time.perf_counter() - t0
+    s2, dt2 = timed(lambda: kp.deflation.DeflatedGmres(ls, U=Ublk, maxiter=60, tol=1e-10, ortho="cgs",
+                                                       store_arnoldi=True))
+    out["c4r"] = {"config": "recycled DeflatedGmres: 20 Ritz vectors ('sm') of solve 1, conv-diff N=%d fp64" % N,
+                  "solve1_it_per_s": (len(s1.resnorms) - 1) / dt1, "ritz_vectors_s": tfac,
+                  "solve2_iterations": len(s2.resnorms) - 1, "solve2_seconds_total": dt2,
+                  "solve2_it_per_s": (len(s2.resnorms) - 1) / dt2,
+                  "solve1_final_resnorm": float(s1.resnorms[-1]), "solve2_final_resnorm": float(s2.resnorms[-1]),
+                  "solve2_explicit_check": float(np.linalg.norm(b.reshape(-1) - A @ s2.xk.reshape(-1)) / np.linalg.norm(b)),
+                  "U_shape": list(s2.projection.U.shape)}
+    del ls, s1, s2, rs, Ublk
 
 if "c5" in which:
     n = 4000; N = n * n
