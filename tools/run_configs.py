@@ -101,7 +101,7 @@ if "c4r" in which:
     rs = kp.recycling.RecyclingGmres()
     s1, dt1 = timed(lambda: rs.solve(ls, vector_factory=fac, maxiter=60, tol=1e-10, ortho="cgs"))
     torch.cuda.synchronize(); t0 = time.perf_counter()
-    Ublk = fac.get(rs.last_solver); torch.cuda.synchronize(); tfac = time.perf_counter() - t0
+    Ublk = fac.get(s1); torch.cuda.synchronize(); tfac = time.perf_counter() - t0   # (s1 may come from a ConvergenceError)
     s2, dt2 = timed(lambda: kp.deflation.DeflatedGmres(ls, U=Ublk, maxiter=60, tol=1e-10, ortho="cgs",
                                                        store_arnoldi=True))
     out["c4r"] = {"config": "recycled DeflatedGmres: 20 Ritz vectors ('sm') of solve 1, conv-diff N=%d fp64" % N,
