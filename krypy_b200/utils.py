@@ -170,8 +170,16 @@ class _Twin(object):
         store = ctx.alloc_basis(2 * max(self.k, 1), 2 * self.N, t.float64, None)
         self.store = store
         self.T = store[: 2 * self.k, : 2 * self.N]
-        self.C = store[0::2].view(t.complex128)[: self.k, : self.N]
-        self.C._kry_twin = self       # _twin_for(C) finds its own storage
+
+    @property
+    def C(self):
+        """complex (k, N) view of the even rows.  The view points back at its storage (so
+        ``_twin_for`` finds it and the storage lives as long as the view); the storage does not
+        reference the view, so there is no reference cycle holding HBM until a cyclic GC."""
+        t = _device.torch()
+        c = self.store[0::2].view(t.complex128)[: self.k, : self.N]
+        c._kry_twin = self
+        return c
 
     def refresh(self, ctx, j):
         """row 2j+1 <- i * row 2j (after vector j was written)"""
