@@ -379,6 +379,8 @@ class DistLinearSystem(linsys.LinearSystem):
         self.part = part
         self.N_global = part.N
         super(DistLinearSystem, self).__init__(op, b, **kwargs)
+        if np.dtype(self.dtype).kind == "c":
+            raise NotImplementedError("complex row-partitioned systems are not implemented (single GPU only)")
 
 
 class DistGmres(linsys.Gmres):
