@@ -108,6 +108,11 @@ class _DeflationMixin(object):
             U = numpy.asarray(U)
             if U.ndim == 1:
                 U = U.reshape(-1, 1)
+        udt = _device.torch_to_np_dtype(U.dtype) if _is_dev(U) else U.dtype
+        if numpy.dtype(udt).kind == "c" and numpy.dtype(linear_system.dtype).kind != "c":
+            # complex deflation vectors (e.g. Ritz vectors of a real nonsymmetric problem):
+            # the projector and the whole solve are complex, deflation.py:123-125
+            linear_system = linear_system._as_dtype(numpy.complex128)
         projection = ObliqueProjection(linear_system, U, **projection_kwargs)
         self.projection = projection
         d = projection._k
@@ -295,6 +300,7 @@ class Ritz(object):
     def __init__(self, deflated_solver, mode="ritz"):
         import scipy.linalg
         self._solver = self._deflated_solver = sv = deflated_solver
+        self._cplx_bases = None
         ls = sv.linear_system
         self.values = None
         self.coeffs = None
@@ -358,9 +364,7 @@ class Ritz(object):
             if numpy.abs(co.imag).max() <= 1e-14 * max(numpy.abs(co).max(), 1e-300):
                 return numpy.ascontiguousarray(co.real)
             if not realify:
-                raise NotImplementedError(
-                    "complex Ritz vectors are not supported by the (real) device path; pass realify=True to "
-                    "get a real basis of the same space (select conjugate pairs together; SURVEY F10)")
+                return None            # complex Ritz vectors of a real problem: the caller goes complex
             # [Re, Im] spans the same space as the selected vectors when conjugate pairs are selected
             # together; a pivoted QR of the coefficients keeps the k most independent combinations
             import scipy.linalg
@@ -380,20 +384,26 @@ class Ritz(object):
         m = pr._k
         Vd = sv._basis_dev()
         N = sv.linear_system.N
-        if sv._td == t.complex128:
-            # complex system: complex coefficients over the twin storage of V_n and U
+        co = None if sv._td == t.complex128 else self._real_coeffs(indices, realify)
+        if co is None:
+            # complex coefficients over the twin storage of V_n and U (complex system, or complex Ritz
+            # vectors of a real nonsymmetric problem, deflation.py:792-796 + SURVEY F10)
             co = self.coeffs if indices is None else self.coeffs[:, indices]
             co = co.reshape(-1, 1) if co.ndim == 1 else co
             k = co.shape[1]
-            out = ctx.empty((k, N), sv._td)
-            tmp = ctx.empty((1, N), sv._td)
+            Ud = pr._Ud
+            if sv._td != t.complex128:
+                if self._cplx_bases is None:
+                    self._cplx_bases = (Vd[:n].to(t.complex128), Ud.to(t.complex128))
+                Vd, Ud = self._cplx_bases
+            out = ctx.empty((k, N), t.complex128)
+            tmp = ctx.empty((1, N), t.complex128)
             for j in range(k):
                 utils._combine(ctx, Vd, n, co[:n, j], None, out[j])
                 if m:
-                    utils._combine(ctx, pr._Ud, m, co[n:, j], out[j], tmp[0])
+                    utils._combine(ctx, Ud, m, co[n:, j], out[j], tmp[0])
                     out[j].copy_(tmp[0])
             return utils.DeviceBlock(out)
-        co = self._real_coeffs(indices, realify)
         k = co.shape[1]
         out = ctx.empty((k, N), sv._td)
         cd = t.from_numpy(numpy.ascontiguousarray(co.T, dtype=numpy.float64)).to(ctx.device)   # (k, n+m)
@@ -406,7 +416,8 @@ class Ritz(object):
     def get_vectors(self, indices=None, realify=False):
         """krypy/deflation.py:840-847."""
         blk = self.get_vectors_dev(indices, realify)
-        return _ctx().to_numpy(blk.block).astype(self._solver.dtype, copy=False)
+        out = _ctx().to_numpy(blk.block)
+        return out if numpy.iscomplexobj(out) else out.astype(self._solver.dtype, copy=False)
 
     def get_explicit_residual(self, indices=None):
         """krypy/deflation.py:849-855 (real Ritz pairs)."""
@@ -416,9 +427,7 @@ class Ritz(object):
         vals = numpy.atleast_1d(vals)
         res = self._solver.linear_system.MlAMr._apply_dev(blk)
         if numpy.iscomplexobj(vals) and not utils._is_cplx(blk):
-            if numpy.abs(vals.imag).max() > 0:
-                raise NotImplementedError("complex Ritz values of a real system (use realify / a complex system)")
-            vals = vals.real
+            vals = vals.real          # real vectors come with (numerically) real values
         for j in range(blk.shape[0]):
             utils._caxpby(ctx, -vals[j], blk[j], 1.0, res[j], res[j])
         return res

@@ -134,6 +134,31 @@ class LinearSystem(object):
     Mlb = _LazyVec("Mlb")
     MMlb = _LazyVec("MMlb")
 
+    def _as_dtype(self, npdtype):
+        """This system for a solver whose dtype is wider than the system's (complex ``x0`` or complex
+        deflation vectors with real ``A, b``: the whole solve becomes complex, linsys.py:370-372,
+        deflation.py:123-125; or a float64 ``x0`` with an fp32-storage system).  Returns ``self`` when
+        the device dtype is unchanged, else a cached shallow copy that shares the operators (their
+        device data is cached per block dtype) and holds promoted copies of the right-hand side."""
+        td = utils._compute_dtype(npdtype)
+        if td == self._td:
+            return self
+        views = self.__dict__.setdefault("_dtype_views", {})
+        view = views.get(td)
+        if view is None:
+            if getattr(self, "part", None) is not None:
+                raise NotImplementedError("dtype promotion of a row-partitioned system")
+            view = object.__new__(type(self))
+            view.__dict__.update(self.__dict__)
+            view.__dict__.pop("_dtype_views", None)
+            view.dtype = numpy.dtype(_device.torch_to_np_dtype(td))
+            view._td = td
+            for name in ("_b_dev", "_exact_dev", "_Mlb_dev", "_MMlb_dev"):
+                blk = self.__dict__.get(name)
+                view.__dict__[name] = None if blk is None else blk.to(td)
+            views[td] = view
+        return view
+
     # -- device residual -------------------------------------------------------
     def _get_residual_dev(self, zd, compute_norm=False):
         """(M Ml (b - A z), Ml (b - A z)[, norm]) on device blocks (linsys.py:130-161)."""
@@ -269,8 +294,9 @@ class _KrylovSolver(object):
         self.dtype = utils._common_type([ls.dtype, x0dt, dtype])
         self._td = utils._compute_dtype(self.dtype)
         if self._td != ls._td:
-            raise NotImplementedError(
-                "solver dtype %s differs from the linear system's device dtype %s" % (self.dtype, ls.dtype))
+            # e.g. complex x0 with real A, b: the whole solve becomes complex
+            self.linear_system = ls = ls._as_dtype(self.dtype)
+            self._td = ls._td
 
         if x0 is None:
             self.flat_vecs = True

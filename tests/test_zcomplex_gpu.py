@@ -277,3 +277,45 @@ def test_householder_arnoldi(ctx, cplx):
     # full-dimensional run ends with an invariant subspace (k+1 == N branch)
     Vf, Hf = utils.arnoldi(A[:9, :9], v[:9], ortho="house")
     assert Vf.shape == (9, 9) and Hf.shape == (9, 9)
+
+
+# ------------------------------------------------------------------ real system, complex x0 / complex U
+def test_real_system_becomes_complex_for_complex_x0_and_deflation_vectors(ctx):
+    """SURVEY 3.6 / F10 (krypy/linsys.py:370-372, deflation.py:123-125): a complex x0 or complex
+    deflation vectors make the whole solve complex; the result must equal the solve of the explicitly
+    complexified system"""
+    import krypy_b200 as kp
+    from krypy_b200 import problems
+    rng = np.random.default_rng(12)
+    n = 12
+    N = n * n
+    A = problems.convdiff2d(n, c=0.4)
+    b = rng.standard_normal((N, 1))
+    x0 = crandn(rng, N, 1)
+    U = crandn(rng, N, 3)
+
+    def run(cls, ls, **kw):
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            try:
+                return cls(ls, **kw)
+            except kp.utils.ConvergenceError as e:
+                return e.solver
+
+    Ac, bc = sp.csr_matrix(A.astype(np.complex128)), b.astype(np.complex128)
+    for cls, kw in ((kp.linsys.Gmres, dict(x0=x0)), (kp.deflation.DeflatedGmres, dict(U=U)),
+                    (kp.deflation.DeflatedGmres, dict(U=U, x0=x0))):
+        ls = kp.linsys.LinearSystem(A, b)
+        assert ls.dtype == np.float64
+        got = run(cls, ls, tol=1e-9, maxiter=40, **kw)
+        ref = run(cls, kp.linsys.LinearSystem(Ac, bc), tol=1e-9, maxiter=40, **kw)
+        assert got.dtype == np.complex128 and got.xk.dtype == np.complex128
+        assert ls.dtype == np.float64                       # the user's system object is left as it was
+        _check_history(np.array(got.resnorms), np.array(ref.resnorms))
+        np.testing.assert_allclose(got.xk, ref.xk, rtol=1e-9, atol=1e-12)
+    # float64 x0 with an fp32-storage system promotes the solve to fp64
+    L = problems.laplace2d(n)
+    ls32 = kp.linsys.LinearSystem(L.astype(np.float32), b.astype(np.float32), dtype=np.float32,
+                                  self_adjoint=True, positive_definite=True)
+    s = run(kp.linsys.Cg, ls32, x0=np.zeros((N, 1)), tol=1e-8)
+    assert s.dtype == np.float64 and s.resnorms[-1] <= 1e-8

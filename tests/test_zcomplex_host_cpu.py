@@ -57,3 +57,7 @@ def test_complex_cases(fake, name):
 @pytest.mark.parametrize("cplx", [False, True])
 def test_householder_arnoldi(fake, cplx):
     z.test_householder_arnoldi(fake, cplx)
+
+
+def test_real_system_promotion(fake):
+    z.test_real_system_becomes_complex_for_complex_x0_and_deflation_vectors(fake)
