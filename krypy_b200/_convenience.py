@@ -25,7 +25,9 @@ def _prepare(A, b, inner_product, U, x0):
     if inner_product:
         # numpy.dot / numpy.vdot on real vectors ARE the Euclidean inner product: keep the
         # fused device path instead of calling back into host code once per reduction
-        if inner_product is numpy.dot or inner_product is numpy.vdot:
+        # (numpy.dot does not conjugate: for complex data it is not the Euclidean inner product)
+        is_cplx = any(numpy.dtype(getattr(z, "dtype", float)).kind == "c" for z in (A, b, U, x0) if z is not None)
+        if inner_product is numpy.vdot or (inner_product is numpy.dot and not is_cplx):
             inner_product = None
         else:
             inner_product = wrap_inner_product(inner_product)
