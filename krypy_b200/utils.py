@@ -30,7 +30,7 @@ __all__ = [
     "ArgumentError", "AssumptionError", "ConvergenceError", "LinearOperatorError",
     "InnerProductError", "RuntimeError", "Arnoldi", "Givens", "House",
     "IdentityLinearOperator", "ZeroLinearOperator", "LinearOperator",
-    "MatrixLinearOperator", "DiagonalLinearOperator", "TimedLinearOperator", "Projection",
+    "MatrixLinearOperator", "DiagonalLinearOperator", "DeviceLinearOperator", "TimedLinearOperator", "Projection",
     "Timer", "Timings", "arnoldi", "arnoldi_res", "get_linearoperator", "inner", "ip_euclid",
     "norm", "norm_squared", "orthonormality", "qr", "shape_vec", "shape_vecs",
     "find_common_dtype", "DeviceBlock", "SolverWorkspace",
@@ -674,6 +674,38 @@ class _FunctionDeviceOperator(_DeviceOperator):
         elif out.data_ptr() != Xd.data_ptr():
             out.copy_(Xd)
         Y = self._fn(out)
+        if Y.data_ptr() != out.data_ptr():
+            out.copy_(Y)
+        return out
+
+
+class DeviceLinearOperator(_DeviceOperator):
+    """A user operator that runs on the device (new): ``dot_dev`` / ``dot_adj_dev``
+    receive a ``(k, N)`` torch CUDA tensor -- k vectors, one per row (vector-major), complex128 for
+    complex systems -- on the current stream and return a tensor of the same layout (or write into
+    and return the ``out`` tensor passed as second argument).  Unlike ``LinearOperator(dot=...)``
+    with a numpy callback nothing crosses PCIe.  The numpy-facing ``dot``/``*`` still work
+    (H2D -> callback -> D2H)."""
+
+    def __init__(self, shape, dtype, dot_dev=None, dot_adj_dev=None):
+        if dot_dev is None and dot_adj_dev is None:
+            raise LinearOperatorError("dot_dev or dot_adj_dev have to be defined")
+        self._dot_dev, self._dot_adj_dev = dot_dev, dot_adj_dev
+        super(DeviceLinearOperator, self).__init__(shape, dtype)
+
+    def _apply_dev(self, Xd, out=None, adj=False):
+        fn = self._dot_adj_dev if adj else self._dot_dev
+        if fn is None:
+            raise LinearOperatorError("dot_adj undefined" if adj else "dot undefined")
+        m = self.shape[1] if adj else self.shape[0]
+        if out is None:
+            out = _ctx().empty((Xd.shape[0], m), Xd.dtype)
+        Y = fn(Xd, out)
+        if Y is None:
+            Y = out
+        if tuple(Y.shape) != (Xd.shape[0], m):
+            raise LinearOperatorError("device callback returned shape %s, expected %s"
+                                      % (tuple(Y.shape), (Xd.shape[0], m)))
         if Y.data_ptr() != out.data_ptr():
             out.copy_(Y)
         return out

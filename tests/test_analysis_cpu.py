@@ -39,3 +39,7 @@ def test_evaluator_recycling(fake, solver, factory):
 
 def test_ritz_factory_options(fake):
     ac.check_ritz_factory_options()
+
+
+def test_device_linear_operator(fake):
+    ac.check_device_linear_operator()

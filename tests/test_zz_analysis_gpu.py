@@ -36,3 +36,7 @@ def test_evaluator_recycling(solver, factory):
 
 def test_ritz_factory_options():
     ac.check_ritz_factory_options()
+
+
+def test_device_linear_operator():
+    ac.check_device_linear_operator()
