@@ -71,7 +71,7 @@ def test_rot90_on_complex_tensors_and_twin_storage(ctx):
     out = ctx.scalars(2 * k)
     ctx.block_dot(tw.T, 2 * k, T(ctx, q), out)
     got = out.cpu().numpy().view(np.complex128)
-    np.testing.assert_allclose(got, Z.conj() @ q, rtol=1e-13)
+    np.testing.assert_allclose(got, Z.conj() @ q, rtol=1e-13, atol=1e-12)
 
 
 @pytest.mark.parametrize("real_valued", [False, True])
