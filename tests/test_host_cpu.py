@@ -146,3 +146,36 @@ def test_peer_addressing_contract_in_numpy(world):
             y = pl.local_matrix() @ np.nan_to_num(xe, nan=0.0)
             assert not np.isnan(xe[: p.nloc]).any() and not np.isnan(xe[p.block: p.block + pl.nhalo]).any()
             assert np.array_equal(y, (A @ X[k])[p.lo:p.hi])
+
+
+def test_every_entry_point_rejects_a_null_context_without_touching_the_device():
+    """C-ABI error convention (SURVEY 8b): int status (0 ok, negative error class) + kry_last_error();
+    a NULL context is refused by every entry point before any CUDA call -- safe to exercise without a GPU."""
+    import ctypes
+    from krypy_b200 import _lib
+    lib = _lib.load()
+    zero = {ctypes.c_int: 0, ctypes.c_longlong: 0, ctypes.c_double: 0.0}
+    called = 0
+    for name, (res, args) in sorted(_lib.PROTOTYPES.items()):
+        if res is not ctypes.c_int or not args or args[0] is not ctypes.c_void_p or name == "kry_ctx_destroy":
+            continue
+        rc = getattr(lib, name)(*[zero.get(a, None) for a in args])
+        msg = lib.kry_last_error()
+        assert rc < 0, (name, rc)
+        assert msg and (b"NULL" in msg or b"ctx" in msg or b"requirement failed" in msg), (name, msg)
+        called += 1
+    assert called >= 30
+    assert lib.kry_ctx_destroy(None) == 0 and lib.kry_launch_count(None) == -1
+    assert lib.kry_mailbox_host(None) is None and lib.kry_mailbox_dev(None) is None
+
+
+def test_context_creation_fails_loudly_without_a_device():
+    import ctypes
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from krypy_b200 import _lib
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    rc = lib.kry_ctx_create(0, None, ctypes.byref(h))
+    assert rc < 0 and not h.value and lib.kry_last_error()
