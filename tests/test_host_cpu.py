@@ -179,3 +179,20 @@ def test_context_creation_fails_loudly_without_a_device():
     h = ctypes.c_void_p()
     rc = lib.kry_ctx_create(0, None, ctypes.byref(h))
     assert rc < 0 and not h.value and lib.kry_last_error()
+
+
+def test_plain_c_consumer_of_the_abi_compiles_and_links():
+    """examples/gmres_c_abi.c: GMRES(m) driven from C through include/krypy_b200.h (no Python, no torch).
+    Compile + link only here; tools/gpu_session.sh runs it on the GPU box."""
+    import shutil
+    import tempfile
+    cuda = "/usr/local/cuda"
+    if shutil.which("gcc") is None or not os.path.exists(os.path.join(cuda, "include", "cuda_runtime.h")):
+        pytest.skip("gcc / CUDA runtime headers not available")
+    out = os.path.join(tempfile.mkdtemp(), "gmres_c_abi")
+    cmd = ["gcc", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(cuda, "include"),
+           os.path.join(ROOT, "examples", "gmres_c_abi.c"), "-o", out, "-L", os.path.join(ROOT, "krypy_b200"),
+           "-lkrypy_b200", "-L", os.path.join(cuda, "lib64"), "-lcudart", "-lm",
+           "-Wl,-rpath," + os.path.join(ROOT, "krypy_b200")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0 and os.path.exists(out), res.stderr[-2000:]

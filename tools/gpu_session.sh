@@ -15,6 +15,9 @@ timeout 900 python -m pytest tests/test_zcomplex_gpu.py tests/test_zz_analysis_g
     > gpurun_out/pytest_new.log 2>&1
 tail -15 gpurun_out/pytest_new.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
+gcc -O2 -I include -I /usr/local/cuda/include examples/gmres_c_abi.c -o gpurun_out/gmres_c_abi -L krypy_b200 -lkrypy_b200 \
+    -L/usr/local/cuda/lib64 -lcudart -lm -Wl,-rpath,$PWD/krypy_b200 && timeout 300 gpurun_out/gmres_c_abi 1024 30 5 \
+    > gpurun_out/c_abi_example.log 2>&1; tail -2 gpurun_out/c_abi_example.log
 timeout 900 python bench.py > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 220 --csv \
