@@ -10,6 +10,7 @@
 // map), so the only grid-wide dependencies are the reductions themselves.
 // Reductions are deterministic for a fixed grid size.
 #include "kry_common.cuh"
+#include <stdlib.h>
 
 #define KRY_ENTER(ctx)                                                         \
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
@@ -83,8 +84,13 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned long 
     __syncthreads();
 }
 
-template <typename T, int VEC, bool PEER>
-__global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
+// JT: basis vectors per register tile.  JT = 16 (128 registers, 2 CTAs/SM) is sized for the long
+// sweeps of GMRES(30); the JT = 4 instantiation (<= 64 registers, 4 CTAs/SM, phase C unrolled by
+// hand) keeps more loads in flight when only a few vectors are involved -- small k, Lanczos, exact
+// MGS.  It is an opt-in measurement variant (KRY_ORTH_SMALLK=1): the JT = 16 code is unchanged.
+template <typename T, int VEC, bool PEER, int JT = 16>
+__global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(OrthArgs<T> a) {
+    constexpr int TB = JT < 8 ? JT : 8;     // vectors loaded per inner tile
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[32];
     __shared__ double c_s[KRY_MAX_SLOTS];
@@ -107,10 +113,10 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
     if (a.algo == KRY_ORTH_CGS) {
         for (int pass = 0; pass < a.passes; ++pass) {
             // ---- phase A: block dots ----
-            for (int jb = 0; jb < cnt || (jb == 0 && pre_pending); jb += ORTH_JT) {
-                double acc[ORTH_JT];
+            for (int jb = 0; jb < cnt || (jb == 0 && pre_pending); jb += JT) {
+                double acc[JT];
 #pragma unroll
-                for (int t = 0; t < ORTH_JT; ++t) acc[t] = 0.0;
+                for (int t = 0; t < JT; ++t) acc[t] = 0.0;
                 for (long long i = i0; i < nvec; i += stride) {
                     double qv[VEC];
                     VecIO<T, VEC>::loadrw(q, i, qv);
@@ -125,17 +131,17 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
                     }
                     if (cnt > 0) {
 #pragma unroll
-                        for (int tb = 0; tb < ORTH_JT; tb += 8) {
+                        for (int tb = 0; tb < JT; tb += TB) {
                             if (jb + tb < cnt) {
-                                double vv[8][VEC];
+                                double vv[TB][VEC];
 #pragma unroll
-                                for (int t = 0; t < 8; ++t) {
+                                for (int t = 0; t < TB; ++t) {
                                     int j = jb + tb + t;
                                     j = j < cnt ? j : cnt - 1;
                                     VecIO<T, VEC>::load(a.Vdot + (long long)(a.j0 + j) * ldv, i, vv[t]);
                                 }
 #pragma unroll
-                                for (int t = 0; t < 8; ++t)
+                                for (int t = 0; t < TB; ++t)
 #pragma unroll
                                     for (int u = 0; u < VEC; ++u) acc[tb + t] = fma(vv[t][u], qv[u], acc[tb + t]);
                             }
@@ -151,14 +157,14 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
                             qe = (double)q[i];
                         }
 #pragma unroll
-                        for (int t = 0; t < ORTH_JT; ++t)
+                        for (int t = 0; t < JT; ++t)
                             if (jb + t < cnt)
                                 acc[t] = fma((double)a.Vdot[(long long)(a.j0 + jb + t) * ldv + i], qe, acc[t]);
                     }
                 }
                 pre_pending = false;
 #pragma unroll
-                for (int t = 0; t < ORTH_JT; ++t) {
+                for (int t = 0; t < JT; ++t) {
                     if (jb + t < cnt) {   // uniform across the CTA
                         double s = kry_block_sum(acc[t], sm);
                         if (threadIdx.x == 0) partial_slot(a.partials, buf, jb + t)[blockIdx.x] = s;
@@ -176,15 +182,15 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
             for (long long i = i0; i < nvec; i += stride) {
                 double qv[VEC];
                 VecIO<T, VEC>::loadrw(q, i, qv);
-                for (int jb = 0; jb < cnt; jb += 8) {
-                    double vv[8][VEC];
+                for (int jb = 0; jb < cnt; jb += TB) {
+                    double vv[TB][VEC];
 #pragma unroll
-                    for (int t = 0; t < 8; ++t) {
+                    for (int t = 0; t < TB; ++t) {
                         int j = jb + t < cnt ? jb + t : cnt - 1;
                         VecIO<T, VEC>::load(a.Vsub + (long long)(a.j0 + j) * ldv, i, vv[t]);
                     }
 #pragma unroll
-                    for (int t = 0; t < 8; ++t)
+                    for (int t = 0; t < TB; ++t)
                         if (jb + t < cnt) {
                             const double c = c_s[jb + t];
 #pragma unroll
@@ -336,7 +342,22 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
         const double nrm = sqrt(nrm2);
         if (blockIdx.x == 0 && threadIdx.x == 0) a.nrm[0] = nrm;
         if (a.vnext != nullptr) {
-            for (long long i = i0; i < nvec; i += stride) {
+            long long i = i0;
+            if (JT < 16) {
+                // four independent loads in flight per thread before the first store
+                for (; i + 3 * stride < nvec; i += 4 * stride) {
+                    double qv[4][VEC];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+#pragma unroll
+                        for (int u = 0; u < VEC; ++u) qv[r][u] = nrm > 0.0 ? qv[r][u] / nrm : 0.0;
+                        VecIO<T, VEC>::store(a.vnext, i + r * stride, qv[r]);
+                    }
+                }
+            }
+            for (; i < nvec; i += stride) {
                 double qv[VEC];
                 VecIO<T, VEC>::loadrw(q, i, qv);
 #pragma unroll
@@ -539,6 +560,40 @@ static int coop_grid(long long work_items, int max_blocks) {
     return (int)(need < cap ? need : cap);
 }
 
+// KRY_ORTH_SMALLK=1 (measurement switch, default off): calls that involve few basis vectors per
+// sweep -- block CGS against <= 4 vectors, every exact-MGS / Lanczos call -- use the JT = 4
+// instantiation (higher occupancy, see orth_kernel).  Single-GPU only.
+static bool orth_smallk_enabled() {
+    static int state = -1;
+    if (state < 0) {
+        const char* e = getenv("KRY_ORTH_SMALLK");
+        state = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return state == 1;
+}
+
+template <typename T>
+static int orth_launch_small(kry_ctx* ctx, OrthArgs<T>& a, bool al) {
+    const int W = VecWidth<T>::value;
+    static int blocks_per_sm[2] = {0, 0};        // [aligned, unaligned] instantiation
+    const int which = al ? 0 : 1;
+    if (blocks_per_sm[which] == 0) {
+        int nb = 0, rc;
+        if (al) rc = max_blocks_of(orth_kernel<T, W, false, 4>, &nb);
+        else rc = max_blocks_of(orth_kernel<T, 1, false, 4>, &nb);
+        if (rc) return rc;
+        KRY_REQUIRE(nb >= 1, "small-tile orth kernel does not fit");
+        blocks_per_sm[which] = nb;
+    }
+    void* args[] = {&a};
+    const int max_blocks = blocks_per_sm[which] * ctx->sm_count;
+    const int g = coop_grid(al ? a.n / W : a.n, max_blocks);
+    void* k = al ? (void*)orth_kernel<T, W, false, 4> : (void*)orth_kernel<T, 1, false, 4>;
+    KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
 template <typename T>
 static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
     const int W = VecWidth<T>::value;
@@ -546,6 +601,8 @@ static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
               (!a.pre_vec || kry_aligned16(a.pre_vec)) && (!a.vnext || kry_aligned16(a.vnext));
     void* args[] = {&a};
     const bool peer = a.peer.world > 1;
+    if (!peer && orth_smallk_enabled() && (a.algo == KRY_ORTH_MGS || a.nv - a.j0 <= 4))
+        return orth_launch_small<T>(ctx, a, al);
     if (al) {
         int g = coop_grid(a.n / W, max_blocks);
         void* k = peer ? (void*)orth_kernel<T, W, true> : (void*)orth_kernel<T, W, false>;

@@ -1455,6 +1455,7 @@ _ORTHO = {
     "cgs2": (KRY_ORTH_CGS, 2),       # new: CGS with re-orthogonalisation
 }
 _CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
+_SPLIT_SCALE = bool(__import__("os").environ.get("KRY_ORTH_SPLIT_SCALE"))   # measurement switch, default off
 
 
 class DeviceBlock(object):
@@ -1699,6 +1700,12 @@ class Arnoldi(object):
                                    nrm=nrm if (last and fused_tail) else None,
                                    vnext=vnext if (last and fused_tail) else None, h_ptr=h_ptr)
                     j0 = j1
+            elif _SPLIT_SCALE and fused_tail and ctx.comm is None:
+                # experiment (KRY_ORTH_SPLIT_SCALE=1): the normalised store as a separate streaming
+                # kernel at full occupancy instead of phase C of the register-heavy cooperative kernel
+                ctx.orth_fused(Vt, Vsub, r0, r1, q0, self._passes, self._algo, None, nrm=nrm, vnext=None,
+                               pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr)
+                ctx.scale_dev(nrm, 1, 1.0, q0, vnext)
             else:
                 ctx.orth_fused(Vt, Vsub, r0, r1, q0, self._passes, self._algo, None,
                                nrm=nrm if fused_tail else None,
