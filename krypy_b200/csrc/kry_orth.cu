@@ -563,13 +563,16 @@ static int coop_grid(long long work_items, int max_blocks) {
 // KRY_ORTH_SMALLK=1 (measurement switch, default off): calls that involve few basis vectors per
 // sweep -- block CGS against <= 4 vectors, every exact-MGS / Lanczos call -- use the JT = 4
 // instantiation (higher occupancy, see orth_kernel).  Single-GPU only.
-static bool orth_smallk_enabled() {
+// Value: 1 = threshold 4 (one register tile); any other n > 1 = use the variant up to n vectors
+// (q is then re-read once per 4-vector tile in the dot phase: a bandwidth-for-occupancy trade to measure).
+static int orth_smallk_threshold() {
     static int state = -1;
     if (state < 0) {
         const char* e = getenv("KRY_ORTH_SMALLK");
-        state = (e && e[0] && e[0] != '0') ? 1 : 0;
+        int v = e ? atoi(e) : 0;
+        state = v <= 0 ? 0 : (v == 1 ? 4 : (v > KRY_MAX_SLOTS ? KRY_MAX_SLOTS : v));
     }
-    return state == 1;
+    return state;
 }
 
 template <typename T>
@@ -601,7 +604,8 @@ static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
               (!a.pre_vec || kry_aligned16(a.pre_vec)) && (!a.vnext || kry_aligned16(a.vnext));
     void* args[] = {&a};
     const bool peer = a.peer.world > 1;
-    if (!peer && orth_smallk_enabled() && (a.algo == KRY_ORTH_MGS || a.nv - a.j0 <= 4))
+    const int small_thr = orth_smallk_threshold();
+    if (!peer && small_thr > 0 && (a.algo == KRY_ORTH_MGS || a.nv - a.j0 <= small_thr))
         return orth_launch_small<T>(ctx, a, al);
     if (al) {
         int g = coop_grid(a.n / W, max_blocks);
