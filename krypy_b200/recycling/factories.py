@@ -16,16 +16,17 @@ class RitzFactory(_DeflationVectorFactory):
     to add, an evaluator rates every enlarged set (estimated time of the next solve), the best one is
     kept; the overall best rated set wins (krypy/recycling/factories.py:20-139)."""
 
-    def __init__(self, subset_evaluator, subsets_generator=None, mode="ritz", print_results=None):
+    def __init__(self, subset_evaluator, subsets_generator=None, mode="ritz", print_results=None, realify=True):
         from . import generators
         self.subsets_generator = generators.RitzSmall() if subsets_generator is None else subsets_generator
         self.subset_evaluator = subset_evaluator
         self.mode = mode
         self.print_results = print_results
+        self.realify = realify      # new, as in RitzFactorySimple: False = the reference's complex vectors
 
     def get(self, deflated_solver):
         ritz = deflation.Ritz(deflated_solver, mode=self.mode)
-        return ritz.get_vectors_dev(self._get_best_subset(ritz), realify=True)
+        return ritz.get_vectors_dev(self._get_best_subset(ritz), realify=self.realify)
 
     def _rate(self, ritz, subset, table):
         try:
