@@ -25,6 +25,13 @@ for sw in KRY_ORTH_SMALLK KRY_ORTH_SPLIT_SCALE; do
       -k "orth or fixture or arnoldi or variants" > gpurun_out/pytest_$sw.log 2>&1; tail -1 gpurun_out/pytest_$sw.log
   env $sw=1 timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/bench_$sw.log 2>&1; tail -1 gpurun_out/bench_$sw.log | cut -c1-200
 done
+# the small-tile variant across many tiles (every CGS call up to 40 vectors goes through it)
+KRY_ORTH_SMALLK=40 timeout 600 python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -p no:cacheprovider -k "orth" \
+    > gpurun_out/pytest_smallk40.log 2>&1; tail -1 gpurun_out/pytest_smallk40.log
+for thr in 2 8 12; do
+  KRY_ORTH_SMALLK=$thr timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/bench_smallk_$thr.log 2>&1
+  tail -1 gpurun_out/bench_smallk_$thr.log | cut -c1-160
+done
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_reference.log 2>&1
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 220 --csv \
     --log-file gpurun_out/launch_list.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e \
