@@ -321,6 +321,18 @@ def run_b200(args, rank, world, local_rank):
                 "timing": "CUDA events in the timed region" if world == 1 else
                           "CUDA events in one eager cycle after the timed region (timed region replays CUDA "
                           "graphs); split kernels + NVLink peer all-reduces, per-rank bytes"}
+    if "orth" in summ:
+        # per-k profile of the fused Gram-Schmidt kernel: average microseconds and algorithmic GB/s by
+        # the number of basis vectors involved (shows the small-k inefficiency; A/B of KRY_ORTH_SMALLK)
+        try:
+            by_nv = {}
+            for t_ms, (nq, nv, passes, algo, has_next) in zip(summ["orth"]["ms"], summ["orth"]["meta"]):
+                by_nv.setdefault(int(nv), []).append((t_ms, (passes * (2 * nv + 3) + (2 if has_next else 0)) * nq * 8.0))
+            extra["orth_by_nv"] = {str(nv): {"us": round(1e3 * sum(t for t, _ in v) / len(v), 1),
+                                             "GBs": round(sum(b for _, b in v) / sum(t for t, _ in v) / 1e6, 0)}
+                                   for nv, v in sorted(by_nv.items())}
+        except Exception as exc:
+            extra["orth_by_nv"] = {"error": repr(exc)}
     if "spmv" in summ:
         s = summ["spmv"]
         by = sum(nnz * 12.0 + 4.0 * (nr + 1) + 2.0 * nr * 8.0 for (nr, nnz) in s["meta"])
