@@ -88,7 +88,9 @@ __device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned long 
 // sweeps of GMRES(30); the JT = 4 instantiation (<= 64 registers, 4 CTAs/SM, phase C unrolled by
 // hand) keeps more loads in flight when only a few vectors are involved -- small k, Lanczos, exact
 // MGS.  It is an opt-in measurement variant (KRY_ORTH_SMALLK=1): the JT = 16 code is unchanged.
-template <typename T, int VEC, bool PEER, int JT = 16>
+// CU: phase C (the normalised store) unrolled by hand, four loads in flight per thread.  Always on
+// for JT = 4; KRY_ORTH_CUNROLL=1 selects it for the JT = 16 kernel as a second measurement variant.
+template <typename T, int VEC, bool PEER, int JT = 16, bool CU = (JT < 16)>
 __global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(OrthArgs<T> a) {
     constexpr int TB = JT < 8 ? JT : 8;     // vectors loaded per inner tile
     cg::grid_group grid = cg::this_grid();
@@ -343,7 +345,7 @@ __global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(O
         if (blockIdx.x == 0 && threadIdx.x == 0) a.nrm[0] = nrm;
         if (a.vnext != nullptr) {
             long long i = i0;
-            if (JT < 16) {
+            if (CU) {
                 // four independent loads in flight per thread before the first store
                 for (; i + 3 * stride < nvec; i += 4 * stride) {
                     double qv[4][VEC];
@@ -575,6 +577,15 @@ static int orth_smallk_threshold() {
     return state;
 }
 
+static bool orth_cunroll_enabled() {
+    static int state = -1;
+    if (state < 0) {
+        const char* e = getenv("KRY_ORTH_CUNROLL");
+        state = (e && e[0] && e[0] != '0') ? 1 : 0;
+    }
+    return state == 1;
+}
+
 template <typename T>
 static int orth_launch_small(kry_ctx* ctx, OrthArgs<T>& a, bool al) {
     const int W = VecWidth<T>::value;
@@ -607,6 +618,14 @@ static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
     const int small_thr = orth_smallk_threshold();
     if (!peer && small_thr > 0 && (a.algo == KRY_ORTH_MGS || a.nv - a.j0 <= small_thr))
         return orth_launch_small<T>(ctx, a, al);
+    if (!peer && orth_cunroll_enabled()) {
+        // same kernel, same grid; only phase C differs
+        const int g = coop_grid(al ? a.n / W : a.n, max_blocks);
+        void* k = al ? (void*)orth_kernel<T, W, false, 16, true> : (void*)orth_kernel<T, 1, false, 16, true>;
+        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
+        KRY_LAUNCHED(ctx);
+        return KRY_OK;
+    }
     if (al) {
         int g = coop_grid(a.n / W, max_blocks);
         void* k = peer ? (void*)orth_kernel<T, W, true> : (void*)orth_kernel<T, W, false>;

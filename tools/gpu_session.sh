@@ -20,7 +20,7 @@ gcc -O2 -I include -I /usr/local/cuda/include examples/gmres_c_abi.c -o gpurun_o
     > gpurun_out/c_abi_example.log 2>&1; tail -2 gpurun_out/c_abi_example.log
 timeout 900 python bench.py > gpurun_out/bench_n1.log 2>&1; tail -1 gpurun_out/bench_n1.log
 # A/B of the two opt-in measurement switches (correctness first, then the bench line without the CPU legs)
-for sw in KRY_ORTH_SMALLK KRY_ORTH_SPLIT_SCALE; do
+for sw in KRY_ORTH_SMALLK KRY_ORTH_SPLIT_SCALE KRY_ORTH_CUNROLL; do
   env $sw=1 timeout 900 python -m pytest tests/test_kernels_gpu.py tests/test_solvers_gpu.py -m gpu -q -x -p no:cacheprovider \
       -k "orth or fixture or arnoldi or variants" > gpurun_out/pytest_$sw.log 2>&1; tail -1 gpurun_out/pytest_$sw.log
   env $sw=1 timeout 600 python bench.py --no-cpu-baseline --no-e2e > gpurun_out/bench_$sw.log 2>&1; tail -1 gpurun_out/bench_$sw.log | cut -c1-200

@@ -57,20 +57,25 @@ def main():
                        stderr=subprocess.DEVNULL)
         objs.append(obj)
     old, new = sass(objs[0]), sass(objs[1])
+    # default template arguments appended by later edits (old kernel == new kernel with these defaults)
+    DEFAULTS = [", (int)16, (bool)0>", ", (int)16>"]
+    dn_new = {n: demangle(n) for n in new}
     bad = 0
+    matched = set()
     for name, body in sorted(old.items()):
-        cands = [n for n in new if n == name or re.sub(r"ELi\d+E(Ev\d)", r"E\1", n) == name]
-        cands = [n for n in cands if n == name or n.replace("ELi16EEv", "EEv") == name] or cands
+        dn = demangle(name)
+        cands = [n for n, d in dn_new.items() if d == dn or any(d == dn.replace(">(", suf + "(", 1) for suf in DEFAULTS)]
         if not cands:
-            print("%s: not present any more" % demangle(name))
+            print("%s: not present any more" % dn)
+            bad += 1
             continue
         n2 = cands[0]
+        matched.add(n2)
         same = [ln.replace(name, "F") for ln in body] == [ln.replace(n2, "F") for ln in new[n2]]
-        print("%s: %s (%d lines)" % (demangle(name), "SAME" if same else "DIFFERENT", len(body)))
+        print("%s: %s (%d lines)" % (dn, "SAME" if same else "DIFFERENT", len(body)))
         bad += not same
-    extra = [n for n in new if all(n != o and n.replace("ELi16EEv", "EEv") != o for o in old)]
-    for n in sorted(extra):
-        print("new kernel: %s" % demangle(n))
+    for n in sorted(set(new) - matched):
+        print("new kernel: %s" % dn_new[n])
     sys.exit(1 if bad else 0)
 
 
