@@ -20,14 +20,36 @@ J2 = np.array([[0.0, -1.0], [1.0, 0.0]])
 
 
 def expand_sparse(A):
-    """N x M (complex or real) scipy sparse -> 2N x 2M real CSR of the embedding"""
+    """N x M (complex or real) scipy sparse -> 2N x 2M real CSR of the embedding (int32 indices,
+    sorted).  Direct O(nnz) construction -- ``scipy.sparse.kron`` needs several times the memory of
+    the result, which matters at the sizes this library is for.  Row 2i holds ``(2j: re, 2j+1: -im)``,
+    row 2i+1 ``(2j: im, 2j+1: re)`` for every entry (i, j)."""
     import scipy.sparse as sp
     A = sp.csr_matrix(A)
-    E = sp.kron(A.real.astype(np.float64), I2, format="csr")
-    if np.iscomplexobj(A.data):
-        E = E + sp.kron(sp.csr_matrix(A.imag.astype(np.float64)), J2, format="csr")
-    E = sp.csr_matrix(E)
-    E.sort_indices()
+    if not A.has_sorted_indices:
+        A = A.sorted_indices()
+    N, M = A.shape
+    nnz = A.nnz
+    if 4 * nnz >= 2 ** 31 - 1:
+        raise NotImplementedError("embedded matrix needs 64-bit row pointers (not built)")
+    indptr = A.indptr.astype(np.int64)
+    counts = np.diff(indptr)
+    re = np.ascontiguousarray(A.data.real, dtype=np.float64)
+    im = np.ascontiguousarray(A.data.imag, dtype=np.float64) if np.iscomplexobj(A.data) else np.zeros(nnz)
+    rows = np.repeat(np.arange(N, dtype=np.int64), counts)
+    t = np.arange(nnz, dtype=np.int64) - indptr[rows]            # position within the row
+    even = 4 * indptr[rows] + 2 * t                                # destination of (2j) in row 2i
+    odd = even + 2 * counts[rows]                                  # ... in row 2i+1
+    cols = np.empty(4 * nnz, dtype=np.int32)
+    vals = np.empty(4 * nnz, dtype=np.float64)
+    c2 = (2 * A.indices.astype(np.int64)).astype(np.int32)
+    cols[even], cols[even + 1], cols[odd], cols[odd + 1] = c2, c2 + 1, c2, c2 + 1
+    vals[even], vals[even + 1], vals[odd], vals[odd + 1] = re, -im, im, re
+    ip2 = np.zeros(2 * N + 1, dtype=np.int64)
+    ip2[1::2] = 4 * indptr[:-1] + 2 * counts
+    ip2[2::2] = 4 * indptr[1:]
+    E = sp.csr_matrix((vals, cols, ip2.astype(np.int32)), shape=(2 * N, 2 * M))
+    E.has_sorted_indices = True
     return E
 
 
