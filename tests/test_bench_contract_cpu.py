@@ -48,3 +48,54 @@ def test_committed_b200_lines_carry_the_contract():
         if n == 1:
             assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
             assert d["cpu_baseline"]["kind"] in ("port", "reference")
+
+
+def test_b200_arm_assembles_its_line_over_the_test_double(monkeypatch, capsys):
+    """Dry run of bench.run_b200 at a tiny grid: the device layer is the numpy test double and the few
+    torch.cuda calls of the bench are stubbed.  Catches Python-level breakage of the bench (names, keys,
+    the e2e / breakdown / per-solve legs) without a GPU; says nothing about performance."""
+    import time
+    import types
+
+    import torch
+
+    import bench
+    import fake_device
+
+    fake = fake_device.install(monkeypatch)
+
+    class Ev(object):
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t) + 1e-3
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", n=24, ortho="cgs",
+                                 no_cpu_baseline=False, no_e2e=False, cpu_iters=3)
+    bench.run_b200(args, 0, 1, 0)
+    out = capsys.readouterr().out
+    lines = [ln for ln in out.splitlines() if ln.strip().startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
+    assert d["metric"] == "gmres_iterations_per_second" and d["n_gpus"] == 1 and d["iterations"] == 60
+    assert d["gpu_launches"] > 0 and d["value"] > 0 and d["dtype"] == "f64"
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    assert "error" not in d["e2e"]["per_solve"] and 0 < d["e2e"]["per_solve"]["iterations_per_upload"] <= 150
+    assert "error" not in d["e2e"]["breakdown_ms"] and d["e2e"]["breakdown_ms"]["total"] > 0
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert d["parity_vs_cpu_max_rel"] < 1e-10           # product (over the double) vs oracle, same inputs
+    assert fake.launch_count() > 0
