@@ -99,3 +99,19 @@ def test_b200_arm_assembles_its_line_over_the_test_double(monkeypatch, capsys):
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert d["parity_vs_cpu_max_rel"] < 1e-10           # product (over the double) vs oracle, same inputs
     assert fake.launch_count() > 0
+
+
+def test_smoke_logic_over_the_test_double(monkeypatch, capsys):
+    """__graft_entry__.smoke() with the device layer replaced by the test double: its oracle comparison
+    and thresholds are sound (the real run on cuda:0 is the driver's)."""
+    import torch
+
+    import fake_device
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as g
+
+    fake_device.install(monkeypatch)
+    monkeypatch.setattr(torch.cuda, "is_available", lambda: True)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    g.smoke()
+    assert "smoke ok" in capsys.readouterr().out
