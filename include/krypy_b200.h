@@ -127,6 +127,17 @@ int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const
                    const void* pre_vec, const double* pre_coef_dev,
                    double* h_dev, double* nrm_dev, void* vnext);
 
+/* Fused Lanczos step for a DIAGONAL inner-product matrix B = diag(bdiag) (BASELINE config C5),
+ * krypy/utils.py:1000-1045 with inner(X, Y, ip_B) = X^H (B Y) (utils.py:190-193), ONE cooperative
+ * kernel:  q -= pre_coef_dev[0]*vprev (vprev may be NULL: k == 0);  alpha = <vk, q>_B;
+ * h3_dev[1] += alpha;  q -= alpha*vk;  h3_dev[2] = beta = sqrt(<q, q>_B);  vnext = q/beta
+ * (vnext may be NULL).  h3_dev is the [H[k-1,k], H[k,k], H[k+1,k]] triple kry_minres_recur reads.
+ * Opt-in variant (host switch KRY_LANCZOS_DIAGB=1); the default runs this step with
+ * kry_axpy_dev / kry_diag_mul / kry_block_dot / kry_scale_dev. */
+int kry_lanczos_diag(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk,
+                     const void* bdiag, void* q, const double* pre_coef_dev, double* h3_dev,
+                     void* vnext);
+
 /* ---- oblique projection for deflation (one cooperative kernel) ---------- */
 /* a <- (I - V (R^-1 Q^H) W^H)^iterations a  (krypy/utils.py:604-627 with
  * :522-552; called from deflation.py:135-143).  W, V: d vectors each; Q, R:

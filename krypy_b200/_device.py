@@ -414,6 +414,11 @@ class Context(object):
             if vnext is not None:
                 self.scale_dev(nrm, 1, 1.0, q, vnext)
 
+    def lanczos_diag(self, vprev, vk, bdiag, q, pre_coef, h3, vnext):
+        """fused Lanczos step for a diagonal inner-product matrix (kry_lanczos_diag)"""
+        check(self.lib.kry_lanczos_diag(self.h, code(q), q.numel(), _p(vprev), vk.data_ptr(), bdiag.data_ptr(),
+                                        q.data_ptr(), _p(pre_coef), h3.data_ptr(), _p(vnext)))
+
     def alloc_basis(self, rows, N, dtype, op=None):
         """(rows, ld) storage for a vector-major basis.  Row-partitioned runs place it in a
         peer-mapped region with room for the halo behind each row, so the SpMV exchange reads

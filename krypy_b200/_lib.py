@@ -51,6 +51,8 @@ PROTOTYPES = {
     "kry_orth_fused": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "kry_lanczos_diag": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                 c_void_p, c_void_p]),
     "kry_project": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p,
                             c_void_p, c_void_p, c_int, c_void_p]),
     "kry_givens_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),

@@ -1456,6 +1456,7 @@ _ORTHO = {
 }
 _CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
 _SPLIT_SCALE = bool(__import__("os").environ.get("KRY_ORTH_SPLIT_SCALE"))   # measurement switch, default off
+_LANCZOS_DIAGB = bool(__import__("os").environ.get("KRY_LANCZOS_DIAGB"))      # measurement switch, default off
 
 
 class DeviceBlock(object):
@@ -1711,6 +1712,12 @@ class Arnoldi(object):
                                nrm=nrm if fused_tail else None,
                                vnext=vnext if fused_tail else None,
                                pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr, halo_op=self._halo_op)
+        elif (_LANCZOS_DIAGB and lanczos and not cplx and self.M is None and ctx.comm is None
+              and self._passes == 1 and self._diag_ip() is not None):
+            # experiment (KRY_LANCZOS_DIAGB=1): the whole Lanczos step for a diagonal ip_B in ONE
+            # cooperative kernel instead of the seven launches of the generic path below
+            ctx.lanczos_diag(pre_vec, Vt[k], self._diag_ip(), q0, pre_coef, self._lz, vnext)
+            return
         else:
             # generic inner product: the reference's loop, one reduction at a time
             if pre_vec is not None:
@@ -1738,6 +1745,22 @@ class Arnoldi(object):
                 ctx.scale_dev(nrm, 1, 1.0, q0, V[k + 1])
         if cplx:
             self._Vtw.refresh(ctx, k + 1)
+
+    def _diag_ip(self):
+        """device vector of the diagonal of ip_B when it is a real positive diagonal operator, else None"""
+        if "_diag_ip_cache" not in self.__dict__:
+            d = None
+            try:
+                B = get_linearoperator((self.N, self.N), self.ip_B)
+            except TypeError:
+                B = None
+            if isinstance(B, TimedLinearOperator):
+                B = B._linear_operator
+            if isinstance(B, DiagonalLinearOperator) and numpy.dtype(B._d.dtype).kind != "c" \
+                    and B._d.shape[0] > 0 and float(B._d.min()) > 0.0:
+                d = B._dev(self._td)
+            self.__dict__["_diag_ip_cache"] = d
+        return self.__dict__["_diag_ip_cache"]
 
     # -- Householder orthogonalisation (utils.py:970-994) ------------------------------------
     def _house_make(self, j, xd):

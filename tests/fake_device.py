@@ -230,6 +230,24 @@ class FakeContext(object):
             if vnext is not None:
                 vnext.copy_((qq / n2 if n2 > 0 else torch.zeros_like(qq)).to(vnext.dtype))
 
+    # ---- kry_lanczos_diag ----
+    def lanczos_diag(self, vprev, vk, bdiag, q, pre_coef, h3, vnext):
+        self._count("lanczos_diag")
+        dt = q.dtype
+        qq = q.double()
+        if vprev is not None:
+            qq = (qq - float(pre_coef[0]) * vprev.double()).to(dt).double()
+        bq = (bdiag.double() * qq).to(dt).double()
+        alpha = float(vk.double() @ bq)
+        h3[1] += alpha
+        qq = (qq - alpha * vk.double()).to(dt).double()
+        bq = (bdiag.double() * qq).to(dt).double()
+        beta = float(np.sqrt(abs(float(qq @ bq))))
+        h3[2] = beta
+        q.copy_(qq.to(dt))
+        if vnext is not None:
+            vnext.copy_((qq / beta if beta > 0 else torch.zeros_like(qq)).to(vnext.dtype))
+
     # ---- kry_project ----
     @realviews
     def project(self, W, V, d, a, Q, R, iterations, c_first):

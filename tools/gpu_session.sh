@@ -38,6 +38,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 
     > gpurun_out/ncu_bench.log 2>&1
 timeout 1200 python tools/run_configs.py c2 c3 c4 c4r c5 > gpurun_out/configs_fullsize.json 2> gpurun_out/configs.err
 tail -3 gpurun_out/configs.err
+# C5 with the fused diagonal-ip_B Lanczos kernel (opt-in) next to the default above
+KRY_LANCZOS_DIAGB=1 timeout 900 python tools/run_configs.py c5 > gpurun_out/configs_c5_lanczos_diagB.json 2>> gpurun_out/configs.err
 # optional (slow, ~10-50x): memory / race checks of the kernels on the small parity cases
 #   compute-sanitizer --tool memcheck python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "not 100003" > gpurun_out/memcheck.log 2>&1
 #   compute-sanitizer --tool racecheck python -m pytest tests/test_kernels_gpu.py -m gpu -q -x -k "block_dot or orth_fused" > gpurun_out/racecheck.log 2>&1
