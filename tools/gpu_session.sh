@@ -14,6 +14,10 @@ tail -5 gpurun_out/pytest_gpu.log
 timeout 900 python -m pytest tests/test_zcomplex_gpu.py tests/test_zz_analysis_gpu.py -m gpu -q -p no:cacheprovider \
     > gpurun_out/pytest_new.log 2>&1
 tail -15 gpurun_out/pytest_new.log
+# opt-in variants (new cooperative kernel): own process, own timeout
+KRY_TEST_VARIANTS=1 timeout 600 python -m pytest tests/test_zz_variants_gpu.py -m gpu -q -p no:cacheprovider \
+    > gpurun_out/pytest_variants.log 2>&1
+tail -5 gpurun_out/pytest_variants.log
 timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; tail -2 gpurun_out/smoke.log
 gcc -O2 -I include -I /usr/local/cuda/include examples/gmres_c_abi.c -o gpurun_out/gmres_c_abi -L krypy_b200 -lkrypy_b200 \
     -L/usr/local/cuda/lib64 -lcudart -lm -Wl,-rpath,$PWD/krypy_b200 && timeout 300 gpurun_out/gmres_c_abi 1024 30 5 \
