@@ -40,6 +40,10 @@ timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/b
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -s 130 -c 220 --csv \
     --log-file gpurun_out/launch_list.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e \
     > gpurun_out/ncu_bench.log 2>&1
+# full ncu capture of the fused Gram-Schmidt kernel at k = 0, 1, 2 (launches 60..62 = start of the 3rd cycle)
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:orth_kernel -s 60 -c 3 -f \
+    -o gpurun_out/orth_smallk python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-e2e > gpurun_out/ncu_orth_smallk.log 2>&1
+ncu -i gpurun_out/orth_smallk.ncu-rep --page details > gpurun_out/orth_smallk_details.txt 2>/dev/null
 timeout 1200 python tools/run_configs.py c2 c3 c4 c4r c5 > gpurun_out/configs_fullsize.json 2> gpurun_out/configs.err
 tail -3 gpurun_out/configs.err
 # C5 with the fused diagonal-ip_B Lanczos kernel (opt-in) next to the default above
