@@ -228,7 +228,22 @@ class Context(object):
 
     def to_numpy(self, Xd):
         """device (k, N) -> numpy (N, k)."""
-        return np.ascontiguousarray(Xd.detach().cpu().numpy().T)
+        t = torch()
+        Xd = Xd.detach()
+        k = Xd.shape[0]
+        if Xd.numel() * Xd.element_size() < (1 << 20):
+            return np.ascontiguousarray(Xd.cpu().numpy().T)
+        # Large results: DMA into page-locked memory (torch's caching host allocator keeps the
+        # block for the next solve) instead of a pageable .cpu() copy, which runs at a tenth of
+        # the PCIe rate.  The returned array owns the pinned block (fresh per call: results are
+        # never aliased, SURVEY 8b ownership).  (k, N) -> (N, k): transposed on the device.
+        src = Xd.reshape(-1, 1) if k == 1 else Xd.t()
+        if not src.is_contiguous():
+            src = src.contiguous()
+        host = t.empty(src.shape, dtype=src.dtype, pin_memory=True)
+        host.copy_(src, non_blocking=True)
+        t.cuda.current_stream(self.device).synchronize()
+        return host.numpy()
 
     def upload_csr(self, A, dtype):
         """scipy.sparse matrix (any format) -> CsrDev."""

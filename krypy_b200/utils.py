@@ -1571,7 +1571,10 @@ class Arnoldi(object):
             self._Vd, self._Vt = self._Vtw.C, self._Vtw.T
             self._Pt = None
             if self.M is not None:
-                self._Ptw = _Twin(ctx, m1, N)
+                # (through the workspace like V: a CUDA graph recorded in one restart cycle is
+                # replayed in the next ones and must find the same buffers)
+                self._Ptw = (ws.tensor("Ptw", (m1, N), lambda: _Twin(ctx, m1, N)) if ws is not None
+                             else _Twin(ctx, m1, N))
                 self._Pd, self._Pt = self._Ptw.C, self._Ptw.T
         else:
             if ws is not None:
@@ -1582,7 +1585,8 @@ class Arnoldi(object):
             self._Vt = self._Vd
             self._Pt = None
             if self.M is not None:
-                self._Ps = ctx.alloc_basis(m1, N, td)
+                self._Ps = (ws.tensor("P", (m1, N, td), lambda: ctx.alloc_basis(m1, N, td)) if ws is not None
+                            else ctx.alloc_basis(m1, N, td))
                 self._Pd = self._Ps[:, :N]
                 self._Pt = self._Pd
         self._ld = self._Vs.stride(0)
@@ -1606,7 +1610,12 @@ class Arnoldi(object):
             self._tmp = ctx.scalars(4)
             self._lz = ctx.scalars(3)          # Lanczos: [H[k-1,k], H[k,k], H[k+1,k]]
             self._lz_st = ctx.scalars(16)
-        self._t = None if (self._euclid and self.M is None) else ctx.empty((1, N), td)
+        if self._euclid and self.M is None:
+            self._t = None
+        elif ws is not None:
+            self._t = ws.tensor("t", (1, N, td), lambda: ctx.empty((1, N), td))
+        else:
+            self._t = ctx.empty((1, N), td)
         self._hcol = self._hcol_store[nr:]      # one leading zero: H[-1, 0] of linsys.py:828
         self._hfro2 = 0.0
 

@@ -56,6 +56,24 @@ def main():
             out["recycling__%s__%s__lens" % (sname, which)] = np.array(lens)
             out["recycling__%s__%s__finals" % (sname, which)] = np.array(finals)
             print(sname, which, lens)
+        # 'smallest_res' after the first recycled solve: the Ritz pairs of the deflated eigenvalues
+        # (0.01, 0.02, 0.03) and of 1e-8, 1e-4 are all converged to rounding level (residual norms
+        # 1e-15 .. 3e-10 = sqrt of cancellation noise), so WHICH of 0.01/0.02/0.03 becomes the third
+        # deflation vector of solve 3 is decided by rounding noise.  Record the reference's iteration
+        # count of solve 3 for each possible outcome (selection forced by Ritz value).
+        by_third = []
+        for third in (0.01, 0.02, 0.03):
+            ls = krypy.linsys.LinearSystem(np.diag(d), np.ones((N, 1)), normal=True, self_adjoint=True,
+                                           positive_definite=True)
+            fac = krypy.recycling.factories.RitzFactorySimple(n_vectors=3, which="smallest_res")
+            rs = Solver()
+            for i in range(2):
+                rs.solve(ls, vector_factory=fac, maxiter=50, tol=1e-5, x0=None)
+            s = rs.solve(ls, vector_factory=cases.NearestRitzValuesFactory(krypy, (1e-8, 1e-4, third)),
+                         maxiter=50, tol=1e-5, x0=None)
+            by_third.append(len(s.resnorms))
+        out["recycling__%s__smallest_res__solve3_len_by_third" % sname] = np.array(by_third)
+        print(sname, "solve-3 length by third deflated value (0.01, 0.02, 0.03):", by_third)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ritz_recycling.npz"), **out)
 
 

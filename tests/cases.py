@@ -242,3 +242,20 @@ COMPLEX_CASES = [
     "z_defl_gmres", "z_defl_gmres_ipB", "z_dense_gmres_M_ipB", "z_dense_minres_M_ipB",
     "z_dense_cg_M_ipB", "z_dense_gmres_MlMr",
 ]
+
+
+class NearestRitzValuesFactory(object):
+    """Deflation-vector factory (duck-typed like krypy.recycling.factories._DeflationVectorFactory)
+    that selects the Ritz vectors whose Ritz values are nearest to the given targets.  Works with
+    the reference package and with krypy_b200 (``kp`` = the package)."""
+
+    def __init__(self, kp, targets):
+        self.kp = kp
+        self.targets = targets
+
+    def get(self, solver):
+        import numpy
+        ritz = self.kp.deflation.Ritz(solver, mode="ritz")
+        vals = numpy.asarray(ritz.values)
+        idx = [int(numpy.argmin(numpy.abs(vals - t))) for t in self.targets]
+        return ritz.get_vectors(idx)

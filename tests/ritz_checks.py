@@ -64,7 +64,18 @@ def check_ritz_pairs(name):
 
 
 def check_recycling(sname, which):
-    """reference test/test_recycling.py:8-39 with the iteration counts the reference produces"""
+    """reference test/test_recycling.py:8-39 with the iteration counts the reference produces.
+
+    'smallest_res', third solve: after the first recycled solve the Ritz pairs of the deflated
+    eigenvalues 0.01, 0.02, 0.03 and of 1e-8, 1e-4 are ALL converged to rounding level (Ritz residual
+    norms 5e-15 .. 3e-10, i.e. square roots of cancellation noise -- measured on the reference and
+    on the B200, tools/diag_recycling.py, profiles/r2_recycling_diag.json).  Which of 0.01/0.02/0.03
+    the criterion ranks third is therefore decided by rounding noise: the reference's arithmetic
+    picks 0.01 (14 iterations), the B200's picked 0.03 in the CG run (15 iterations) -- and the
+    UNMODIFIED reference also needs 15 when it is handed that selection (fixture
+    ``solve3_len_by_third``, oracle/make_golden_ritz.py).  The check is therefore: solves 1 and 2
+    exactly as the reference; every selected pair converged to the noise floor; solve 3 exactly the
+    reference's count for the selection that was made."""
     import krypy_b200 as kp
     gold = runners.load_golden("ritz_recycling")
     N = 100
@@ -76,9 +87,19 @@ def check_recycling(sname, which):
     fac = kp.recycling.factories.RitzFactorySimple(n_vectors=3, which=which)
     rs = Solver()
     lens = []
+    want = list(gold["recycling__%s__%s__lens" % (sname, which)])
     with warnings.catch_warnings():
         warnings.simplefilter("ignore")
         for i in range(3):
+            if which == "smallest_res" and i == 2:
+                r = kp.deflation.Ritz(rs.last_solver, mode="ritz")
+                order = np.argsort(r.resnorms)[:3]
+                sel = np.sort(np.real(np.asarray(r.values)[order]))
+                assert np.all(np.asarray(r.resnorms)[order] < 1e-8), r.resnorms        # converged to the noise floor
+                np.testing.assert_allclose(sel[:2], [1e-8, 1e-4], rtol=1e-4)
+                third = int(np.argmin(np.abs(np.array([0.01, 0.02, 0.03]) - sel[2])))
+                assert abs(sel[2] - (0.01, 0.02, 0.03)[third]) < 1e-9
+                want[2] = int(gold["recycling__%s__smallest_res__solve3_len_by_third" % sname][third])
             s = rs.solve(ls, vector_factory=fac, maxiter=50, tol=1e-5, x0=None)
             lens.append(len(s.resnorms))
             assert s.resnorms[-1] <= 1e-5
@@ -86,4 +107,4 @@ def check_recycling(sname, which):
             np.testing.assert_almost_equal(s.resnorms[-1], rn / ls.MMlb_norm, decimal=12)
             if i > 0:
                 assert lens[-1] <= lens[0]
-    assert lens == list(gold["recycling__%s__%s__lens" % (sname, which)]), (lens, sname, which)
+    assert lens == want, (lens, want, sname, which)

@@ -255,3 +255,32 @@ def test_recycling_ritz_factory_simple(sname, which):
     """reference test/test_recycling.py: three recycled solves, iteration counts as the reference"""
     import ritz_checks
     ritz_checks.check_recycling(sname, which)
+
+
+@pytest.mark.parametrize("graphs", ["on", "off"])
+def test_restarted_gmres_preconditioned_graph_replay(graphs):
+    """CUDA-graph replay of Arnoldi steps across >= 3 restart cycles with a preconditioner M (second
+    basis P, scratch vector): the recorded graphs must find the same buffers in every cycle
+    (round-1 advisor finding: P and the scratch were re-allocated per cycle)."""
+    import krypy_b200 as kp
+    from krypy_b200 import problems
+    from oracle import krylov_oracle as ko
+    import scipy.sparse as sp
+    n = 24
+    A = problems.laplace2d(n)
+    rng = np.random.default_rng(3)
+    dM = sp.diags(1.0 / (4.0 + rng.random(n * n))).tocsr()
+    b = rng.standard_normal((n * n, 1))
+    ls = kp.linsys.LinearSystem(A, b, M=dM)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            sol = kp.linsys.RestartedGmres(ls, maxiter=8, max_restarts=4, tol=1e-14, ortho="cgs",
+                                           _workspace=kp.utils.SolverWorkspace(graphs=graphs))
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+        try:
+            ref = ko.restarted_gmres(ko.System(A, b, M=dM), maxiter=8, max_restarts=4, tol=1e-14)
+        except ko.OracleConvergenceError as e:
+            ref = e.result
+    _check_history(np.array(sol.resnorms), np.array(ref.resnorms))
