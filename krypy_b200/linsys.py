@@ -71,6 +71,59 @@ class _LazyVec(object):
             obj.__dict__[self.dev] = None
 
 
+class _LazyBasis(object):
+    """Descriptor for the ``V`` / ``P`` attributes of a solve with ``store_arnoldi=True``: the basis
+    stays in HBM (vector-major) and the reference's ``(N, k)`` numpy array is materialised on first
+    access.  The reference builds these arrays eagerly (linsys.py:694-696, 860-862, 1003-1006); at
+    N = 4M, k = 61 that is a 2 GB device-to-host copy plus a transpose that the recycling
+    work-flow (deflation.Ritz, the factories) never looks at -- it reads the device basis."""
+
+    def __init__(self, name, fallback=None):
+        self.name = name
+        self.fallback = fallback
+
+    def __get__(self, obj, objtype=None):
+        if obj is None:
+            return self
+        d = obj.__dict__
+        v = d.get("_%s_np" % self.name)
+        if v is not None:
+            return v
+        thunk = d.get("_%s_thunk" % self.name)
+        if thunk is not None:
+            v = d["_%s_np" % self.name] = thunk()
+            d["_%s_thunk" % self.name] = None
+            return v
+        if self.fallback is not None:
+            return self.fallback(obj)
+        raise AttributeError(self.name)
+
+    def __set__(self, obj, value):
+        if callable(value) and not hasattr(value, "shape"):
+            obj.__dict__["_%s_thunk" % self.name] = value
+            obj.__dict__["_%s_np" % self.name] = None
+        else:
+            obj.__dict__["_%s_np" % self.name] = value
+            obj.__dict__["_%s_thunk" % self.name] = None
+
+
+def _store_arnoldi_lazily(solver, ar, with_P):
+    """V, H[, P] of ``Arnoldi.get()`` (utils.py:1050-1061) with the N-sized parts deferred"""
+    k = ar.iter
+    ncols = k if ar.invariant else k + 1
+    ctx = _ctx()
+    solver.H = ar.H[:k, :k] if ar.invariant else ar.H[: k + 1, :k]
+    solver.V = lambda: ctx.to_numpy(ar._Vd[:ncols]).astype(ar.dtype, copy=False)
+    if with_P:
+        solver.P = lambda: ctx.to_numpy(ar._Pd[:ncols]).astype(ar.dtype, copy=False)
+    if getattr(ar, "_ws", None) is not None:
+        # restart cycles share their basis buffers through the workspace: the next cycle overwrites
+        # them, so this cycle's arrays are taken now
+        solver.V
+        if with_P:
+            solver.P
+
+
 class LinearSystem(object):
     """krypy/linsys.py:11-201.  ``dtype`` (new, optional): storage/compute dtype
     of the device path; the default follows the reference's promotion rule
@@ -450,6 +503,8 @@ class Cg(_KrylovSolver):
 
     Mlrk = _LazyVec("Mlrk")
     MMlrk = _LazyVec("MMlrk")
+    V = _LazyBasis("V")
+    P = _LazyBasis("P")
 
     def _apply_op_dot(self, p, Ap, pAp):
         """Ap = MlAMr p and pAp[0] = <p, Ap>_B (linsys.py:631-634)."""
@@ -556,9 +611,10 @@ class Cg(_KrylovSolver):
         """krypy/linsys.py:691-696."""
         if self.store_arnoldi:
             ctx = self._ctx
-            self.V = ctx.to_numpy(self._Vd[: self.iter + 1]).astype(self.dtype, copy=False)
+            nc = self.iter + 1
+            self.V = lambda: ctx.to_numpy(self._Vd[:nc]).astype(self.dtype, copy=False)
             if self._Pd is not None:
-                self.P = ctx.to_numpy(self._Pd[: self.iter + 1]).astype(self.dtype, copy=False)
+                self.P = lambda: ctx.to_numpy(self._Pd[:nc]).astype(self.dtype, copy=False)
             self.H = self.H[: self.iter + 1, : self.iter]
 
     @staticmethod
@@ -584,6 +640,9 @@ class Minres(_KrylovSolver):
 
     def __repr__(self):
         return self._repr("MINRES")
+
+    V = _LazyBasis("V")
+    P = _LazyBasis("P")
 
     def _solve(self):
         """krypy/linsys.py:791-853."""
@@ -631,10 +690,8 @@ class Minres(_KrylovSolver):
     def _finalize(self):
         """krypy/linsys.py:855-862."""
         if self.store_arnoldi:
-            if not isinstance(self.linear_system.M, utils.IdentityLinearOperator):
-                self.V, self.H, self.P = self.lanczos.get()
-            else:
-                self.V, self.H = self.lanczos.get()
+            _store_arnoldi_lazily(self, self.lanczos,
+                                  not isinstance(self.linear_system.M, utils.IdentityLinearOperator))
 
     @staticmethod
     def operations(nsteps):
@@ -664,16 +721,9 @@ class Gmres(_KrylovSolver):
         return self._repr("GMRES", ["    R: {} x {} matrix\n".format(*self.R.shape),
                                     "    V: {} x {} matrix\n".format(*self.V.shape)])
 
-    @property
-    def V(self):
-        v = self.__dict__.get("_V_final")
-        if v is not None:
-            return v
-        return self.arnoldi.V
-
-    @V.setter
-    def V(self, value):
-        self.__dict__["_V_final"] = value
+    # without store_arnoldi, V aliases the Arnoldi object's full-width basis (linsys.py:981)
+    V = _LazyBasis("V", fallback=lambda self: self.arnoldi.V)
+    P = _LazyBasis("P")
 
     def _get_xk(self, y):
         """krypy/linsys.py:941-949: y is a device vector holding y[:k] (or None)."""
@@ -820,10 +870,8 @@ class Gmres(_KrylovSolver):
     def _finalize(self):
         """krypy/linsys.py:999-1006."""
         if self.store_arnoldi:
-            if not isinstance(self.linear_system.M, utils.IdentityLinearOperator):
-                self.V, self.H, self.P = self.arnoldi.get()
-            else:
-                self.V, self.H = self.arnoldi.get()
+            _store_arnoldi_lazily(self, self.arnoldi,
+                                  not isinstance(self.linear_system.M, utils.IdentityLinearOperator))
 
     @staticmethod
     def operations(nsteps):

@@ -14,11 +14,19 @@ import types
 REFERENCE_ROOT = os.environ.get("KRYPY_REFERENCE_ROOT", "/root/reference")
 
 
+VENDORED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
 def available():
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "krypy"))
 
 
-def import_reference():
+def vendored_available():
+    """the unmodified reference installed by pip into baseline/_ref (travels to the GPU box)"""
+    return os.path.isdir(os.path.join(VENDORED_ROOT, "krypy"))
+
+
+def import_reference(root=None):
     import numpy
     import scipy.sparse
     import scipy.sparse._sputils as _sputils
@@ -40,8 +48,9 @@ def import_reference():
         sys.modules["scipy.sparse.sputils"] = sputils
         scipy.sparse.sputils = sputils
     sputils.isintlike = _sputils.isintlike
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    root = REFERENCE_ROOT if root is None else root
+    if root not in sys.path:
+        sys.path.insert(0, root)
     import krypy
 
     return krypy
