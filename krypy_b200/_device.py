@@ -166,6 +166,7 @@ class Context(object):
         host = lib.kry_mailbox_host(h)
         self.mailbox = np.ctypeslib.as_array(
             ctypes.cast(host, ctypes.POINTER(ctypes.c_double)), shape=(_lib.KRY_MAILBOX_DOUBLES,))
+        self.mailbox_dev = int(lib.kry_mailbox_dev(h))      # device alias of the mapped mailbox
         info = (ctypes.c_longlong * 8)()
         check(lib.kry_device_info(h, info))
         self.sm_count, self.cc, self.l2_bytes = int(info[0]), int(info[1]), int(info[2])

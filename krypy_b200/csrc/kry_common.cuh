@@ -163,6 +163,8 @@ __device__ __forceinline__ unsigned long long dglobal_timer_ns() {
     return t;
 }
 
+__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
+
 // the calling CTA stores vals[0..n) into every rank's slot row for `epoch` and releases the flag
 __device__ __forceinline__ void peer_publish(const PeerArgs& pa, unsigned long long epoch, const double* vals_smem,
                                              int n) {
@@ -204,5 +206,23 @@ __device__ __forceinline__ double peer_sum(const PeerArgs& pa, unsigned long lon
     return s;
 }
 
-__device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
-
+// Row-partitioned run: turn the local sums c_s[0..cnt) (identical in every CTA) into global sums.
+// CTA 0 stores them into every peer's slot array and releases its flag; every CTA acquires all
+// flags and sums the per-rank partials in rank order (bitwise identical on all ranks).
+__device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned long long epoch, double* c_s, int cnt,
+                                              double* stage, int* okflag) {
+    if (blockIdx.x == 0) peer_publish(pa, epoch, c_s, cnt);
+    const bool ok = peer_wait(pa, epoch, okflag);
+    const double* mine = pa.slots[pa.rank] + (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
+    for (int idx = threadIdx.x; idx < pa.world * cnt; idx += blockDim.x) {
+        const int r = idx / cnt, j = idx - r * cnt;
+        stage[r * PEER_SLOT + j] = dld_volatile_f64(mine + (size_t)r * PEER_SLOT + j);
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
+        double sum = 0.0;
+        for (int r = 0; r < pa.world; ++r) sum += stage[r * PEER_SLOT + j];
+        c_s[j] = ok ? sum : nan_f64();
+    }
+    __syncthreads();
+}

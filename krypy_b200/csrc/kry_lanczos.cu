@@ -8,9 +8,9 @@
 //
 // as ONE cooperative kernel (two grid-wide reductions) instead of the seven launches of the
 // generic-inner-product path (axpy, diag_mul, block_dot, axpy, diag_mul, block_dot, scale): 11
-// instead of 21 vector passes.  Opt-in measurement variant (KRY_LANCZOS_DIAGB=1 in the host layer):
-// written after this round's GPU budget was spent; a separate translation unit, so the device code
-// of the validated kernels is untouched (tools/sass_identity.py).
+// instead of 21 vector passes.  Default for a diagonal ip_B since round 2 (KRY_LANCZOS_DIAGB=0 in the
+// host layer selects the generic sequence).  Row-partitioned runs (kry_lanczos_diag_dist) complete
+// both reductions over NVLink peer memory inside the kernel.
 //
 // Rounding mirrors the unfused path: b*q is rounded to the storage type before it enters the dot
 // (kry_diag_mul stores B q), q is used as stored.  Reductions are deterministic for a fixed grid.
@@ -33,6 +33,7 @@ struct LanczosArgs {
     double* h3;              // [H[k-1,k], H[k,k] (+=), H[k+1,k]] (device), as kry_minres_recur reads it
     T* vnext;                // v_{k+1}
     double* partials;        // [2][KRY_MAX_SLOTS][KRY_MAX_PARTIAL_BLOCKS] scratch of the context
+    PeerArgs peer;           // world == 1: single GPU; otherwise both reductions are completed over NVLink
 };
 
 __device__ __forceinline__ double* lz_slot(double* partials, int buf) {
@@ -47,10 +48,14 @@ __device__ __forceinline__ double lz_reduce(double* partials, int buf, double* s
     return kry_block_sum(v, sm);
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool PEER>
 __global__ void __launch_bounds__(KRY_THREADS, 4) lanczos_diag_kernel(LanczosArgs<T> a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[32];
+    __shared__ double c_s[2];
+    __shared__ double stage[PEER ? PEER_MAX_RANKS * PEER_SLOT : 1];
+    __shared__ int okflag;
+    unsigned long long epoch = PEER ? dld_volatile_u64(a.peer.epoch_dev) : 0ull;
     const long long n = a.n;
     const long long nvec = n / VEC;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -96,7 +101,15 @@ __global__ void __launch_bounds__(KRY_THREADS, 4) lanczos_diag_kernel(LanczosArg
         if (threadIdx.x == 0) lz_slot(a.partials, 0)[blockIdx.x] = s;
     }
     grid.sync();
-    const double alpha = lz_reduce(a.partials, 0, sm);
+    double alpha = lz_reduce(a.partials, 0, sm);
+    if (PEER) {   // local sum (identical in every CTA) -> global sum in rank order
+        __syncthreads();
+        if (threadIdx.x == 0) c_s[0] = alpha;
+        __syncthreads();
+        peer_exchange(a.peer, ++epoch, c_s, 1, stage, &okflag);
+        alpha = c_s[0];
+        __syncthreads();
+    }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.h3[1] += alpha;
 
     // ---- phase B: q -= alpha v_k, beta^2 = <q, B q> ----
@@ -128,7 +141,16 @@ __global__ void __launch_bounds__(KRY_THREADS, 4) lanczos_diag_kernel(LanczosArg
         if (threadIdx.x == 0) lz_slot(a.partials, 1)[blockIdx.x] = s;
     }
     grid.sync();
-    const double beta = sqrt(fabs(lz_reduce(a.partials, 1, sm)));      // sqrt(|ip|), utils.py:238
+    double beta2 = lz_reduce(a.partials, 1, sm);
+    if (PEER) {
+        __syncthreads();
+        if (threadIdx.x == 0) c_s[0] = beta2;
+        __syncthreads();
+        peer_exchange(a.peer, ++epoch, c_s, 1, stage, &okflag);
+        beta2 = c_s[0];
+        __syncthreads();
+    }
+    const double beta = sqrt(fabs(beta2));      // sqrt(|ip|), utils.py:238
     if (blockIdx.x == 0 && threadIdx.x == 0) a.h3[2] = beta;
 
     // ---- phase C: v_{k+1} = q / beta ----
@@ -144,6 +166,11 @@ __global__ void __launch_bounds__(KRY_THREADS, 4) lanczos_diag_kernel(LanczosArg
             for (long long i = tail0; i < n; i += blockDim.x)
                 a.vnext[i] = (T)(beta > 0.0 ? (double)q[i] / beta : 0.0);
     }
+    if (PEER) {
+        // every CTA read epoch_dev before the first grid.sync: order the write-back after those reads
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) *a.peer.epoch_dev = epoch;
+    }
 }
 
 template <typename T>
@@ -153,10 +180,12 @@ static int lanczos_launch(kry_ctx* ctx, LanczosArgs<T>& a) {
                     (!a.vprev || kry_aligned16(a.vprev)) && (!a.vnext || kry_aligned16(a.vnext));
     static int blocks_per_sm[2] = {0, 0};
     const int which = al ? 0 : 1;
+    const bool peer = a.peer.world > 1;
     if (blocks_per_sm[which] == 0) {
+        // (the PEER instantiation needs more shared memory: size the grid for it, it fits both)
         int nb = 0;
-        if (al) KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lanczos_diag_kernel<T, W>, KRY_THREADS, 0));
-        else KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lanczos_diag_kernel<T, 1>, KRY_THREADS, 0));
+        if (al) KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lanczos_diag_kernel<T, W, true>, KRY_THREADS, 0));
+        else KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, lanczos_diag_kernel<T, 1, true>, KRY_THREADS, 0));
         KRY_REQUIRE(nb >= 1, "lanczos kernel does not fit");
         blocks_per_sm[which] = nb;
     }
@@ -166,7 +195,8 @@ static int lanczos_launch(kry_ctx* ctx, LanczosArgs<T>& a) {
     if (cap > KRY_MAX_PARTIAL_BLOCKS) cap = KRY_MAX_PARTIAL_BLOCKS;
     const int g = (int)(need < cap ? need : cap);
     void* args[] = {&a};
-    void* k = al ? (void*)lanczos_diag_kernel<T, W> : (void*)lanczos_diag_kernel<T, 1>;
+    void* k = peer ? (al ? (void*)lanczos_diag_kernel<T, W, true> : (void*)lanczos_diag_kernel<T, 1, true>)
+                   : (al ? (void*)lanczos_diag_kernel<T, W, false> : (void*)lanczos_diag_kernel<T, 1, false>);
     KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
     KRY_LAUNCHED(ctx);
     return KRY_OK;
@@ -174,23 +204,46 @@ static int lanczos_launch(kry_ctx* ctx, LanczosArgs<T>& a) {
 
 extern "C" {
 
-int kry_lanczos_diag(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk, const void* bdiag,
-                     void* q, const double* pre_coef_dev, double* h3_dev, void* vnext) {
+static int lanczos_impl(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk, const void* bdiag,
+                        void* q, const double* pre_coef_dev, double* h3_dev, void* vnext, PeerArgs peer) {
     KRY_ENTER(ctx);
     KRY_REQUIRE(n >= 0 && vk && bdiag && q && h3_dev, "bad arguments");
     KRY_REQUIRE(!vprev || pre_coef_dev, "vprev without pre_coef_dev");
     if (dtype == KRY_F64) {
         LanczosArgs<double> a = {n, (const double*)vprev, (const double*)vk, (const double*)bdiag, (double*)q,
-                                 pre_coef_dev, h3_dev, (double*)vnext, ctx->d_partials};
+                                 pre_coef_dev, h3_dev, (double*)vnext, ctx->d_partials, peer};
         return lanczos_launch<double>(ctx, a);
     }
     if (dtype == KRY_F32) {
         LanczosArgs<float> a = {n, (const float*)vprev, (const float*)vk, (const float*)bdiag, (float*)q,
-                                pre_coef_dev, h3_dev, (float*)vnext, ctx->d_partials};
+                                pre_coef_dev, h3_dev, (float*)vnext, ctx->d_partials, peer};
         return lanczos_launch<float>(ctx, a);
     }
     kry_set_error("kry_lanczos_diag: unsupported dtype %d", dtype);
     return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_lanczos_diag(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk, const void* bdiag,
+                     void* q, const double* pre_coef_dev, double* h3_dev, void* vnext) {
+    PeerArgs peer;
+    memset(&peer, 0, sizeof(peer));
+    peer.world = 1;
+    return lanczos_impl(ctx, dtype, n, vprev, vk, bdiag, q, pre_coef_dev, h3_dev, vnext, peer);
+}
+
+int kry_lanczos_diag_dist(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk, const void* bdiag,
+                          void* q, const double* pre_coef_dev, double* h3_dev, void* vnext, int world, int rank,
+                          unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                          unsigned long long* const* peer_flags_dev) {
+    KRY_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "bad world/rank");
+    KRY_REQUIRE(epoch_dev && peer_slots_dev && peer_flags_dev, "NULL peer argument");
+    PeerArgs peer;
+    peer.world = world;
+    peer.rank = rank;
+    peer.epoch_dev = epoch_dev;
+    peer.slots = peer_slots_dev;
+    peer.flags = peer_flags_dev;
+    return lanczos_impl(ctx, dtype, n, vprev, vk, bdiag, q, pre_coef_dev, h3_dev, vnext, peer);
 }
 
 }  // extern "C"

@@ -10,7 +10,6 @@
 // map), so the only grid-wide dependencies are the reductions themselves.
 // Reductions are deterministic for a fixed grid size.
 #include "kry_common.cuh"
-#include <stdlib.h>
 
 #define KRY_ENTER(ctx)                                                         \
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
@@ -63,48 +62,379 @@ __device__ __forceinline__ void reduce_slots(double* partials, int buf, int cnt,
     __syncthreads();
 }
 
-// Row-partitioned run: turn the local sums c_s[0..cnt) (identical in every CTA) into global sums.
-// CTA 0 stores them into every peer's slot array and releases its flag; every CTA acquires all
-// flags and sums the per-rank partials in rank order (bitwise identical on all ranks).
-__device__ __forceinline__ void peer_exchange(const PeerArgs& pa, unsigned long long epoch, double* c_s, int cnt,
-                                              double* stage, int* okflag) {
-    if (blockIdx.x == 0) peer_publish(pa, epoch, c_s, cnt);
-    const bool ok = peer_wait(pa, epoch, okflag);
-    const double* mine = pa.slots[pa.rank] + (size_t)(epoch & 1ull) * (size_t)pa.world * PEER_SLOT;
-    for (int idx = threadIdx.x; idx < pa.world * cnt; idx += blockDim.x) {
-        const int r = idx / cnt, j = idx - r * cnt;
-        stage[r * PEER_SLOT + j] = dld_volatile_f64(mine + (size_t)r * PEER_SLOT + j);
+// ---------------------------------------------------------------------------
+// Sweep building blocks.  Every thread owns the same elements (grid-stride map over 16-byte
+// packs) in every phase.  The loops are specialised on the EXACT number of basis vectors they
+// touch (no clamped duplicate loads for remainder tiles) and unrolled over the grid stride (U)
+// when only a few vectors are involved, so that every thread keeps >= 8 independent 16-byte
+// loads in flight: with 2 CTAs/SM x 256 threads that is what it takes to cover the HBM latency
+// (measured: 2 loads in flight per thread = 45 % of the copy bandwidth at nv = 1).
+// ---------------------------------------------------------------------------
+__host__ __device__ constexpr int orth_unroll(int nt) { return nt <= 1 ? 4 : (nt == 2 ? 3 : (nt <= 4 ? 2 : 1)); }
+
+// CTA reduction of NT accumulators with ONE barrier pair; per-CTA partials to slots [slot0, slot0+NT)
+template <int NT>
+__device__ __forceinline__ void reduce_store(double (&acc)[NT], double* red /*[16*8]*/, double* partials, int buf,
+                                             int slot0) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = kry_warp_sum(acc[t]);
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) red[t * 8 + w] = acc[t];
     }
     __syncthreads();
-    for (int j = threadIdx.x; j < cnt; j += blockDim.x) {
-        double sum = 0.0;
-        for (int r = 0; r < pa.world; ++r) sum += stage[r * PEER_SLOT + j];
-        c_s[j] = ok ? sum : nan_f64();
+    if (threadIdx.x < NT) {
+        double s = 0.0;
+        for (int ww = 0; ww < nw; ++ww) s += red[threadIdx.x * 8 + ww];     // fixed warp order
+        partial_slot(partials, buf, slot0 + threadIdx.x)[blockIdx.x] = s;
     }
-    __syncthreads();
 }
 
-// JT: basis vectors per register tile.  JT = 16 (128 registers, 2 CTAs/SM) is sized for the long
-// sweeps of GMRES(30); the JT = 4 instantiation (<= 64 registers, 4 CTAs/SM, phase C unrolled by
-// hand) keeps more loads in flight when only a few vectors are involved -- small k, Lanczos, exact
-// MGS.  It is an opt-in measurement variant (KRY_ORTH_SMALLK=1): the JT = 16 code is unchanged.
-// CU: phase C (the normalised store) unrolled by hand, four loads in flight per thread.  Always on
-// for JT = 4; KRY_ORTH_CUNROLL=1 selects it for the JT = 16 kernel as a second measurement variant.
-template <typename T, int VEC, bool PEER, int JT = 16, bool CU = (JT < 16)>
-__global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(OrthArgs<T> a) {
-    constexpr int TB = JT < 8 ? JT : 8;     // vectors loaded per inner tile
+// acc[t] += <V[t], q> over this thread's elements, t < NT (1 <= NT <= 16), one pass over q
+template <typename T, int VEC, int NT>
+__device__ __forceinline__ void dots_pass(const T* __restrict__ V, long long ldv, const T* q, long long n,
+                                          double* red, double* partials, int buf, int slot0) {
+    constexpr int U = orth_unroll(NT);
+    constexpr int B0 = NT < 8 ? NT : 8, B1 = NT - B0;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[NT];
+#pragma unroll
+    for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+    if (U > 1) {
+        for (; i + (U - 1) * stride < nvec; i += U * stride) {
+            double qv[U][VEC], vv[U][B0][VEC];
+#pragma unroll
+            for (int r = 0; r < U; ++r) {
+                VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+#pragma unroll
+                for (int t = 0; t < B0; ++t) VecIO<T, VEC>::load(V + (long long)t * ldv, i + r * stride, vv[r][t]);
+            }
+#pragma unroll
+            for (int r = 0; r < U; ++r)
+#pragma unroll
+                for (int t = 0; t < B0; ++t)
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) acc[t] = fma(vv[r][t][u], qv[r][u], acc[t]);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+        {
+            double vv[B0][VEC];
+#pragma unroll
+            for (int t = 0; t < B0; ++t) VecIO<T, VEC>::load(V + (long long)t * ldv, i, vv[t]);
+#pragma unroll
+            for (int t = 0; t < B0; ++t)
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) acc[t] = fma(vv[t][u], qv[u], acc[t]);
+        }
+        if (B1 > 0) {
+            double vv[B1 > 0 ? B1 : 1][VEC];
+#pragma unroll
+            for (int t = 0; t < B1; ++t) VecIO<T, VEC>::load(V + (long long)(B0 + t) * ldv, i, vv[t]);
+#pragma unroll
+            for (int t = 0; t < B1; ++t)
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) acc[B0 + t] = fma(vv[t][u], qv[u], acc[B0 + t]);
+        }
+    }
+    if (blockIdx.x == 0) {   // scalar tail
+        for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) {
+            const double qe = (double)q[e];
+#pragma unroll
+            for (int t = 0; t < NT; ++t) acc[t] = fma((double)V[(long long)t * ldv + e], qe, acc[t]);
+        }
+    }
+    reduce_store<NT>(acc, red, partials, buf, slot0);
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void dots_dispatch(int nt, const T* V, long long ldv, const T* q, long long n, double* red,
+                                              double* partials, int buf, int slot0) {
+    switch (nt) {
+#define KRY_DOTS_CASE(NT) case NT: dots_pass<T, VEC, NT>(V, ldv, q, n, red, partials, buf, slot0); break;
+        KRY_DOTS_CASE(1) KRY_DOTS_CASE(2) KRY_DOTS_CASE(3) KRY_DOTS_CASE(4) KRY_DOTS_CASE(5) KRY_DOTS_CASE(6)
+        KRY_DOTS_CASE(7) KRY_DOTS_CASE(8) KRY_DOTS_CASE(9) KRY_DOTS_CASE(10) KRY_DOTS_CASE(11) KRY_DOTS_CASE(12)
+        KRY_DOTS_CASE(13) KRY_DOTS_CASE(14) KRY_DOTS_CASE(15) KRY_DOTS_CASE(16)
+#undef KRY_DOTS_CASE
+        default: break;
+    }
+}
+
+// one element pack: q -= sum_j c[j] V[j] over full blocks of 8 and an exact remainder block of R vectors.
+// FORM_FIRST: accumulate Pa = sum_j c[j] V[j] first and subtract once (the projector's rounding,
+// krypy/utils.py:549, 621) instead of updating q vector by vector (Gram-Schmidt's).
+template <typename T, int VEC, int R, bool FORM_FIRST>
+__device__ __forceinline__ void update_pack(const T* __restrict__ V, long long ldv, int nfull, const double* c_s,
+                                            long long i, double (&qv)[VEC]) {
+    double pa[VEC];
+#pragma unroll
+    for (int u = 0; u < VEC; ++u) pa[u] = 0.0;
+    for (int jb = 0; jb < nfull; jb += 8) {
+        double vv[8][VEC];
+#pragma unroll
+        for (int t = 0; t < 8; ++t) VecIO<T, VEC>::load(V + (long long)(jb + t) * ldv, i, vv[t]);
+#pragma unroll
+        for (int t = 0; t < 8; ++t) {
+            const double c = c_s[jb + t];
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                if (FORM_FIRST) pa[u] = fma(c, vv[t][u], pa[u]);
+                else qv[u] = fma(-c, vv[t][u], qv[u]);
+            }
+        }
+    }
+    if (R > 0) {
+        double vv[R > 0 ? R : 1][VEC];
+#pragma unroll
+        for (int t = 0; t < R; ++t) VecIO<T, VEC>::load(V + (long long)(nfull + t) * ldv, i, vv[t]);
+#pragma unroll
+        for (int t = 0; t < R; ++t) {
+            const double c = c_s[nfull + t];
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                if (FORM_FIRST) pa[u] = fma(c, vv[t][u], pa[u]);
+                else qv[u] = fma(-c, vv[t][u], qv[u]);
+            }
+        }
+    }
+    if (FORM_FIRST) {
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] -= pa[u];
+    }
+}
+
+// q -= V c for cnt vectors (cnt = nfull + R, nfull a multiple of 8, 0 <= R < 8); returns this thread's
+// share of ||q||^2 (of the values as stored) when want_nrm
+template <typename T, int VEC, int R, bool FORM_FIRST>
+__device__ __forceinline__ double update_pass(const T* __restrict__ V, long long ldv, int cnt, const double* c_s, T* q,
+                                              long long n, bool want_nrm) {
+    const int nfull = cnt - R;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double nrm2 = 0.0;
+    // few vectors: unroll over the stride to keep enough loads in flight
+    constexpr int U = (R >= 1 && R <= 4) ? orth_unroll(R) : 1;
+    if (U > 1 && nfull == 0) {
+        for (; i + (U - 1) * stride < nvec; i += U * stride) {
+            double qv[U][VEC], vv[U][R > 0 ? R : 1][VEC];
+#pragma unroll
+            for (int r = 0; r < U; ++r) {
+                VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+#pragma unroll
+                for (int t = 0; t < R; ++t) VecIO<T, VEC>::load(V + (long long)t * ldv, i + r * stride, vv[r][t]);
+            }
+#pragma unroll
+            for (int r = 0; r < U; ++r) {
+                double pa[VEC];
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) pa[u] = 0.0;
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const double c = c_s[t];
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) {
+                        if (FORM_FIRST) pa[u] = fma(c, vv[r][t][u], pa[u]);
+                        else qv[r][u] = fma(-c, vv[r][t][u], qv[r][u]);
+                    }
+                }
+                if (FORM_FIRST) {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) qv[r][u] -= pa[u];
+                }
+                VecIO<T, VEC>::store(q, i + r * stride, qv[r]);
+                if (want_nrm) {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) {
+                        const double v = round_as<T>(qv[r][u]);
+                        nrm2 = fma(v, v, nrm2);
+                    }
+                }
+            }
+        }
+    }
+    for (; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+        update_pack<T, VEC, R, FORM_FIRST>(V, ldv, nfull, c_s, i, qv);
+        VecIO<T, VEC>::store(q, i, qv);
+        if (want_nrm) {
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) {
+                const double v = round_as<T>(qv[u]);
+                nrm2 = fma(v, v, nrm2);
+            }
+        }
+    }
+    if (blockIdx.x == 0) {   // scalar tail
+        for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) {
+            double qe = (double)q[e];
+            if (FORM_FIRST) {
+                double pa = 0.0;
+                for (int j = 0; j < cnt; ++j) pa = fma(c_s[j], (double)V[(long long)j * ldv + e], pa);
+                qe -= pa;
+            } else {
+                for (int j = 0; j < cnt; ++j) qe = fma(-c_s[j], (double)V[(long long)j * ldv + e], qe);
+            }
+            q[e] = (T)qe;
+            qe = (double)q[e];
+            if (want_nrm) nrm2 = fma(qe, qe, nrm2);
+        }
+    }
+    return nrm2;
+}
+
+template <typename T, int VEC, bool FORM_FIRST>
+__device__ __forceinline__ double update_dispatch(const T* V, long long ldv, int cnt, const double* c_s, T* q,
+                                                  long long n, bool want_nrm) {
+    switch (cnt & 7) {
+        case 1: return update_pass<T, VEC, 1, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        case 2: return update_pass<T, VEC, 2, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        case 3: return update_pass<T, VEC, 3, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        case 4: return update_pass<T, VEC, 4, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        case 5: return update_pass<T, VEC, 5, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        case 6: return update_pass<T, VEC, 6, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        case 7: return update_pass<T, VEC, 7, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+        default: return update_pass<T, VEC, 0, FORM_FIRST>(V, ldv, cnt, c_s, q, n, want_nrm);
+    }
+}
+
+// vnext = q / nrm (0 when nrm == 0), four loads in flight per thread
+template <typename T, int VEC>
+__device__ __forceinline__ void scale_pass(const T* q, T* vnext, long long n, double nrm) {
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + 3 * stride < nvec; i += 4 * stride) {
+        double qv[4][VEC];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) qv[r][u] = nrm > 0.0 ? qv[r][u] / nrm : 0.0;
+            VecIO<T, VEC>::store(vnext, i + r * stride, qv[r]);
+        }
+    }
+    for (; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) qv[u] = nrm > 0.0 ? qv[u] / nrm : 0.0;
+        VecIO<T, VEC>::store(vnext, i, qv);
+    }
+    if (blockIdx.x == 0)
+        for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x)
+            vnext[e] = (T)(nrm > 0.0 ? (double)q[e] / nrm : 0.0);
+}
+
+// One sweep of exact modified Gram-Schmidt: q -= pre_c*pre (optional), q -= c_prev*vp (optional, the
+// pending update of the previous vector), store q if modified, return this thread's share of
+// <vj, q> (vj == nullptr: of ||q||^2 when want_nrm, else 0).  Unrolled 2x over the stride.
+template <typename T, int VEC>
+__device__ __forceinline__ double mgs_pass(const T* __restrict__ vj, const T* __restrict__ vp, double c_prev,
+                                           const T* __restrict__ pre, double pre_c, T* q, long long n, bool want_nrm) {
+    constexpr int U = 2;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool modify = (vp != nullptr) || (pre != nullptr);
+    double acc = 0.0;
+    for (; i + (U - 1) * stride < nvec; i += U * stride) {
+        double qv[U][VEC], vv[U][VEC], pv[U][VEC], wv[U][VEC];
+#pragma unroll
+        for (int r = 0; r < U; ++r) {
+            VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+            if (vj) VecIO<T, VEC>::load(vj, i + r * stride, vv[r]);
+            if (pre) VecIO<T, VEC>::load(pre, i + r * stride, wv[r]);
+            if (vp) VecIO<T, VEC>::load(vp, i + r * stride, pv[r]);
+        }
+#pragma unroll
+        for (int r = 0; r < U; ++r) {
+            if (pre) {
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) qv[r][u] = fma(-pre_c, wv[r][u], qv[r][u]);
+            }
+            if (vp) {
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) qv[r][u] = fma(-c_prev, pv[r][u], qv[r][u]);
+            }
+            if (modify) {
+                VecIO<T, VEC>::store(q, i + r * stride, qv[r]);
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) qv[r][u] = round_as<T>(qv[r][u]);
+            }
+            if (vj) {
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) acc = fma(vv[r][u], qv[r][u], acc);
+            } else if (want_nrm) {
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) acc = fma(qv[r][u], qv[r][u], acc);
+            }
+        }
+    }
+    for (; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+        if (pre) {
+            double wv[VEC];
+            VecIO<T, VEC>::load(pre, i, wv);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, wv[u], qv[u]);
+        }
+        if (vp) {
+            double pv[VEC];
+            VecIO<T, VEC>::load(vp, i, pv);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) qv[u] = fma(-c_prev, pv[u], qv[u]);
+        }
+        if (modify) {
+            VecIO<T, VEC>::store(q, i, qv);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);
+        }
+        if (vj) {
+            double vv[VEC];
+            VecIO<T, VEC>::load(vj, i, vv);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) acc = fma(vv[u], qv[u], acc);
+        } else if (want_nrm) {
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) acc = fma(qv[u], qv[u], acc);
+        }
+    }
+    if (blockIdx.x == 0) {   // scalar tail
+        for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) {
+            double qe = (double)q[e];
+            if (pre) qe = fma(-pre_c, (double)pre[e], qe);
+            if (vp) qe = fma(-c_prev, (double)vp[e], qe);
+            if (modify) {
+                q[e] = (T)qe;
+                qe = (double)q[e];
+            }
+            if (vj) acc = fma((double)vj[e], qe, acc);
+            else if (want_nrm) acc = fma(qe, qe, acc);
+        }
+    }
+    return acc;
+}
+
+template <typename T, int VEC, bool PEER>
+__global__ void __launch_bounds__(KRY_THREADS, 2) orth_kernel(OrthArgs<T> a) {
     cg::grid_group grid = cg::this_grid();
     __shared__ double sm[32];
+    __shared__ double red[ORTH_JT * 8];
     __shared__ double c_s[KRY_MAX_SLOTS];
     __shared__ double stage[PEER ? PEER_MAX_RANKS * PEER_SLOT : 1];
     __shared__ int okflag;
     unsigned long long epoch = PEER ? dld_volatile_u64(a.peer.epoch_dev) : 0ull;
     const long long n = a.n, ldv = a.ldv;
-    const long long nvec = n / VEC;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tail0 = nvec * VEC + threadIdx.x;   // scalar tail handled by CTA 0
-    const bool tail_cta = (blockIdx.x == 0);
     T* q = a.q;
     int buf = 0;
     const int cnt = a.nv - a.j0;
@@ -113,65 +443,17 @@ __global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(O
     double nrm2_part = 0.0;
 
     if (a.algo == KRY_ORTH_CGS) {
+        if (pre_pending) {
+            // (Lanczos-style pre-subtraction with the block algorithm: not used by the solvers, kept
+            // for the ABI) q -= pre_c * pre_vec as a sweep of its own
+            mgs_pass<T, VEC>(nullptr, nullptr, 0.0, a.pre_vec, pre_c, q, n, false);
+            pre_pending = false;
+        }
         for (int pass = 0; pass < a.passes; ++pass) {
-            // ---- phase A: block dots ----
-            for (int jb = 0; jb < cnt || (jb == 0 && pre_pending); jb += JT) {
-                double acc[JT];
-#pragma unroll
-                for (int t = 0; t < JT; ++t) acc[t] = 0.0;
-                for (long long i = i0; i < nvec; i += stride) {
-                    double qv[VEC];
-                    VecIO<T, VEC>::loadrw(q, i, qv);
-                    if (pre_pending) {
-                        double pv[VEC];
-                        VecIO<T, VEC>::load(a.pre_vec, i, pv);
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, pv[u], qv[u]);
-                        VecIO<T, VEC>::store(q, i, qv);
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);   // value as stored
-                    }
-                    if (cnt > 0) {
-#pragma unroll
-                        for (int tb = 0; tb < JT; tb += TB) {
-                            if (jb + tb < cnt) {
-                                double vv[TB][VEC];
-#pragma unroll
-                                for (int t = 0; t < TB; ++t) {
-                                    int j = jb + tb + t;
-                                    j = j < cnt ? j : cnt - 1;
-                                    VecIO<T, VEC>::load(a.Vdot + (long long)(a.j0 + j) * ldv, i, vv[t]);
-                                }
-#pragma unroll
-                                for (int t = 0; t < TB; ++t)
-#pragma unroll
-                                    for (int u = 0; u < VEC; ++u) acc[tb + t] = fma(vv[t][u], qv[u], acc[tb + t]);
-                            }
-                        }
-                    }
-                }
-                if (tail_cta) {
-                    for (long long i = tail0; i < n; i += blockDim.x) {
-                        double qe = (double)q[i];
-                        if (pre_pending) {
-                            qe = fma(-pre_c, (double)a.pre_vec[i], qe);
-                            q[i] = (T)qe;
-                            qe = (double)q[i];
-                        }
-#pragma unroll
-                        for (int t = 0; t < JT; ++t)
-                            if (jb + t < cnt)
-                                acc[t] = fma((double)a.Vdot[(long long)(a.j0 + jb + t) * ldv + i], qe, acc[t]);
-                    }
-                }
-                pre_pending = false;
-#pragma unroll
-                for (int t = 0; t < JT; ++t) {
-                    if (jb + t < cnt) {   // uniform across the CTA
-                        double s = kry_block_sum(acc[t], sm);
-                        if (threadIdx.x == 0) partial_slot(a.partials, buf, jb + t)[blockIdx.x] = s;
-                    }
-                }
+            // ---- phase A: block dots, up to 16 vectors per pass over q ----
+            for (int jb = 0; jb < cnt; jb += ORTH_JT) {
+                const int nt = cnt - jb < ORTH_JT ? cnt - jb : ORTH_JT;
+                dots_dispatch<T, VEC>(nt, a.Vdot + (long long)(a.j0 + jb) * ldv, ldv, q, n, red, a.partials, buf, jb);
             }
             grid.sync();
             reduce_slots(a.partials, buf, cnt, c_s);
@@ -179,93 +461,22 @@ __global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(O
             if (blockIdx.x == 0)
                 for (int s = threadIdx.x; s < cnt; s += blockDim.x) a.h[a.j0 + s] += c_s[s];
             buf ^= 1;
-            // ---- phase B: q -= Vsub c ----
+            // ---- phase B: q -= Vsub c (+ ||q||^2 in the last pass) ----
             const bool want_nrm = (a.nrm != nullptr) && (pass == a.passes - 1);
-            for (long long i = i0; i < nvec; i += stride) {
-                double qv[VEC];
-                VecIO<T, VEC>::loadrw(q, i, qv);
-                for (int jb = 0; jb < cnt; jb += TB) {
-                    double vv[TB][VEC];
-#pragma unroll
-                    for (int t = 0; t < TB; ++t) {
-                        int j = jb + t < cnt ? jb + t : cnt - 1;
-                        VecIO<T, VEC>::load(a.Vsub + (long long)(a.j0 + j) * ldv, i, vv[t]);
-                    }
-#pragma unroll
-                    for (int t = 0; t < TB; ++t)
-                        if (jb + t < cnt) {
-                            const double c = c_s[jb + t];
-#pragma unroll
-                            for (int u = 0; u < VEC; ++u) qv[u] = fma(-c, vv[t][u], qv[u]);
-                        }
-                }
-                VecIO<T, VEC>::store(q, i, qv);
-                if (want_nrm) {
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) {
-                        const double r = round_as<T>(qv[u]);
-                        nrm2_part = fma(r, r, nrm2_part);
-                    }
-                }
-            }
-            if (tail_cta) {
-                for (long long i = tail0; i < n; i += blockDim.x) {
-                    double qe = (double)q[i];
-                    for (int j = 0; j < cnt; ++j)
-                        qe = fma(-c_s[j], (double)a.Vsub[(long long)(a.j0 + j) * ldv + i], qe);
-                    q[i] = (T)qe;
-                    qe = (double)q[i];
-                    if (want_nrm) nrm2_part = fma(qe, qe, nrm2_part);
-                }
-            }
+            if (cnt > 0 || want_nrm)
+                nrm2_part = update_dispatch<T, VEC, false>(a.Vsub + (long long)a.j0 * ldv, ldv, cnt, c_s, q, n, want_nrm);
             __syncthreads();   // c_s is rewritten by the next pass
         }
     } else {
-        // ---- exact modified Gram-Schmidt: one dependent reduction per basis vector ----
+        // ---- exact modified Gram-Schmidt: one dependent reduction per basis vector; the update with
+        //      vector j-1 is fused into the sweep that computes <v_j, q> ----
         double c_prev = 0.0;
         int j_prev = -1;
         for (int pass = 0; pass < a.passes; ++pass) {
             for (int j = a.j0; j < a.nv; ++j) {
-                double acc = 0.0;
                 const T* vj = a.Vdot + (long long)j * ldv;
                 const T* vp = j_prev >= 0 ? a.Vsub + (long long)j_prev * ldv : nullptr;
-                const bool modify = (j_prev >= 0) || pre_pending;
-                for (long long i = i0; i < nvec; i += stride) {
-                    double qv[VEC], vv[VEC];
-                    VecIO<T, VEC>::loadrw(q, i, qv);
-                    VecIO<T, VEC>::load(vj, i, vv);
-                    if (pre_pending) {
-                        double pv[VEC];
-                        VecIO<T, VEC>::load(a.pre_vec, i, pv);
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, pv[u], qv[u]);
-                    }
-                    if (vp) {
-                        double pv[VEC];
-                        VecIO<T, VEC>::load(vp, i, pv);
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) qv[u] = fma(-c_prev, pv[u], qv[u]);
-                    }
-                    if (modify) {
-                        VecIO<T, VEC>::store(q, i, qv);
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);
-                    }
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) acc = fma(vv[u], qv[u], acc);
-                }
-                if (tail_cta) {
-                    for (long long i = tail0; i < n; i += blockDim.x) {
-                        double qe = (double)q[i];
-                        if (pre_pending) qe = fma(-pre_c, (double)a.pre_vec[i], qe);
-                        if (vp) qe = fma(-c_prev, (double)vp[i], qe);
-                        if (modify) {
-                            q[i] = (T)qe;
-                            qe = (double)q[i];
-                        }
-                        acc = fma((double)vj[i], qe, acc);
-                    }
-                }
+                double acc = mgs_pass<T, VEC>(vj, vp, c_prev, pre_pending ? a.pre_vec : nullptr, pre_c, q, n, false);
                 pre_pending = false;
                 double s = kry_block_sum(acc, sm);
                 if (threadIdx.x == 0) partial_slot(a.partials, buf, 0)[blockIdx.x] = s;
@@ -287,45 +498,8 @@ __global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(O
         // flush the pending subtraction (and a lone pre-subtraction when nv == j0)
         const T* vp = j_prev >= 0 ? a.Vsub + (long long)j_prev * ldv : nullptr;
         const bool want_nrm = (a.nrm != nullptr);
-        if (vp || pre_pending || want_nrm) {
-            for (long long i = i0; i < nvec; i += stride) {
-                double qv[VEC];
-                VecIO<T, VEC>::loadrw(q, i, qv);
-                if (pre_pending) {
-                    double pv[VEC];
-                    VecIO<T, VEC>::load(a.pre_vec, i, pv);
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) qv[u] = fma(-pre_c, pv[u], qv[u]);
-                }
-                if (vp) {
-                    double pv[VEC];
-                    VecIO<T, VEC>::load(vp, i, pv);
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) qv[u] = fma(-c_prev, pv[u], qv[u]);
-                }
-                if (vp || pre_pending) {
-                    VecIO<T, VEC>::store(q, i, qv);
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) qv[u] = round_as<T>(qv[u]);
-                }
-                if (want_nrm) {
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) nrm2_part = fma(qv[u], qv[u], nrm2_part);
-                }
-            }
-            if (tail_cta) {
-                for (long long i = tail0; i < n; i += blockDim.x) {
-                    double qe = (double)q[i];
-                    if (pre_pending) qe = fma(-pre_c, (double)a.pre_vec[i], qe);
-                    if (vp) qe = fma(-c_prev, (double)vp[i], qe);
-                    if (vp || pre_pending) {
-                        q[i] = (T)qe;
-                        qe = (double)q[i];
-                    }
-                    if (want_nrm) nrm2_part = fma(qe, qe, nrm2_part);
-                }
-            }
-        }
+        if (vp || pre_pending || want_nrm)
+            nrm2_part = mgs_pass<T, VEC>(nullptr, vp, c_prev, pre_pending ? a.pre_vec : nullptr, pre_c, q, n, want_nrm);
     }
 
     // ---- norm and phase C ----
@@ -343,33 +517,7 @@ __global__ void __launch_bounds__(KRY_THREADS, (JT >= 16 ? 2 : 4)) orth_kernel(O
         }
         const double nrm = sqrt(nrm2);
         if (blockIdx.x == 0 && threadIdx.x == 0) a.nrm[0] = nrm;
-        if (a.vnext != nullptr) {
-            long long i = i0;
-            if (CU) {
-                // four independent loads in flight per thread before the first store
-                for (; i + 3 * stride < nvec; i += 4 * stride) {
-                    double qv[4][VEC];
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
-#pragma unroll
-                    for (int r = 0; r < 4; ++r) {
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) qv[r][u] = nrm > 0.0 ? qv[r][u] / nrm : 0.0;
-                        VecIO<T, VEC>::store(a.vnext, i + r * stride, qv[r]);
-                    }
-                }
-            }
-            for (; i < nvec; i += stride) {
-                double qv[VEC];
-                VecIO<T, VEC>::loadrw(q, i, qv);
-#pragma unroll
-                for (int u = 0; u < VEC; ++u) qv[u] = nrm > 0.0 ? qv[u] / nrm : 0.0;
-                VecIO<T, VEC>::store(a.vnext, i, qv);
-            }
-            if (tail_cta)
-                for (long long i = tail0; i < n; i += blockDim.x)
-                    a.vnext[i] = (T)(nrm > 0.0 ? (double)q[i] / nrm : 0.0);
-        }
+        if (a.vnext != nullptr) scale_pass<T, VEC>(q, a.vnext, n, nrm);
     }
     if (PEER) {
         // every CTA read epoch_dev before the first grid.sync; one more grid-wide sync orders the
@@ -400,58 +548,17 @@ struct ProjArgs {
 template <typename T, int VEC>
 __global__ void __launch_bounds__(KRY_THREADS, 2) proj_kernel(ProjArgs<T> p) {
     cg::grid_group grid = cg::this_grid();
-    __shared__ double sm[32];
+    __shared__ double red[ORTH_JT * 8];
     __shared__ double c_s[KRY_MAX_SLOTS];
     __shared__ double t_s[KRY_MAX_SLOTS];
     const long long n = p.n;
-    const long long nvec = n / VEC;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const long long tail0 = nvec * VEC + threadIdx.x;
-    const bool tail_cta = (blockIdx.x == 0);
     const int d = p.d;
     T* av = p.a;
     int buf = 0;
     for (int iter = 0; iter < p.iterations; ++iter) {
         for (int jb = 0; jb < d; jb += ORTH_JT) {
-            double acc[ORTH_JT];
-#pragma unroll
-            for (int t = 0; t < ORTH_JT; ++t) acc[t] = 0.0;
-            for (long long i = i0; i < nvec; i += stride) {
-                double qv[VEC];
-                VecIO<T, VEC>::loadrw(av, i, qv);
-#pragma unroll
-                for (int tb = 0; tb < ORTH_JT; tb += 8) {
-                    if (jb + tb < d) {
-                        double vv[8][VEC];
-#pragma unroll
-                        for (int t = 0; t < 8; ++t) {
-                            int j = jb + tb + t;
-                            j = j < d ? j : d - 1;
-                            VecIO<T, VEC>::load(p.W + (long long)j * p.ldw, i, vv[t]);
-                        }
-#pragma unroll
-                        for (int t = 0; t < 8; ++t)
-#pragma unroll
-                            for (int u = 0; u < VEC; ++u) acc[tb + t] = fma(vv[t][u], qv[u], acc[tb + t]);
-                    }
-                }
-            }
-            if (tail_cta) {
-                for (long long i = tail0; i < n; i += blockDim.x) {
-                    const double qe = (double)av[i];
-#pragma unroll
-                    for (int t = 0; t < ORTH_JT; ++t)
-                        if (jb + t < d) acc[t] = fma((double)p.W[(long long)(jb + t) * p.ldw + i], qe, acc[t]);
-                }
-            }
-#pragma unroll
-            for (int t = 0; t < ORTH_JT; ++t) {
-                if (jb + t < d) {
-                    double s = kry_block_sum(acc[t], sm);
-                    if (threadIdx.x == 0) partial_slot(p.partials, buf, jb + t)[blockIdx.x] = s;
-                }
-            }
+            const int nt = d - jb < ORTH_JT ? d - jb : ORTH_JT;
+            dots_dispatch<T, VEC>(nt, p.W + (long long)jb * p.ldw, p.ldw, av, n, red, p.partials, buf, jb);
         }
         grid.sync();
         reduce_slots(p.partials, buf, d, c_s);
@@ -478,40 +585,8 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) proj_kernel(ProjArgs<T> p) {
             for (int i = threadIdx.x; i < d; i += blockDim.x) t_s[i] = c_s[i];
             __syncthreads();
         }
-        // a -= V x
-        for (long long i = i0; i < nvec; i += stride) {
-            double qv[VEC];
-            VecIO<T, VEC>::loadrw(av, i, qv);
-            // reference forms Pa = V.dot(x) first and then subtracts (utils.py:549, 621)
-            double pa[VEC];
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) pa[u] = 0.0;
-            for (int jb = 0; jb < d; jb += 8) {
-                double vv[8][VEC];
-#pragma unroll
-                for (int t = 0; t < 8; ++t) {
-                    int j = jb + t < d ? jb + t : d - 1;
-                    VecIO<T, VEC>::load(p.V + (long long)j * p.ldv, i, vv[t]);
-                }
-#pragma unroll
-                for (int t = 0; t < 8; ++t)
-                    if (jb + t < d) {
-                        const double c = t_s[jb + t];
-#pragma unroll
-                        for (int u = 0; u < VEC; ++u) pa[u] = fma(c, vv[t][u], pa[u]);
-                    }
-            }
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) qv[u] -= pa[u];
-            VecIO<T, VEC>::store(av, i, qv);
-        }
-        if (tail_cta) {
-            for (long long i = tail0; i < n; i += blockDim.x) {
-                double pa = 0.0;
-                for (int j = 0; j < d; ++j) pa = fma(t_s[j], (double)p.V[(long long)j * p.ldv + i], pa);
-                av[i] = (T)((double)av[i] - pa);
-            }
-        }
+        // a -= V x  (the reference forms Pa = V.dot(x) first and then subtracts, utils.py:549, 621)
+        update_dispatch<T, VEC, true>(p.V, p.ldv, d, t_s, av, n, false);
         __syncthreads();
     }
 }
@@ -562,52 +637,6 @@ static int coop_grid(long long work_items, int max_blocks) {
     return (int)(need < cap ? need : cap);
 }
 
-// KRY_ORTH_SMALLK=1 (measurement switch, default off): calls that involve few basis vectors per
-// sweep -- block CGS against <= 4 vectors, every exact-MGS / Lanczos call -- use the JT = 4
-// instantiation (higher occupancy, see orth_kernel).  Single-GPU only.
-// Value: 1 = threshold 4 (one register tile); any other n > 1 = use the variant up to n vectors
-// (q is then re-read once per 4-vector tile in the dot phase: a bandwidth-for-occupancy trade to measure).
-static int orth_smallk_threshold() {
-    static int state = -1;
-    if (state < 0) {
-        const char* e = getenv("KRY_ORTH_SMALLK");
-        int v = e ? atoi(e) : 0;
-        state = v <= 0 ? 0 : (v == 1 ? 4 : (v > KRY_MAX_SLOTS ? KRY_MAX_SLOTS : v));
-    }
-    return state;
-}
-
-static bool orth_cunroll_enabled() {
-    static int state = -1;
-    if (state < 0) {
-        const char* e = getenv("KRY_ORTH_CUNROLL");
-        state = (e && e[0] && e[0] != '0') ? 1 : 0;
-    }
-    return state == 1;
-}
-
-template <typename T>
-static int orth_launch_small(kry_ctx* ctx, OrthArgs<T>& a, bool al) {
-    const int W = VecWidth<T>::value;
-    static int blocks_per_sm[2] = {0, 0};        // [aligned, unaligned] instantiation
-    const int which = al ? 0 : 1;
-    if (blocks_per_sm[which] == 0) {
-        int nb = 0, rc;
-        if (al) rc = max_blocks_of(orth_kernel<T, W, false, 4>, &nb);
-        else rc = max_blocks_of(orth_kernel<T, 1, false, 4>, &nb);
-        if (rc) return rc;
-        KRY_REQUIRE(nb >= 1, "small-tile orth kernel does not fit");
-        blocks_per_sm[which] = nb;
-    }
-    void* args[] = {&a};
-    const int max_blocks = blocks_per_sm[which] * ctx->sm_count;
-    const int g = coop_grid(al ? a.n / W : a.n, max_blocks);
-    void* k = al ? (void*)orth_kernel<T, W, false, 4> : (void*)orth_kernel<T, 1, false, 4>;
-    KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
-    KRY_LAUNCHED(ctx);
-    return KRY_OK;
-}
-
 template <typename T>
 static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
     const int W = VecWidth<T>::value;
@@ -615,17 +644,6 @@ static int orth_launch(kry_ctx* ctx, OrthArgs<T>& a, int max_blocks) {
               (!a.pre_vec || kry_aligned16(a.pre_vec)) && (!a.vnext || kry_aligned16(a.vnext));
     void* args[] = {&a};
     const bool peer = a.peer.world > 1;
-    const int small_thr = orth_smallk_threshold();
-    if (!peer && small_thr > 0 && (a.algo == KRY_ORTH_MGS || a.nv - a.j0 <= small_thr))
-        return orth_launch_small<T>(ctx, a, al);
-    if (!peer && orth_cunroll_enabled()) {
-        // same kernel, same grid; only phase C differs
-        const int g = coop_grid(al ? a.n / W : a.n, max_blocks);
-        void* k = al ? (void*)orth_kernel<T, W, false, 16, true> : (void*)orth_kernel<T, 1, false, 16, true>;
-        KRY_CHECK_CUDA(cudaLaunchCooperativeKernel(k, dim3(g), dim3(KRY_THREADS), args, 0, ctx->stream));
-        KRY_LAUNCHED(ctx);
-        return KRY_OK;
-    }
     if (al) {
         int g = coop_grid(a.n / W, max_blocks);
         void* k = peer ? (void*)orth_kernel<T, W, true> : (void*)orth_kernel<T, W, false>;

@@ -330,7 +330,19 @@ class DistCsrOperator(utils._DeviceOperator):
         return (reg.peer_table.data_ptr(), off, hp.data_ptr(), ho.data_ptr(), pl.nhalo,
                 row.data_ptr() + pl.block * es)
 
-    def _apply_dev(self, Xd, out=None, adj=False):
+    def _alloc_vec(self, td):
+        """a (1, nloc) block whose storage is a peer-mapped extended vector: applying the operator
+        to it needs no staging copy (its halo is gathered in place)"""
+        buf = self.comm.shared_basis(1, _roundup(self._ext_len, 32), td)
+        v = buf[:, : self.plan.nloc]
+        v._keep = buf        # the region returns to the pool when `buf` is collected
+        return v
+
+    def _apply_dot_dev(self, p, Ap, pAp):
+        """Ap = A p and pAp[0] = <p, Ap> (global) with the dot in the SpMV epilogue (CG, linsys.py:631-634)"""
+        self._apply_dev(p, out=Ap, dot_out=pAp)
+
+    def _apply_dev(self, Xd, out=None, adj=False, dot_out=None):
         if adj:
             raise utils.LinearOperatorError("dot_adj undefined for a row-partitioned operator")
         comm, ctx, pl = self.comm, self.comm.ctx, self.plan
@@ -365,7 +377,10 @@ class DistCsrOperator(utils._DeviceOperator):
                     check(ctx.lib.kry_halo_gather(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(),
                                                   off, hp.data_ptr(), ho.data_ptr(), None,
                                                   xext.data_ptr() + pl.block * es))
-            ctx.spmv(A, xext, out[j])
+            if dot_out is not None:
+                ctx.spmv(A, xext, out[j], w=xext[: pl.nloc], dot_out=dot_out)   # (+ peer all-reduce of the dot)
+            else:
+                ctx.spmv(A, xext, out[j])
         return out
 
 

@@ -517,6 +517,9 @@ class Cg(_KrylovSolver):
             if isinstance(A, _device.CsrDev):
                 ctx.spmv(A, p[0], Ap[0], w=p[0], dot_out=pAp)      # fused <p,Ap> epilogue
                 return
+        if euclid and hasattr(op, "_apply_dot_dev"):
+            op._apply_dot_dev(p, Ap, pAp)     # row-partitioned: halo + SpMV with epilogue + peer all-reduce
+            return
         op._apply_dev(p, out=Ap)
         utils._ip_coef(p, Ap, ls.ip_B, pAp)
 
@@ -533,11 +536,18 @@ class Cg(_KrylovSolver):
         M_is_id = isinstance(ls.M, utils.IdentityLinearOperator)
         Mdiag = _diag_of(ls.M)
         euclid = utils._is_identity_ip(ls.ip_B)
-        # (the fused update publishes a LOCAL rho: row-partitioned runs take the general path)
-        fast = euclid and (M_is_id or Mdiag is not None) and ctx.comm is None
+        # Row-partitioned runs: the fused update publishes the LOCAL rho into the mailbox, which is
+        # then summed in place over NVLink (the mailbox is mapped pinned memory: a device address).
+        dist = ctx.comm is not None
+        fast = euclid and (M_is_id or Mdiag is not None) and (not dist or (
+            hasattr(self.MlAMr, "_apply_dot_dev") and ctx.comm.reduce == "peer"))
         z = r if M_is_id else MMlr0d.clone()       # MMlrk (aliases Mlrk when M is the identity)
         dinv = Mdiag._dev(td) if (fast and Mdiag is not None) else None
-        p = MMlr0d.clone()
+        if dist and fast:
+            p = self.MlAMr._alloc_vec(td)          # peer-mapped: its halo is read in place by the neighbours
+            p.copy_(MMlr0d)
+        else:
+            p = MMlr0d.clone()
         Ap = ctx.empty((1, N), td)
         pAp = ctx.scalars(1)
         tmp = ctx.scalars(1)
@@ -570,6 +580,8 @@ class Cg(_KrylovSolver):
             if fast:
                 ctx.cg_update(Ap[0], p[0], yk[0], r[0], z[0] if dinv is not None else None, dinv,
                               rhos[-1], pAp, 0)                            # linsys.py:655-665
+                if dist:
+                    ctx.comm.allreduce(ctx.mailbox_dev, 1)                 # rho: local -> global sum
                 ctx.sync()
                 rho_new, alpha = float(mb[0]), float(mb[1])
                 if not numpy.isfinite(rho_new) or rho_new < 0:

@@ -1455,8 +1455,10 @@ _ORTHO = {
     "cgs2": (KRY_ORTH_CGS, 2),       # new: CGS with re-orthogonalisation
 }
 _CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
-_SPLIT_SCALE = bool(__import__("os").environ.get("KRY_ORTH_SPLIT_SCALE"))   # measurement switch, default off
-_LANCZOS_DIAGB = bool(__import__("os").environ.get("KRY_LANCZOS_DIAGB"))      # measurement switch, default off
+# the fused one-kernel Lanczos step for a diagonal inner-product matrix (kry_lanczos_diag) is the
+# default since round 2 (validated on B200: +30 % on config C5); KRY_LANCZOS_DIAGB=0 selects the
+# generic seven-launch sequence
+_LANCZOS_DIAGB = __import__("os").environ.get("KRY_LANCZOS_DIAGB", "1") not in ("0", "")
 
 
 class DeviceBlock(object):
@@ -1710,12 +1712,6 @@ class Arnoldi(object):
                                    nrm=nrm if (last and fused_tail) else None,
                                    vnext=vnext if (last and fused_tail) else None, h_ptr=h_ptr)
                     j0 = j1
-            elif _SPLIT_SCALE and fused_tail and ctx.comm is None:
-                # experiment (KRY_ORTH_SPLIT_SCALE=1): the normalised store as a separate streaming
-                # kernel at full occupancy instead of phase C of the register-heavy cooperative kernel
-                ctx.orth_fused(Vt, Vsub, r0, r1, q0, self._passes, self._algo, None, nrm=nrm, vnext=None,
-                               pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr)
-                ctx.scale_dev(nrm, 1, 1.0, q0, vnext)
             else:
                 ctx.orth_fused(Vt, Vsub, r0, r1, q0, self._passes, self._algo, None,
                                nrm=nrm if fused_tail else None,
@@ -1723,8 +1719,8 @@ class Arnoldi(object):
                                pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr, halo_op=self._halo_op)
         elif (_LANCZOS_DIAGB and lanczos and not cplx and self.M is None and ctx.comm is None
               and self._passes == 1 and self._diag_ip() is not None):
-            # experiment (KRY_LANCZOS_DIAGB=1): the whole Lanczos step for a diagonal ip_B in ONE
-            # cooperative kernel instead of the seven launches of the generic path below
+            # the whole Lanczos step for a diagonal ip_B in ONE cooperative kernel instead of the seven
+            # launches of the generic path below (KRY_LANCZOS_DIAGB=0 turns it off)
             ctx.lanczos_diag(pre_vec, Vt[k], self._diag_ip(), q0, pre_coef, self._lz, vnext)
             return
         else:

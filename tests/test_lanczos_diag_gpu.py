@@ -1,19 +1,13 @@
-"""Opt-in measurement variants (default off) on the GPU: the fused Lanczos step
-for a diagonal inner-product matrix (kry_lanczos_diag, host switch KRY_LANCZOS_DIAGB) and the split
-normalised store (KRY_ORTH_SPLIT_SCALE).  The kernel-level switches KRY_ORTH_SMALLK / KRY_ORTH_CUNROLL
-are read once per process by the library: tools/gpu_session.sh runs the orth kernel tests under them.
-Written without GPU time left; sorts last like the other test_z* files."""
+"""The fused Lanczos step for a diagonal inner-product matrix (kry_lanczos_diag; default for
+MINRES / Lanczos with a diagonal ``ip_B`` since round 2, ``KRY_LANCZOS_DIAGB=0`` turns it off) on the
+GPU: the kernel against numpy with the same rounding points, and the fixtures with the fused step on
+and off."""
 import numpy as np
 import pytest
 
 import runners
 
-import os
-
-# A NEW cooperative kernel that has never run on a GPU must not be able to wedge the default GPU test
-# tier: these tests only run when asked for (tools/gpu_session.sh sets KRY_TEST_VARIANTS=1, under `timeout`).
-pytestmark = [pytest.mark.gpu,
-              pytest.mark.skipif(not os.environ.get("KRY_TEST_VARIANTS"), reason="opt-in: set KRY_TEST_VARIANTS=1")]
+pytestmark = pytest.mark.gpu
 
 
 def _ctx():
@@ -71,10 +65,10 @@ def test_lanczos_diag_kernel(n, dt, with_prev, offset):
     check_lanczos_diag_kernel(_ctx(), n, dt, with_prev, offset)
 
 
-def check_switch_parity(monkeypatch, switch, name, **kw):
-    """a fixture case with a host-level measurement switch turned on still reproduces the reference"""
+def check_switch_parity(monkeypatch, switch, name, value=True, **kw):
+    """a fixture case with a host-level switch set to `value` reproduces the reference"""
     from krypy_b200 import utils
-    monkeypatch.setattr(utils, switch, True)
+    monkeypatch.setattr(utils, switch, value)
     gold = runners.load_golden(name)
     got = runners.run_product(name, **kw)
     a, b = got["resnorms"], gold["resnorms"]
@@ -89,16 +83,8 @@ def check_switch_parity(monkeypatch, switch, name, **kw):
 def test_fused_diagonal_ipB_lanczos_reproduces_the_reference(monkeypatch, name):
     ctx = _ctx()
     before = ctx.launch_count()
-    check_switch_parity(monkeypatch, "_LANCZOS_DIAGB", name)
+    check_switch_parity(monkeypatch, "_LANCZOS_DIAGB", name, True)
     fused = ctx.launch_count() - before
-    from krypy_b200 import utils
-    monkeypatch.setattr(utils, "_LANCZOS_DIAGB", False)
     before = ctx.launch_count()
-    runners.run_product(name)
+    check_switch_parity(monkeypatch, "_LANCZOS_DIAGB", name, False)      # the generic sequence still matches
     assert fused < ctx.launch_count() - before          # one kernel instead of seven per step
-
-
-@pytest.mark.parametrize("name,kw", [("lap2d_gmres30", dict(ortho="cgs")), ("lap2d_gmres_mgs", {}),
-                                     ("c1_minres", {})])
-def test_split_normalised_store_reproduces_the_reference(monkeypatch, name, kw):
-    check_switch_parity(monkeypatch, "_SPLIT_SCALE", name, **kw)

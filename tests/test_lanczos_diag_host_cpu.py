@@ -1,9 +1,9 @@
-"""CPU tier twin of tests/test_zz_variants_gpu.py over the device test double."""
+"""CPU tier twin of tests/test_lanczos_diag_gpu.py over the device test double."""
 import numpy as np
 import pytest
 
 import fake_device
-import test_zz_variants_gpu as v
+import test_lanczos_diag_gpu as v
 
 
 @pytest.fixture()
@@ -21,9 +21,3 @@ def test_lanczos_diag_contract(fake, dt, with_prev):
 def test_fused_diagonal_ipB_lanczos(fake, monkeypatch, name):
     v.check_switch_parity(monkeypatch, "_LANCZOS_DIAGB", name)
     assert fake.calls.get("lanczos_diag", 0) == 30 and "axpy_dev" not in fake.calls
-
-
-@pytest.mark.parametrize("name,kw", [("lap2d_gmres30", dict(ortho="cgs")), ("lap2d_gmres_mgs", {})])
-def test_split_normalised_store(fake, monkeypatch, name, kw):
-    v.check_switch_parity(monkeypatch, "_SPLIT_SCALE", name, **kw)
-    assert fake.calls.get("scale_dev", 0) >= 30
