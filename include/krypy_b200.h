@@ -132,11 +132,17 @@ int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const
  * kernel:  q -= pre_coef_dev[0]*vprev (vprev may be NULL: k == 0);  alpha = <vk, q>_B;
  * h3_dev[1] += alpha;  q -= alpha*vk;  h3_dev[2] = beta = sqrt(<q, q>_B);  vnext = q/beta
  * (vnext may be NULL).  h3_dev is the [H[k-1,k], H[k,k], H[k+1,k]] triple kry_minres_recur reads.
- * Opt-in variant (host switch KRY_LANCZOS_DIAGB=1); the default runs this step with
- * kry_axpy_dev / kry_diag_mul / kry_block_dot / kry_scale_dev. */
+ * Default for a real positive diagonal ip_B (host switch KRY_LANCZOS_DIAGB=0: the generic sequence
+ * kry_axpy_dev / kry_diag_mul / kry_block_dot / kry_scale_dev). */
 int kry_lanczos_diag(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk,
                      const void* bdiag, void* q, const double* pre_coef_dev, double* h3_dev,
                      void* vnext);
+/* The same step on a row-partitioned run: both reductions are completed over NVLink peer memory
+ * inside the kernel (peer arguments as for kry_peer_allreduce). */
+int kry_lanczos_diag_dist(kry_ctx* ctx, int dtype, long long n, const void* vprev, const void* vk,
+                          const void* bdiag, void* q, const double* pre_coef_dev, double* h3_dev,
+                          void* vnext, int world, int rank, unsigned long long* epoch_dev,
+                          double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 
 /* ---- oblique projection for deflation (one cooperative kernel) ---------- */
 /* a <- (I - V (R^-1 Q^H) W^H)^iterations a  (krypy/utils.py:604-627 with
@@ -263,6 +269,15 @@ int kry_dist_scale_halo(kry_ctx* ctx, int dtype, long long n, const void* q, voi
                         long long elem_offset, const int* halo_peer, const int* halo_off, void* halo_dst,
                         int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
                         unsigned long long* const* peer_flags_dev);
+/* kry_dist_scale_haloq: like kry_dist_scale_halo, but the halo of v_next is gathered from the peers'
+ * un-normalised q (element offset q_elem_offset inside the peer-mapped regions) and divided by the norm
+ * here, so the norm's flag doubles as the "segment complete" handshake (one cross-GPU wait per call
+ * instead of two).  The caller alternates between two q buffers from step to step. */
+int kry_dist_scale_haloq(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext, double* nrm_out_dev,
+                         long long nhalo, const void* const* peer_bases_dev, long long q_elem_offset,
+                         const int* halo_peer, const int* halo_off, void* halo_dst, int world, int rank,
+                         unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                         unsigned long long* const* peer_flags_dev);
 int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev,
                   long long elem_offset, const int* halo_peer, const int* halo_off, void* dst, int world,
                   int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,

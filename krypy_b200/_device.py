@@ -404,7 +404,16 @@ class Context(object):
                     j += c
             if nrm is not None:
                 hal = halo_op._halo_args(vnext) if (halo_op is not None and vnext is not None) else None
-                if hal is not None:
+                halq = halo_op._halo_src_args(q) if hal is not None else None
+                if halq is not None and comm.halo_from_q:
+                    # scale + halo of v_next gathered from the peers' un-normalised q: the norm's flag is the
+                    # only cross-GPU wait of this kernel (q alternates between two buffers, see utils.Arnoldi)
+                    _, _, hp, ho, nhalo, dst = hal
+                    q_tab, q_off = halq
+                    check(lib.kry_dist_scale_haloq(self.h, dt, n, q.data_ptr(), vnext.data_ptr(), nrm.data_ptr(),
+                                                   nhalo, q_tab, q_off, hp, ho, dst, w, r, ep, sl, fl))
+                    comm.halo_ready = vnext.data_ptr()
+                elif hal is not None:
                     # scale + "segment complete" handshake + halo gather of v_next in one kernel
                     peer_tab, off, hp, ho, nhalo, dst = hal
                     check(lib.kry_dist_scale_halo(self.h, dt, n, q.data_ptr(), vnext.data_ptr(), nrm.data_ptr(),
@@ -432,6 +441,13 @@ class Context(object):
 
     def lanczos_diag(self, vprev, vk, bdiag, q, pre_coef, h3, vnext):
         """fused Lanczos step for a diagonal inner-product matrix (kry_lanczos_diag)"""
+        if self.comm is not None:
+            c = self.comm
+            check(self.lib.kry_lanczos_diag_dist(
+                self.h, code(q), q.numel(), _p(vprev), vk.data_ptr(), bdiag.data_ptr(), q.data_ptr(), _p(pre_coef),
+                h3.data_ptr(), _p(vnext), c.world, c.rank, c.epoch_dev.data_ptr(), c.slots.peer_table.data_ptr(),
+                c.flags.peer_table.data_ptr()))
+            return
         check(self.lib.kry_lanczos_diag(self.h, code(q), q.numel(), _p(vprev), vk.data_ptr(), bdiag.data_ptr(),
                                         q.data_ptr(), _p(pre_coef), h3.data_ptr(), _p(vnext)))
 

@@ -53,6 +53,8 @@ PROTOTYPES = {
                                c_void_p]),
     "kry_lanczos_diag": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
+    "kry_lanczos_diag_dist": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "kry_project": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p,
                             c_void_p, c_void_p, c_int, c_void_p]),
     "kry_givens_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
@@ -84,6 +86,8 @@ PROTOTYPES = {
                                c_void_p, c_void_p]),
     "kry_dist_scale_halo": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll,
                                     c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kry_dist_scale_haloq": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll,
+                                     c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "kry_dist_halo": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "kry_small_qr_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),

@@ -16,71 +16,27 @@
 // sequence on all ranks); slot arrays are double buffered by epoch parity; a rank publishes
 // epoch e only after it has observed every peer's epoch e-1.
 #include "kry_common.cuh"
+#include "kry_sweeps.cuh"
 
 #define KRY_ENTER(ctx)                                                         \
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
     KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
 
 // ---------------------------------------------------------------------------
-// K1: local block dot + publish
+// K1: local block dot + publish.  Up to 16 vectors per pass over q, sweeps specialised on the exact
+// vector count (kry_sweeps.cuh), one barrier pair per CTA reduction.
 // ---------------------------------------------------------------------------
-#define DD_JT 8
 template <typename T, int VEC>
 __global__ void __launch_bounds__(KRY_THREADS, 2)
 dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, const T* q, double* partials,
                 unsigned int* ticket, PeerArgs pa) {
-    __shared__ double red[DD_JT * 8];
+    __shared__ double red[ORTH_JT * 8];
     __shared__ double fin[PEER_SLOT];
     __shared__ bool last;
     const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
-    const long long nvec = n / VEC;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    const long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    for (int jb = 0; jb < nv; jb += DD_JT) {
-        double acc[DD_JT];
-#pragma unroll
-        for (int t = 0; t < DD_JT; ++t) acc[t] = 0.0;
-        for (long long i = i0; i < nvec; i += stride) {
-            double qv[VEC];
-            VecIO<T, VEC>::loadrw(q, i, qv);
-            double vv[DD_JT][VEC];
-#pragma unroll
-            for (int t = 0; t < DD_JT; ++t) {
-                int j = jb + t;
-                j = j < nv ? j : nv - 1;
-                VecIO<T, VEC>::load(V + (long long)j * ldv, i, vv[t]);
-            }
-#pragma unroll
-            for (int t = 0; t < DD_JT; ++t)
-#pragma unroll
-                for (int u = 0; u < VEC; ++u) acc[t] = fma(vv[t][u], qv[u], acc[t]);
-        }
-        if (blockIdx.x == 0) {
-            for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
-                const double qe = (double)q[i];
-#pragma unroll
-                for (int t = 0; t < DD_JT; ++t)
-                    if (jb + t < nv) acc[t] = fma((double)V[(long long)(jb + t) * ldv + i], qe, acc[t]);
-            }
-        }
-        // CTA reduction of all DD_JT accumulators with ONE barrier pair (at the per-rank sizes of an
-        // 8-GPU run the per-accumulator barriers were ~15 % of the kernel)
-        {
-            const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-#pragma unroll
-            for (int t = 0; t < DD_JT; ++t) acc[t] = kry_warp_sum(acc[t]);
-            __syncthreads();
-            if (lane == 0) {
-#pragma unroll
-                for (int t = 0; t < DD_JT; ++t) red[t * 8 + w] = acc[t];
-            }
-            __syncthreads();
-            if (threadIdx.x < DD_JT && jb + threadIdx.x < nv) {
-                double s = 0.0;
-                for (int ww = 0; ww < nw; ++ww) s += red[threadIdx.x * 8 + ww];     // fixed warp order
-                partials[(long long)(jb + threadIdx.x) * KRY_MAX_PARTIAL_BLOCKS + blockIdx.x] = s;
-            }
-        }
+    for (int jb = 0; jb < nv; jb += ORTH_JT) {
+        const int nt = nv - jb < ORTH_JT ? nv - jb : ORTH_JT;
+        dots_dispatch<T, VEC>(nt, V + (long long)jb * ldv, ldv, q, n, red, partials, 0, jb);
     }
     __threadfence();
     __syncthreads();
@@ -140,45 +96,7 @@ dist_update_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, 
     __syncthreads();
     if (blockIdx.x == 0 && h_acc)
         for (int j = threadIdx.x; j < nv; j += blockDim.x) h_acc[j] += c_s[j];
-    const long long nvec = n / VEC;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    double nrm2 = 0.0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
-        double qv[VEC];
-        VecIO<T, VEC>::loadrw(q, i, qv);
-        for (int jb = 0; jb < nv; jb += 8) {
-            double vv[8][VEC];
-#pragma unroll
-            for (int t = 0; t < 8; ++t) {
-                int j = jb + t < nv ? jb + t : nv - 1;
-                VecIO<T, VEC>::load(V + (long long)j * ldv, i, vv[t]);
-            }
-#pragma unroll
-            for (int t = 0; t < 8; ++t)
-                if (jb + t < nv) {
-                    const double c = c_s[jb + t];
-#pragma unroll
-                    for (int u = 0; u < VEC; ++u) qv[u] = fma(-c, vv[t][u], qv[u]);
-                }
-        }
-        VecIO<T, VEC>::store(q, i, qv);
-        if (want_nrm) {
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) {
-                const double r = (double)(T)qv[u];
-                nrm2 = fma(r, r, nrm2);
-            }
-        }
-    }
-    if (blockIdx.x == 0) {
-        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x) {
-            double qe = (double)q[i];
-            for (int j = 0; j < nv; ++j) qe = fma(-c_s[j], (double)V[(long long)j * ldv + i], qe);
-            q[i] = (T)qe;
-            qe = (double)q[i];
-            if (want_nrm) nrm2 = fma(qe, qe, nrm2);
-        }
-    }
+    const double nrm2 = update_dispatch<T, VEC, false>(V, ldv, nv, c_s, q, n, want_nrm != 0);
     if (!want_nrm) return;
     double s = kry_block_sum(nrm2, sm);
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
@@ -203,6 +121,37 @@ dist_update_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, 
             *ticket = 0u;
         }
     }
+}
+
+// ---------------------------------------------------------------------------
+// K3q: acquire ||q||^2, v_next = q / nrm, and the halo of v_next gathered from the peers'
+// UN-NORMALISED q (divided by the same nrm here: bitwise the value the owner stores).  A peer
+// publishes its ||q||^2 partial only after its q segment is complete, so the norm's flag is also
+// the "segment complete" handshake: one cross-GPU wait instead of two.  The peers rewrite their q
+// with the next SpMV, therefore the host alternates between two q buffers (step parity): a rank
+// cannot reach the SpMV after next before every neighbour has passed this kernel.
+// ---------------------------------------------------------------------------
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 4)
+dist_scale_haloq_kernel(long long n, const T* q, T* vnext, double* nrm_out, long long nhalo,
+                        const T* const* peer_bases, long long q_elem_offset, const int* __restrict__ halo_peer,
+                        const int* __restrict__ halo_off, T* halo_dst, PeerArgs pa) {
+    __shared__ int okflag;
+    __shared__ double nrm_s;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
+    const bool ok = peer_wait(pa, E, &okflag);
+    if (threadIdx.x == 0) nrm_s = ok ? sqrt(fabs(peer_sum(pa, E, 0))) : nan_f64();
+    __syncthreads();
+    const double nrm = nrm_s;
+    if (blockIdx.x == 0 && threadIdx.x == 0) nrm_out[0] = nrm;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    // halo first: the remote loads' latency overlaps with the local sweep
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nhalo; i += stride) {
+        const T* src = peer_bases[__ldg(halo_peer + i)] + q_elem_offset;
+        const T v = *(const volatile T*)(src + __ldg(halo_off + i));
+        halo_dst[i] = ok ? (T)(nrm > 0.0 ? (double)v / nrm : 0.0) : (T)nan_f64();
+    }
+    scale_pass<T, VEC>(q, vnext, n, nrm);
 }
 
 // ---------------------------------------------------------------------------
@@ -483,6 +432,47 @@ int kry_dist_scale_halo(kry_ctx* ctx, int dtype, long long n, const void* q, voi
                 (float*)halo_dst, tk, pa);
     } else {
         kry_set_error("kry_dist_scale_halo: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_dist_scale_haloq(kry_ctx* ctx, int dtype, long long n, const void* q, void* vnext, double* nrm_out_dev,
+                         long long nhalo, const void* const* peer_bases_dev, long long q_elem_offset,
+                         const int* halo_peer, const int* halo_off, void* halo_dst, int world, int rank,
+                         unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                         unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && q && vnext && nrm_out_dev && nhalo >= 0, "bad arguments");
+    KRY_REQUIRE(nhalo == 0 || (peer_bases_dev && halo_peer && halo_off && halo_dst), "NULL halo argument");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    if (dtype == KRY_F64) {
+        const double* qq = (const double*)q;
+        double* vn = (double*)vnext;
+        if (kry_aligned16(qq) && kry_aligned16(vn))
+            dist_scale_haloq_kernel<double, 2><<<dgrid(ctx, n / 2, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const double* const*)peer_bases_dev, q_elem_offset, halo_peer,
+                halo_off, (double*)halo_dst, pa);
+        else
+            dist_scale_haloq_kernel<double, 1><<<dgrid(ctx, n, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const double* const*)peer_bases_dev, q_elem_offset, halo_peer,
+                halo_off, (double*)halo_dst, pa);
+    } else if (dtype == KRY_F32) {
+        const float* qq = (const float*)q;
+        float* vn = (float*)vnext;
+        if (kry_aligned16(qq) && kry_aligned16(vn))
+            dist_scale_haloq_kernel<float, 4><<<dgrid(ctx, n / 4, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const float* const*)peer_bases_dev, q_elem_offset, halo_peer,
+                halo_off, (float*)halo_dst, pa);
+        else
+            dist_scale_haloq_kernel<float, 1><<<dgrid(ctx, n, 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, qq, vn, nrm_out_dev, nhalo, (const float* const*)peer_bases_dev, q_elem_offset, halo_peer,
+                halo_off, (float*)halo_dst, pa);
+    } else {
+        kry_set_error("kry_dist_scale_haloq: unsupported dtype %d", dtype);
         return KRY_ERR_UNSUPPORTED;
     }
     KRY_LAUNCHED(ctx);

@@ -162,7 +162,12 @@ class _DeflationMixin(object):
         nr = 2 if self._td == _device.torch().complex128 else 1
         self._Craw = ctx.scalars(max((self.maxiter + 2) * nr * max(self._d, 1), 1)).reshape(
             self.maxiter + 2, nr * max(self._d, 1))
-        P = utils._FunctionDeviceOperator((N, N), self.linear_system.dtype, self._apply_projection)
+        # (a weak reference: the operator is stored on the solver, and a bound method would make the
+        # solver -- with its bases in HBM -- cyclic garbage that only Python's cyclic collector frees)
+        import weakref
+        me = weakref.ref(self)
+        P = utils._FunctionDeviceOperator((N, N), self.linear_system.dtype,
+                                          lambda Av: me()._apply_projection(Av))
         self.MlAMr = P * self.linear_system.MlAMr
         super(_DeflationMixin, self)._solve()
 

@@ -168,6 +168,9 @@ class PeerComm(object):
         # 6603 vs 6301 it/s on C2 at 8 GPUs); coop: ONE cooperative kernel per Gram-Schmidt step
         self.orth_mode = os.environ.get("KRY_DIST_ORTH", "split")
         self.halo_ready = None      # data_ptr of the basis row whose halo the last orth step already gathered
+        # gather the halo of v_{k+1} from the peers' un-normalised q (one cross-GPU wait less per
+        # Arnoldi step; KRY_DIST_HALO_FROM_Q=0: from their v_{k+1} rows after a second handshake)
+        self.halo_from_q = os.environ.get("KRY_DIST_HALO_FROM_Q", "1") not in ("0", "")
         self.barrier_sync()
 
     def all_gather_object(self, obj):
@@ -341,6 +344,16 @@ class DistCsrOperator(utils._DeviceOperator):
     def _apply_dot_dev(self, p, Ap, pAp):
         """Ap = A p and pAp[0] = <p, Ap> (global) with the dot in the SpMV epilogue (CG, linsys.py:631-634)"""
         self._apply_dev(p, out=Ap, dot_out=pAp)
+
+    def _halo_src_args(self, vec):
+        """(peer pointer table, element offset) of a vector that lives in a peer-mapped region (the
+        gather SOURCE of a halo exchange), or None"""
+        comm, pl = self.comm, self.plan
+        es = vec.element_size()
+        reg = comm.find_region(vec.data_ptr(), pl.nloc * es)
+        if reg is None or comm.reduce != "peer":
+            return None
+        return reg.peer_table.data_ptr(), (vec.data_ptr() - reg.base) // es
 
     def _apply_dev(self, Xd, out=None, adj=False, dot_out=None):
         if adj:

@@ -623,10 +623,11 @@ class Cg(_KrylovSolver):
         """krypy/linsys.py:691-696."""
         if self.store_arnoldi:
             ctx = self._ctx
-            nc = self.iter + 1
-            self.V = lambda: ctx.to_numpy(self._Vd[:nc]).astype(self.dtype, copy=False)
-            if self._Pd is not None:
-                self.P = lambda: ctx.to_numpy(self._Pd[:nc]).astype(self.dtype, copy=False)
+            nc, dt = self.iter + 1, self.dtype
+            Vd, Pd = self._Vd, self._Pd           # (no reference to self in the thunks: no cycle)
+            self.V = lambda: ctx.to_numpy(Vd[:nc]).astype(dt, copy=False)
+            if Pd is not None:
+                self.P = lambda: ctx.to_numpy(Pd[:nc]).astype(dt, copy=False)
             self.H = self.H[: self.iter + 1, : self.iter]
 
     @staticmethod
@@ -673,11 +674,23 @@ class Minres(_KrylovSolver):
         st[6:7].fill_(float(self.MMlr0_norm))                       # y = [||r0||, 0], linsys.py:809
         mb = ctx.mailbox
         is_lanczos = self.ortho == "lanczos"
+        # Look-ahead (three-term Lanczos): the operator apply and the Lanczos kernel of step k+1 -- three
+        # quarters of an iteration's bytes -- are enqueued BEFORE the host waits for step k's residual,
+        # so the device works through the host's bookkeeping.  A Lanczos step does not depend on the
+        # host's decision; if the loop ends at k the speculative step only wrote V[k+2] and the
+        # three-entry accumulator, which nothing reads afterwards.  The solution update of step k+1
+        # (which changes y, W) is launched only after the decision.
+        lookahead = is_lanczos
+        ev = ctx.event()
+        launched = -1
         while (self.resnorms[-1] > self.tol and lz.iter < lz.maxiter and not lz.invariant):
             k = self.iter = lz.iter
-            lz._enqueue(k)                                           # linsys.py:823
+            if launched < k:
+                lz._enqueue(k)                                       # linsys.py:823
+                launched = k
             if is_lanczos:
                 ctx.minres_recur(k, lz._lz, st, 1, 0)                # linsys.py:827-841, 847
+                ev.record()
             elif lz._cplx:
                 # the recurrence takes the real parts (linsys.py:828-833): gather them from the
                 # interleaved column
@@ -688,7 +701,10 @@ class Minres(_KrylovSolver):
             ctx.minres_update(lz._Vd[k], W0[0], W1[0], yk[0], st)    # linsys.py:844-846
             W0, W1 = W1, W0
             if is_lanczos:
-                ctx.sync()
+                if lookahead and k + 1 < lz.maxiter:
+                    lz._enqueue(k + 1)
+                    launched = k + 1
+                ev.synchronize()
                 resid = float(mb[0])
                 lz._finish(k, mb[6:8].copy())
             else:
@@ -696,8 +712,14 @@ class Minres(_KrylovSolver):
                 resid = float(mb[0])
                 lz._finish(k, hc)
             self._finalize_iteration(yk, resid)                      # linsys.py:849
+        if launched >= 0 and launched == lz.iter:      # step lz.iter was enqueued but not consumed
+            self._discard_speculative()
         if self.__dict__.get("_xk_dev") is None:
             self.xk = self._get_xk(yk)
+
+    def _discard_speculative(self):
+        """hook: a look-ahead Lanczos step was enqueued but not consumed"""
+        pass
 
     def _finalize(self):
         """krypy/linsys.py:855-862."""

@@ -378,7 +378,17 @@ class _DeviceOperator(LinearOperator):
     _device_native = True
 
     def __init__(self, shape, dtype):
-        super(_DeviceOperator, self).__init__(shape, dtype, self._dot_np, self._dot_adj_np)
+        super(_DeviceOperator, self).__init__(shape, dtype, _DeviceOperator._dot, _DeviceOperator._dot_adj)
+        # the class-level methods below take over: storing BOUND methods on the instance would make
+        # every operator a reference cycle, and a cycle keeps its device arrays (the CSR matrix of a
+        # MatrixLinearOperator: 0.8 GB on config C2) in HBM until Python's cyclic collector runs
+        del self._dot, self._dot_adj
+
+    def _dot(self, X):
+        return self._dot_np(X)
+
+    def _dot_adj(self, X):
+        return self._dot_adj_np(X)
 
     def _np(self, X, adj):
         ctx = _ctx()
@@ -1595,6 +1605,14 @@ class Arnoldi(object):
         # small quantities are always >= fp64 on the device path (also in fp32 storage mode)
         self.H = numpy.zeros((self.maxiter + 1, self.maxiter), dtype=_common_type([self.dtype, numpy.float64]))
         self._euclid = _is_identity_ip(ip_B)
+        # Row-partitioned runs: A v_k goes to one of TWO peer-mapped buffers (step parity), because the
+        # neighbours gather the halo of v_{k+1} from this rank's un-normalised q (kry_dist_scale_haloq)
+        # while this rank may already be writing the next A v.
+        self._q2 = None
+        if self._halo_op is not None and not cplx and getattr(ctx.comm, "halo_from_q", False):
+            mk = lambda: ctx.alloc_basis(2, N, td, rf)
+            q2 = ws.tensor("q2", (2, N, td), mk) if ws is not None else mk()
+            self._q2 = (q2, q2[0:1, :N], q2[1:2, :N])
         if ws is not None:
             # buffers persist across restart cycles so that a step's launch arguments are stable
             # (CUDA-graph replay); everything that must start from zero is re-zeroed here
@@ -1679,7 +1697,7 @@ class Arnoldi(object):
         # Vt/Pt: the rows the kernels work on.  Real: the basis itself.  Complex: twin storage,
         # rows nr*j (+1) = v_j (i v_j); coefficients are nr doubles each (interleaved re/im).
         Vt, Pt, nr, cplx = self._Vt, self._Pt, self._nr, self._cplx
-        q = self._q
+        q = self._q if self._q2 is None else self._q2[1 + (k & 1)]
         self.A._apply_dev(V[k:k + 1], out=q)                       # utils.py:968
         q0 = q[0]
         if self.ortho == "house":
@@ -1717,7 +1735,8 @@ class Arnoldi(object):
                                nrm=nrm if fused_tail else None,
                                vnext=vnext if fused_tail else None,
                                pre_vec=pre_vec, pre_coef=pre_coef, h_ptr=h_ptr, halo_op=self._halo_op)
-        elif (_LANCZOS_DIAGB and lanczos and not cplx and self.M is None and ctx.comm is None
+        elif (_LANCZOS_DIAGB and lanczos and not cplx and self.M is None
+              and (ctx.comm is None or ctx.comm.reduce == "peer")
               and self._passes == 1 and self._diag_ip() is not None):
             # the whole Lanczos step for a diagonal ip_B in ONE cooperative kernel instead of the seven
             # launches of the generic path below (KRY_LANCZOS_DIAGB=0 turns it off)
