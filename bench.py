@@ -46,6 +46,10 @@ def parse():
     p.add_argument("--ortho", default="cgs", help="cgs (fused block, default) | mgs | dmgs | cgs2")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-e2e", action="store_true")
+    p.add_argument("--no-extra-configs", action="store_true",
+                   help="skip the other named configurations (C3/C4/C5 at N=1, C5 at N=4, C3 at N=8)")
+    p.add_argument("--extra", default=None, help="comma list overriding the extra configurations, e.g. c3,c5")
+    p.add_argument("--no-mgs", action="store_true", help="skip the drop-in default (ortho='mgs') figure")
     p.add_argument("--cpu-iters", type=int, default=4, help="iterations of the bounded CPU sample (cpu_baseline)")
     p.add_argument("--ref-iters", type=int, default=3, help="--impl reference: Arnoldi iterations per step")
     return p.parse_args()
@@ -425,26 +429,92 @@ def run_b200(args, rank, world, local_rank):
 
     # ---- e2e: public API from host buffers, copies inside the timed region --------------------
     e2e = None
-    if not args.no_e2e and world == 1:
-        e2e = run_e2e(args, kp, torch, A, b, x)
+    if not args.no_e2e:
+        e2e = run_e2e(args, kp, torch, A, b, x, dist=dist, part=part if world > 1 else None, ls0=ls)
 
-    # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same workload ----------------
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        it, dt, rn, kind, sample = cpu_sample(A, b, args.cpu_iters)
-        cpu = {"value": it / dt, "unit": UNIT, "cores": cpu_threads(), "host_cpus": os.cpu_count(), "kind": kind,
-               "sample": sample + " [%.1f s]" % dt}
-        # parity of the first cycle's history against the CPU run, same inputs (x0 = None)
+    # ---- the drop-in default: the same cycle with ortho='mgs' (the reference's exact operation order) ----
+    if not args.no_mgs and args.ortho != "mgs":
         try:
-            first = kp.linsys.Gmres(ls, maxiter=it, tol=TOL, ortho=args.ortho)
+            wsm = kp.utils.SolverWorkspace()
+            mcarry = {"r": None}
+            def mcycle(x0):
+                try:
+                    sm = kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, _workspace=wsm,      # default ortho
+                                         _x0_residual=mcarry["r"] if x0 is not None else None)
+                except kp.utils.ConvergenceError as e:
+                    sm = e.solver
+                mcarry["r"] = sm.__dict__.get("_last_residual")
+                return sm
+            xm = mcycle(None).__dict__["_xk_dev"].reshape(-1)
+            barrier()
+            m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            m0.record()
+            nm, itm = 3, 0
+            for _ in range(nm):
+                sm_ = mcycle(xm)
+                xm = sm_.__dict__["_xk_dev"].reshape(-1)
+                itm += len(sm_.resnorms) - 1
+            m1.record()
+            barrier()
+            mms = m0.elapsed_time(m1)
+            if dist is not None:
+                tm_ = torch.tensor([mms], device="cuda", dtype=torch.float64)
+                dist.all_reduce(tm_, op=dist.ReduceOp.MAX)
+                mms = float(tm_.item())
+            extra["mgs_value"] = {"value": itm / (mms * 1e-3), "unit": UNIT, "steps": nm, "ms_per_step": mms / nm,
+                                  "what": "the same C2 cycle with the drop-in default ortho='mgs' (exact modified "
+                                          "Gram-Schmidt: k+1 dependent reductions per step, (4(k+1)+4) N s bytes)"}
+            del wsm, sm_, xm
+        except Exception as exc:       # noqa: BLE001
+            extra["mgs_value"] = {"error": repr(exc)}
+
+    # ---- CPU baseline (rank 0): bounded sample of the same workload, and parity against it ----------------
+    cpu = None
+    if not args.no_cpu_baseline:
+        try:
+            first = kp.linsys.Gmres(ls, maxiter=args.cpu_iters, tol=TOL, ortho=args.ortho)
         except kp.utils.ConvergenceError as e:
             first = e.solver
-        a, r = np.array(first.resnorms), np.array(rn)
-        m = min(len(a), len(r))
-        extra["parity_vs_cpu_max_rel"] = float(np.max(np.abs(a[:m] - r[:m]) / r[:m]))
+        if rank == 0:
+            Ag, bg = (A, b) if world == 1 else (problems.laplace2d(n), problems.rhs_normal(N))
+            it, dt, rn, kind, sample = cpu_sample(Ag, bg, args.cpu_iters)
+            cpu = {"value": it / dt, "unit": UNIT, "cores": cpu_threads(), "host_cpus": os.cpu_count(), "kind": kind,
+                   "sample": sample + " [%.1f s]" % dt}
+            # parity of the first cycle's history against the CPU run, same inputs (x0 = None)
+            a, r = np.array(first.resnorms), np.array(rn)
+            m = min(len(a), len(r))
+            extra["parity_vs_cpu_max_rel"] = float(np.max(np.abs(a[:m] - r[:m]) / r[:m]))
+            del Ag, bg
+        if dist is not None:
+            dist.barrier()
+
+    # ---- the other named configurations (BASELINE.json configs[2..4]) at full size ------------------------
+    if not args.no_extra_configs and n == N_GRID:
+        import bench_configs
+        del sol
+        which = {1: [("c5", 6), ("c4", 0), ("c3", 4)], 4: [("c5", 6)], 8: [("c3", 4)]}.get(world, [])
+        if getattr(args, "extra", None):
+            which = [(c, {"c5": 6, "c3": 4}.get(c, 0)) for c in args.extra.split(",") if c]
+        if which:
+            # release C2's device memory first
+            ws.bufs.clear(); ws.graphs.clear()
+            carry["r"] = None
+            x = None
+            torch.cuda.empty_cache()
+        cfgs = {}
+        for cname, ref_steps in which:
+            try:
+                cfgs[cname] = bench_configs.run_device(cname, peak, dist=dist, rank=rank, world=world,
+                                                       ref_steps=0 if args.no_cpu_baseline else ref_steps,
+                                                       log=lambda *a: sys.stderr.write(" ".join(map(str, a)) + "\n"))
+            except Exception as exc:       # noqa: BLE001  (never lose the bench line over an extra)
+                cfgs[cname] = {"error": repr(exc)}
+            torch.cuda.empty_cache()
+        if which:
+            extra["configs"] = cfgs
 
     if rank == 0 and os.environ.get("KRY_TRACE"):
-        tr = sol.__dict__.get("_trace", [])
+        tr = []
         sys.stderr.write("phase trace (ms since start): " + ", ".join(
             "%s=%.3f" % (nm, 1e3 * (tt - tr[0][1])) for nm, tt in tr) + "\n")
     if rank == 0:
@@ -463,8 +533,11 @@ def run_b200(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
-def run_e2e(args, kp, torch, A, b, x_dev):
-    """Every step: host (pinned) A, b, x0 -> LinearSystem -> one Gmres(30) cycle -> x_k on the host."""
+def run_e2e(args, kp, torch, A, b, x_dev, dist=None, part=None, ls0=None):
+    """Every step: host (pinned) A, b, x0 -> LinearSystem -> one Gmres(30) cycle -> x_k on the host.
+    Row-partitioned runs: every rank uploads ITS row block of A, b, x0 and reads back its segment of
+    x_k; the halo plan (host-side symbolic analysis of the sparsity pattern, computed once when the
+    first operator over this matrix was built) is reused, the numeric arrays are uploaded every step."""
     import numpy as np
     import scipy.sparse as sp
 
@@ -486,17 +559,33 @@ def run_e2e(args, kp, torch, A, b, x_dev):
     keep.append(tx)
     h2d = parts[0].nbytes + parts[1].nbytes + parts[2].nbytes + bh.nbytes + xh.nbytes
     d2h = xh.nbytes
+    world = 1
+    if part is not None:
+        from krypy_b200 import dist as kdist
+        world = part.world
+        plan = ls0.A.plan
+
+    def make_ls():
+        if part is None:
+            return kp.linsys.LinearSystem(Ah, bh)
+        return kdist.DistLinearSystem(kdist.DistCsrOperator(Ah, part, plan=plan), bh, part)
 
     def step(x0h):
-        ls = kp.linsys.LinearSystem(Ah, bh)
+        ls = make_ls()
         try:
             sol = kp.linsys.Gmres(ls, x0=x0h, maxiter=RESTART, tol=TOL, ortho=args.ortho)
         except kp.utils.ConvergenceError as e:
             sol = e.solver
         return sol.xk, len(sol.resnorms) - 1       # .xk: device -> host read of the step's result
 
+    def sync():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     xk, _ = step(xh)                                 # warm-up
-    torch.cuda.synchronize()
+    xk, _ = step(xk)
+    sync()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     steps = max(2, min(args.steps, 5))
     e0.record()
@@ -508,11 +597,22 @@ def run_e2e(args, kp, torch, A, b, x_dev):
         wall.append(round(1e3 * (time.perf_counter() - tw), 2))
         its += it
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     ms = e0.elapsed_time(e1)
+    if dist is not None:
+        tms = torch.tensor([ms, float(h2d), float(d2h)], device="cuda", dtype=torch.float64)
+        mx = tms.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        dist.all_reduce(tms, op=dist.ReduceOp.SUM)
+        ms, h2d, d2h = float(mx[0].item()), float(tms[1].item()), float(tms[2].item())
     out = {"value": its / (ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "steps": steps, "ms_per_step": ms / steps, "step_ms_wall": wall,
-           "api": "krypy_b200.linsys.LinearSystem(A_host, b_host) + Gmres(x0=x_host, maxiter=30) per step"}
+           "api": ("krypy_b200.linsys.LinearSystem(A_host, b_host) + Gmres(x0=x_host, maxiter=30) per step"
+                   if part is None else
+                   "per rank: krypy_b200.dist.DistLinearSystem(DistCsrOperator(A_rows_host, part, plan), b_rows_host) + "
+                   "Gmres(x0=x_rows_host, maxiter=30) per step; bytes summed over the %d ranks" % world)}
+    if part is not None:
+        return out
     # the same from the user's actual call: ONE RestartedGmres(30) solve of 5 cycles per upload of A
     # (informational; the strict per-cycle-upload number above stays the e2e figure)
     try:

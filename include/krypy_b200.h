@@ -184,6 +184,24 @@ int kry_tri_solve_z(kry_ctx* ctx, int k, const double* R_dev, long long ldr, con
  * h3[0] = H[k+1,k] and h3[1] = 0 for the next step (utils.py:1003).
  * Mailbox at off: [ |y_next|, R0, R1, R2, ycoef, H[k-1,k], H[k,k], H[k+1,k] ]. */
 int kry_minres_recur(kry_ctx* ctx, int k, double* h3_dev, double* st_dev, int shift, int mailbox_off);
+/* CG with the scalars of the recurrence resident on the device (krypy/linsys.py:627-665), so that the
+ * direction update and the operator apply of iteration k+1 can be enqueued before the host has read
+ * iteration k's residual (look-ahead) and, on row-partitioned runs, without a host round trip per
+ * reduction.  st_dev: [0] rho_{k-1}  [1] rho_k  [2] <p,Ap>  [3] alpha  [4] beta  [5] local share of
+ * the new rho.
+ *   kry_cg_update_dev : kry_cg_update with rho = st[1], <p,Ap> = st[2]; writes st[3] = alpha, st[5]
+ *   kry_cg_scalars    : new rho (global sum over the peers when world > 1; stored as sqrt(|sum|)^2 like
+ *                       the reference, which squares the norm), shift, beta; mailbox[off..off+2] =
+ *                       (raw sum, alpha, <p,Ap>)
+ *   kry_xpby_dev      : out = x + beta_dev[0]*y   (p_k = z + beta p_{k-1}) */
+int kry_cg_update_dev(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk, void* r,
+                      void* z, const void* dinv, double* st_dev);
+int kry_cg_scalars(kry_ctx* ctx, double* st_dev, int mailbox_off, int world, int rank,
+                   unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                   unsigned long long* const* peer_flags_dev);
+int kry_xpby_dev(kry_ctx* ctx, int dtype, long long n, const void* x, const double* beta_dev, const void* y,
+                 void* out);
+
 /* z = (v - R0*W0 - R1*W1)/R2 ; W0 <- W1 ; W1 <- z ; yk += ycoef*z, scalars from
  * st_dev[8..11] (krypy/linsys.py:844-846). w0/w1 are swapped by the caller. */
 int kry_minres_update(kry_ctx* ctx, int dtype, long long n, const void* v, void* w0, const void* w1,

@@ -516,3 +516,24 @@ class Context(object):
     def cg_update(self, Ap, p, yk, r, z, dinv, rho, pAp, off=0):
         check(self.lib.kry_cg_update(self.h, code(p), p.numel(), Ap.data_ptr(), p.data_ptr(), yk.data_ptr(),
                                      r.data_ptr(), _p(z), _p(dinv), float(rho), pAp.data_ptr(), int(off)))
+
+    @realviews
+    def cg_update_dev(self, Ap, p, yk, r, z, dinv, st):
+        """kry_cg_update with the scalars in device memory (st: see include/krypy_b200.h)"""
+        check(self.lib.kry_cg_update_dev(self.h, code(p), p.numel(), Ap.data_ptr(), p.data_ptr(), yk.data_ptr(),
+                                         r.data_ptr(), _p(z), _p(dinv), st.data_ptr()))
+
+    def cg_scalars(self, st, off=0):
+        """new rho (global on row-partitioned runs), shift, beta; publishes to the mailbox"""
+        c = self.comm
+        if c is not None:
+            check(self.lib.kry_cg_scalars(self.h, st.data_ptr(), int(off), c.world, c.rank, c.epoch_dev.data_ptr(),
+                                          c.slots.peer_table.data_ptr(), c.flags.peer_table.data_ptr()))
+        else:
+            check(self.lib.kry_cg_scalars(self.h, st.data_ptr(), int(off), 1, 0, None, None, None))
+
+    @realviews
+    def xpby_dev(self, x, beta, y, out):
+        """out = x + beta[0] * y with beta in device memory"""
+        check(self.lib.kry_xpby_dev(self.h, code(x), x.numel(), x.data_ptr(), beta.data_ptr(), y.data_ptr(),
+                                    out.data_ptr()))

@@ -66,6 +66,10 @@ PROTOTYPES = {
                                   c_void_p]),
     "kry_cg_update": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
                               c_void_p, c_void_p, c_double, c_void_p, c_int]),
+    "kry_cg_update_dev": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_void_p, c_void_p]),
+    "kry_cg_scalars": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kry_xpby_dev": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "kry_peer_alloc": (c_int, [c_void_p, c_ll, ctypes.POINTER(c_void_p)]),
     "kry_peer_free": (c_int, [c_void_p, c_void_p]),
     "kry_ipc_export": (c_int, [c_void_p, c_void_p, ctypes.c_char_p]),

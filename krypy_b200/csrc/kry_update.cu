@@ -14,10 +14,13 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(KRY_THREADS, 2)
 cg_update_kernel(long long n, const T* __restrict__ Ap, const T* __restrict__ p, T* yk, T* r, T* z,
                  const T* __restrict__ dinv, double rho, const double* pAp, double* partials,
-                 unsigned int* ticket, double* mailbox) {
+                 unsigned int* ticket, double* mailbox, double* st) {
     __shared__ double sm[32];
     __shared__ bool last;
-    const double pap = pAp[0];
+    // st != NULL: the scalars of the recurrence live in device memory (kry_cg_update_dev):
+    // st[1] = rho, st[2] = <p,Ap>; out: st[3] = alpha, st[5] = this device's share of the new rho
+    const double pap = st ? st[2] : pAp[0];
+    if (st) rho = st[1];
     const double alpha = rho / pap;
     const long long nvec = n / VEC;
     const long long stride = (long long)gridDim.x * blockDim.x;
@@ -76,9 +79,14 @@ cg_update_kernel(long long n, const T* __restrict__ Ap, const T* __restrict__ p,
         for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) v += __ldcg(partials + b);
         double rr = kry_block_sum(v, sm);
         if (threadIdx.x == 0) {
-            mailbox[0] = rr;
-            mailbox[1] = alpha;
-            mailbox[2] = pap;
+            if (st) {
+                st[3] = alpha;
+                st[5] = rr;
+            } else {
+                mailbox[0] = rr;
+                mailbox[1] = alpha;
+                mailbox[2] = pap;
+            }
             *ticket = 0u;
         }
     }
@@ -115,6 +123,57 @@ minres_update_kernel(long long n, const T* __restrict__ v, T* w0, const T* __res
     }
 }
 
+// The scalar recurrence of CG on the device (one small CTA): completes the new rho (row-partitioned runs:
+// global sum over NVLink peer memory), shifts rho, forms beta and publishes to the pinned mailbox.
+//   st: [0] rho_{k-1}  [1] rho_k  [2] <p,Ap>  [3] alpha  [4] beta = rho_k / rho_{k-1}  [5] local share of the new rho
+// rho_k is stored as sqrt(|sum|)^2 -- the reference squares the NORM it computed (linsys.py:664-665).
+__global__ void __launch_bounds__(64) cg_scalars_kernel(double* st, double* mailbox, PeerArgs pa) {
+    __shared__ int okflag;
+    __shared__ double v[1];
+    double sum = st[5];
+    if (pa.world > 1) {
+        const unsigned long long E = dld_volatile_u64(pa.epoch_dev) + 1ull;
+        if (threadIdx.x == 0) v[0] = sum;
+        __syncthreads();
+        peer_publish(pa, E, v, 1);
+        const bool ok = peer_wait(pa, E, &okflag);
+        sum = ok ? peer_sum(pa, E, 0) : nan_f64();
+        __syncthreads();
+        if (threadIdx.x == 0) *pa.epoch_dev = E;
+    }
+    if (threadIdx.x == 0) {
+        const double nrm = sqrt(fabs(sum));
+        const double rho_new = __dmul_rn(nrm, nrm);
+        const double prev = st[1];
+        st[0] = prev;
+        st[1] = rho_new;
+        st[4] = rho_new / prev;
+        mailbox[0] = sum;
+        mailbox[1] = st[3];
+        mailbox[2] = st[2];
+    }
+}
+
+// out = x + beta_dev[0] * y   (CG direction update p_k = z + beta p_{k-1}, linsys.py:627, beta on the device)
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 4)
+xpby_dev_kernel(long long n, const T* __restrict__ x, const double* beta_dev, const T* y, T* out) {
+    const double beta = beta_dev[0];
+    const long long nvec = n / VEC;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        double xv[VEC], yv[VEC];
+        VecIO<T, VEC>::load(x, i, xv);
+        VecIO<T, VEC>::loadrw(y, i, yv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) yv[u] = __dadd_rn(xv[u], __dmul_rn(beta, yv[u]));   // numpy: z + (beta*p)
+        VecIO<T, VEC>::store(out, i, yv);
+    }
+    if (blockIdx.x == 0)
+        for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x)
+            out[i] = (T)__dadd_rn((double)x[i], __dmul_rn(beta, (double)y[i]));
+}
+
 static inline int upd_grid(const kry_ctx* ctx, long long nvec) {
     long long need = (nvec + KRY_THREADS - 1) / KRY_THREADS;
     long long cap = (long long)ctx->sm_count * 4;
@@ -124,10 +183,10 @@ static inline int upd_grid(const kry_ctx* ctx, long long nvec) {
 
 extern "C" {
 
-int kry_cg_update(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk, void* r, void* z,
-                  const void* dinv, double rho, const double* pAp_dev, int mailbox_off) {
+static int cg_update_impl(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk, void* r,
+                          void* z, const void* dinv, double rho, const double* pAp_dev, int mailbox_off, double* st) {
     KRY_ENTER(ctx);
-    KRY_REQUIRE(n >= 0 && Ap && p && yk && r && pAp_dev, "bad arguments");
+    KRY_REQUIRE(n >= 0 && Ap && p && yk && r && (pAp_dev || st), "bad arguments");
     KRY_REQUIRE(!dinv || z, "dinv given without z");
     KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 3 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
     bool al = kry_aligned16(Ap) && kry_aligned16(p) && kry_aligned16(yk) && kry_aligned16(r) &&
@@ -137,22 +196,78 @@ int kry_cg_update(kry_ctx* ctx, int dtype, long long n, const void* Ap, const vo
         if (al)
             cg_update_kernel<double, 2><<<upd_grid(ctx, n / 2), KRY_THREADS, 0, ctx->stream>>>(
                 n, (const double*)Ap, (const double*)p, (double*)yk, (double*)r, (double*)z, (const double*)dinv, rho,
-                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb, st);
         else
             cg_update_kernel<double, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
                 n, (const double*)Ap, (const double*)p, (double*)yk, (double*)r, (double*)z, (const double*)dinv, rho,
-                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb, st);
     } else if (dtype == KRY_F32) {
         if (al)
             cg_update_kernel<float, 4><<<upd_grid(ctx, n / 4), KRY_THREADS, 0, ctx->stream>>>(
                 n, (const float*)Ap, (const float*)p, (float*)yk, (float*)r, (float*)z, (const float*)dinv, rho,
-                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb, st);
         else
             cg_update_kernel<float, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
                 n, (const float*)Ap, (const float*)p, (float*)yk, (float*)r, (float*)z, (const float*)dinv, rho,
-                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb);
+                pAp_dev, ctx->d_partials, ctx->d_ticket + 2, mb, st);
     } else {
         kry_set_error("kry_cg_update: unsupported dtype %d", dtype);
+        return KRY_ERR_UNSUPPORTED;
+    }
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_cg_update(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk, void* r, void* z,
+                  const void* dinv, double rho, const double* pAp_dev, int mailbox_off) {
+    return cg_update_impl(ctx, dtype, n, Ap, p, yk, r, z, dinv, rho, pAp_dev, mailbox_off, nullptr);
+}
+
+int kry_cg_update_dev(kry_ctx* ctx, int dtype, long long n, const void* Ap, const void* p, void* yk, void* r, void* z,
+                      const void* dinv, double* st_dev) {
+    KRY_REQUIRE(st_dev != nullptr, "st_dev is NULL");
+    return cg_update_impl(ctx, dtype, n, Ap, p, yk, r, z, dinv, 0.0, nullptr, 0, st_dev);
+}
+
+int kry_cg_scalars(kry_ctx* ctx, double* st_dev, int mailbox_off, int world, int rank, unsigned long long* epoch_dev,
+                   double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(st_dev != nullptr, "st_dev is NULL");
+    KRY_REQUIRE(mailbox_off >= 0 && mailbox_off + 3 <= KRY_MAILBOX_DOUBLES, "mailbox overflow");
+    KRY_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "bad world/rank");
+    KRY_REQUIRE(world == 1 || (epoch_dev && peer_slots_dev && peer_flags_dev), "NULL peer argument");
+    PeerArgs pa;
+    pa.world = world;
+    pa.rank = rank;
+    pa.epoch_dev = epoch_dev;
+    pa.slots = peer_slots_dev;
+    pa.flags = peer_flags_dev;
+    cg_scalars_kernel<<<1, 64, 0, ctx->stream>>>(st_dev, ctx->d_mailbox + mailbox_off, pa);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_xpby_dev(kry_ctx* ctx, int dtype, long long n, const void* x, const double* beta_dev, const void* y,
+                 void* out) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && x && beta_dev && y && out, "bad arguments");
+    const bool al = kry_aligned16(x) && kry_aligned16(y) && kry_aligned16(out);
+    if (dtype == KRY_F64) {
+        if (al)
+            xpby_dev_kernel<double, 2><<<upd_grid(ctx, n / 2), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const double*)x, beta_dev, (const double*)y, (double*)out);
+        else
+            xpby_dev_kernel<double, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const double*)x, beta_dev, (const double*)y, (double*)out);
+    } else if (dtype == KRY_F32) {
+        if (al)
+            xpby_dev_kernel<float, 4><<<upd_grid(ctx, n / 4), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const float*)x, beta_dev, (const float*)y, (float*)out);
+        else
+            xpby_dev_kernel<float, 1><<<upd_grid(ctx, n), KRY_THREADS, 0, ctx->stream>>>(
+                n, (const float*)x, beta_dev, (const float*)y, (float*)out);
+    } else {
+        kry_set_error("kry_xpby_dev: unsupported dtype %d", dtype);
         return KRY_ERR_UNSUPPORTED;
     }
     KRY_LAUNCHED(ctx);

@@ -425,7 +425,12 @@ class Ritz(object):
         return out if numpy.iscomplexobj(out) else out.astype(self._solver.dtype, copy=False)
 
     def get_explicit_residual(self, indices=None):
-        """krypy/deflation.py:849-855 (real Ritz pairs)."""
+        """krypy/deflation.py:849-855: ``MlAMr Z - Z diag(values)`` as an ``(N, k)`` numpy array like
+        every other public accessor (the device block stays internal)."""
+        return _ctx().to_numpy(self._explicit_residual_dev(indices))
+
+    def _explicit_residual_dev(self, indices=None):
+        """the explicit Ritz residuals as a vector-major (k, N) device block"""
         ctx = _ctx()
         blk = self.get_vectors_dev(indices).block
         vals = self.values if indices is None else self.values[indices]
@@ -440,7 +445,7 @@ class Ritz(object):
     def get_explicit_resnorms(self, indices=None):
         """krypy/deflation.py:857-869."""
         ls = self._solver.linear_system
-        res = self.get_explicit_residual(indices)
+        res = self._explicit_residual_dev(indices)
         out = numpy.zeros(res.shape[0])
         for j in range(res.shape[0]):
             rj = res[j:j + 1]

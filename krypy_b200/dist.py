@@ -279,18 +279,32 @@ class DistCsrOperator(utils._DeviceOperator):
     ``shape`` is reported as ``(nloc, nloc)`` so the (local) LinearSystem machinery accepts it;
     ``N_global`` holds the true dimension."""
 
-    def __init__(self, A_rows, part, comm=None):
+    def __init__(self, A_rows, part, comm=None, plan=None):
+        """``plan``: the HaloPlan of an earlier operator over the SAME sparsity pattern and partition
+        (host-side symbolic work: which remote entries each row block needs); the numeric values are
+        taken from ``A_rows``."""
         self.part = part
         self.comm = comm if comm is not None else _COMM
         if self.comm is None:
             raise RuntimeError("call krypy_b200.dist.init() first")
-        self.plan = HaloPlan(A_rows, part)
+        if plan is not None:
+            import copy
+            import scipy.sparse as sp
+            A_rows = sp.csr_matrix(A_rows)
+            if A_rows.shape != (part.nloc, part.N) or A_rows.nnz != plan.indices.shape[0]:
+                raise utils.ArgumentError("plan does not belong to this matrix / partition")
+            plan = copy.copy(plan)
+            plan.data = A_rows.data
+        self.plan = plan if plan is not None else HaloPlan(A_rows, part)
         self.N_global = part.N
         super(DistCsrOperator, self).__init__((part.nloc, part.nloc), A_rows.dtype)
         # peers address each other's basis rows with ONE element offset (row index * leading
         # dimension), so the leading dimension must be identical on every rank: size the halo part
         # of a row for the largest halo of any rank
-        self._ext_len = part.block + max(self.comm.all_gather_object(int(self.plan.nhalo)))
+        ext = getattr(self.plan, "ext_len_all", None)
+        if ext is None:
+            ext = self.plan.ext_len_all = part.block + max(self.comm.all_gather_object(int(self.plan.nhalo)))
+        self._ext_len = ext
         self._devcache = {}
         self._xbuf = {}
         self._napply = 0

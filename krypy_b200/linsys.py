@@ -543,9 +543,13 @@ class Cg(_KrylovSolver):
             hasattr(self.MlAMr, "_apply_dot_dev") and ctx.comm.reduce == "peer"))
         z = r if M_is_id else MMlr0d.clone()       # MMlrk (aliases Mlrk when M is the identity)
         dinv = Mdiag._dev(td) if (fast and Mdiag is not None) else None
-        if dist and fast:
-            p = self.MlAMr._alloc_vec(td)          # peer-mapped: its halo is read in place by the neighbours
-            p.copy_(MMlr0d)
+        def pvec():
+            # row-partitioned: peer-mapped, the neighbours read its halo in place
+            return self.MlAMr._alloc_vec(td) if dist else ctx.empty((1, N), td)
+        if fast:
+            pp = (pvec(), pvec())                  # p_k lives in pp[k & 1] (see the look-ahead below)
+            pp[0].copy_(MMlr0d)
+            p = pp[0]
         else:
             p = MMlr0d.clone()
         Ap = ctx.empty((1, N), td)
@@ -570,31 +574,87 @@ class Cg(_KrylovSolver):
             alpha_old = 0
         mb = ctx.mailbox
 
-        while self.resnorms[-1] > self.tol and self.iter < self.maxiter:
+        if fast:
+            # The scalars of the recurrence (rho, <p,Ap>, alpha, beta) live in device memory, so the FRONT
+            # half of iteration k+1 -- p_{k+1} = z + beta p_k and A p_{k+1} with <p,Ap> in the SpMV
+            # epilogue, two thirds of an iteration's bytes -- is enqueued BEFORE the host waits for
+            # iteration k's residual (look-ahead): the device works through the host's bookkeeping, and
+            # on row-partitioned runs no rank's host sits on the critical path of the others.  The
+            # speculative front only writes p_{k+1} (the other buffer), A p and <p,Ap>, none of which
+            # the solver exposes; x, r, z change in the BACK half, which is launched after the decision.
+            st = ctx.scalars(8)                    # [rho_{k-1}, rho_k, <p,Ap>, alpha, beta, local rho share]
+            st[1:2].fill_(float(rhos[-1]))
+            # (deflated CG keeps its bookkeeping per operator application in step with the iteration
+            # counter, deflation.py:247-263: no speculation there)
+            lookahead = (not self.explicit_residual and ls.exact_solution is None
+                         and not hasattr(self, "projection"))
+            ev = ctx.event()
+
+            def front(k):
+                if k > 0:
+                    ctx.xpby_dev(z[0], st[4:], pp[(k - 1) & 1][0], pp[k & 1][0])      # linsys.py:627
+                self._apply_op_dot(pp[k & 1], Ap, st[2:3])                           # linsys.py:631-634
+
+            launched = -1
+            while self.resnorms[-1] > self.tol and self.iter < self.maxiter:
+                k = self.iter
+                if launched < k:
+                    front(k)
+                    launched = k
+                if k > 0 and store:
+                    omega = rhos[-1] / rhos[-2]
+                ctx.cg_update_dev(Ap[0], pp[k & 1][0], yk[0], r[0], z[0] if dinv is not None else None, dinv, st)
+                ctx.cg_scalars(st, 0)                                                # linsys.py:655-665
+                ev.record()
+                if lookahead and k + 1 < self.maxiter:
+                    front(k + 1)
+                    launched = k + 1
+                ev.synchronize()
+                rho_new, alpha = float(mb[0]), float(mb[1])
+                if not numpy.isfinite(rho_new) or rho_new < 0:
+                    rho_new = abs(rho_new)
+                MMlrk_norm = numpy.sqrt(rho_new)
+                rhos.append(MMlrk_norm ** 2)                                         # linsys.py:665
+                if store:
+                    if k > 0:
+                        self.H[k - 1, k] = self.H[k, k - 1]
+                        self.H[k, k] = (1.0 + alpha * omega / alpha_old) / alpha
+                    else:
+                        self.H[k, k] = 1.0 / alpha
+                    tmp.fill_(float(MMlrk_norm))
+                    sgn = (-1.0) ** (k + 1)
+                    ctx.scale_dev(tmp, 1, sgn, z[0], self._Vd[k + 1])                # linsys.py:669
+                    if self._Pd is not None:
+                        ctx.scale_dev(tmp, 1, sgn, r[0], self._Pd[k + 1])            # linsys.py:671
+                    self.H[k + 1, k] = numpy.sqrt(rhos[-1] / rhos[-2]) / alpha
+                    alpha_old = alpha
+                self._Mlrk_dev, self._MMlrk_dev = r, z
+                rkn = self._finalize_iteration(yk, MMlrk_norm)                       # linsys.py:678
+                if rkn is not None:
+                    # the explicit residual replaces rho (linsys.py:681-683): on the device too, and a
+                    # front half that was already enqueued with the old beta is redone (p is double
+                    # buffered for exactly this)
+                    rhos[-1] = rkn ** 2
+                    st[1:2].fill_(float(rhos[-1]))
+                    st[4:5].fill_(float(rhos[-1] / rhos[-2]))
+                    launched = min(launched, k)
+                self.iter += 1
+            p = pp[(self.iter - 1) & 1] if self.iter > 0 else pp[0]
+
+        while (not fast) and self.resnorms[-1] > self.tol and self.iter < self.maxiter:
             k = self.iter
             if k > 0:
                 ctx.axpby(1.0, z[0], rhos[-1] / rhos[-2], p[0], p[0])       # linsys.py:627
                 if store:
                     omega = rhos[-1] / rhos[-2]
             self._apply_op_dot(p, Ap, pAp)                                 # linsys.py:631-634
-            if fast:
-                ctx.cg_update(Ap[0], p[0], yk[0], r[0], z[0] if dinv is not None else None, dinv,
-                              rhos[-1], pAp, 0)                            # linsys.py:655-665
-                if dist:
-                    ctx.comm.allreduce(ctx.mailbox_dev, 1)                 # rho: local -> global sum
-                ctx.sync()
-                rho_new, alpha = float(mb[0]), float(mb[1])
-                if not numpy.isfinite(rho_new) or rho_new < 0:
-                    rho_new = abs(rho_new)
-                MMlrk_norm = numpy.sqrt(rho_new)
-            else:
-                ctx.cg_update(Ap[0], p[0], yk[0], r[0], None, None, rhos[-1], pAp, 0)
-                zz = ls.M._apply_dev(r, out=None if M_is_id else z)       # linsys.py:661
-                if M_is_id:
-                    z = r
-                utils._ip_coef(r, zz, ls.ip_B, tmp, post=1)                # linsys.py:664
-                MMlrk_norm = numpy.float64(tmp[0].item())
-                alpha = float(mb[1])
+            ctx.cg_update(Ap[0], p[0], yk[0], r[0], None, None, rhos[-1], pAp, 0)
+            zz = ls.M._apply_dev(r, out=None if M_is_id else z)           # linsys.py:661
+            if M_is_id:
+                z = r
+            utils._ip_coef(r, zz, ls.ip_B, tmp, post=1)                    # linsys.py:664
+            MMlrk_norm = numpy.float64(tmp[0].item())
+            alpha = float(mb[1])
             rhos.append(MMlrk_norm ** 2)                                   # linsys.py:665
             if store:
                 if k > 0:
@@ -794,6 +854,15 @@ class Gmres(_KrylovSolver):
         """krypy/linsys.py:951-997."""
         ctx = self._ctx
         ls = self.linear_system
+        # The Givens / back-substitution recurrences run in ONE CTA with the column and the rotations in
+        # shared memory: at most 2000 (complex: 1000) steps per cycle.  The reference has no such limit;
+        # say so before any work is done instead of failing at step 2001 (maxiter defaults to N).
+        cap = 1000 if self._td == _device.torch().complex128 else 2000
+        if self.maxiter > cap:
+            raise utils.ArgumentError(
+                "Gmres on the device path supports at most %d steps per cycle (maxiter=%d; the default is "
+                "N): pass maxiter<=%d or use RestartedGmres(ls, maxiter=m, max_restarts=r)"
+                % (cap, self.maxiter, cap))
         self.arnoldi = ar = utils.Arnoldi(
             self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
             Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype,

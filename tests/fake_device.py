@@ -374,6 +374,36 @@ class FakeContext(object):
             rz = float(r.double() @ r.double())
         self.mailbox[off: off + 3] = [rz, alpha, pap]
 
+    # ---- CG with device-resident scalars: kry_cg_update_dev / kry_cg_scalars / kry_xpby_dev ----
+    @realviews
+    def cg_update_dev(self, Ap, p, yk, r, z, dinv, st):
+        self._count("cg_update_dev")
+        alpha = float(st[1]) / float(st[2])
+        yk.copy_((yk.double() + alpha * p.double()).to(yk.dtype))
+        r.copy_((r.double() - alpha * Ap.double()).to(r.dtype))
+        if dinv is not None:
+            z.copy_((dinv.double() * r.double()).to(z.dtype))
+            rz = float(r.double() @ z.double())
+        else:
+            rz = float(r.double() @ r.double())
+        st[3] = alpha
+        st[5] = rz
+
+    def cg_scalars(self, st, off=0):
+        self._count("cg_scalars")
+        s = float(st[5])
+        nrm = float(np.sqrt(abs(s)))
+        prev = float(st[1])
+        st[0] = prev
+        st[1] = nrm * nrm
+        st[4] = (nrm * nrm) / prev
+        self.mailbox[off: off + 3] = [s, float(st[3]), float(st[2])]
+
+    @realviews
+    def xpby_dev(self, x, beta, y, out):
+        self._count("xpby_dev")
+        out.copy_((x.double() + float(beta[0]) * y.double()).to(out.dtype))
+
 
 def install(monkeypatch):
     """swap the product's device context for the test double (pytest monkeypatch fixture)"""

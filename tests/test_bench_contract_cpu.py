@@ -86,7 +86,8 @@ def test_b200_arm_assembles_its_line_over_the_test_double(monkeypatch, capsys):
     real_empty = torch.empty
     monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
     args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", n=24, ortho="cgs",
-                                 no_cpu_baseline=False, no_e2e=False, cpu_iters=3)
+                                 no_cpu_baseline=False, no_e2e=False, cpu_iters=3, no_mgs=False,
+                                 no_extra_configs=True, ref_iters=3)
     bench.run_b200(args, 0, 1, 0)
     out = capsys.readouterr().out
     lines = [ln for ln in out.splitlines() if ln.strip().startswith("{")]
@@ -98,6 +99,7 @@ def test_b200_arm_assembles_its_line_over_the_test_double(monkeypatch, capsys):
     assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     assert "error" not in d["e2e"]["per_solve"] and 0 < d["e2e"]["per_solve"]["iterations_per_upload"] <= 150
     assert "error" not in d["e2e"]["breakdown_ms"] and d["e2e"]["breakdown_ms"]["total"] > 0
+    assert "error" not in d["mgs_value"] and d["mgs_value"]["value"] > 0
     assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] > 0
     assert d["parity_vs_cpu_max_rel"] < 1e-10           # product (over the double) vs oracle, same inputs
     assert fake.launch_count() > 0
@@ -117,3 +119,52 @@ def test_smoke_logic_over_the_test_double(monkeypatch, capsys):
     monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
     g.smoke()
     assert "smoke ok" in capsys.readouterr().out
+
+
+def _stub_cuda(monkeypatch):
+    import time
+
+    import torch
+
+    class Ev(object):
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t) + 1e-3
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+
+
+def test_named_configurations_dry_run_with_reference_parity(monkeypatch):
+    """bench_configs.run_device (C3, C4, C5) at toy sizes over the test double: the result keys the bench
+    line / profiles carry, and the parity leg against the host reference (the unmodified reference when
+    baseline/_ref exists, else the oracle port)."""
+    import bench_configs
+    import fake_device
+
+    fake_device.install(monkeypatch)
+    _stub_cuda(monkeypatch)
+    for name, n, steps, tol in (("c3", 10, 6, 1e-10), ("c5", 24, 6, 1e-4), ("c4", 24, 0, None)):
+        out = bench_configs.run_device(name, 6538.9, n=n, maxiter=30 if name == "c4" else 12, ref_steps=steps)
+        assert out["iterations"] > 0 and out["it_per_s"] > 0 and out["algorithmic_GBs"] > 0
+        assert 0 < out["frac_of_measured_peak"] and out["n_gpus"] == 1
+        if steps:
+            par = out["parity_vs_reference"]
+            assert par["entries"] == steps + 1 and par["reference_kind"] in ("reference", "port")
+            assert par["max_rel_updated"] <= tol, (name, par)
+        else:
+            assert out["projector_setup_s"] >= 0 and out["undeflated_it_per_s"] > 0
+    # the byte model reproduces SURVEY 8(d): 192 N (C3, fp64), 144 N (C5, fp32) up to boundary terms
+    N = 400 ** 3
+    assert abs(bench_configs.bytes_per_iteration("c3", N, 7 * N, 8) / N - 192.0) < 1e-6
+    N = 4000 ** 2
+    assert abs(bench_configs.bytes_per_iteration("c5", N, 5 * N, 4) / N - 144.0) < 1e-5

@@ -124,3 +124,45 @@ def test_ritz_pairs_host_logic(fake, name):
 def test_recycling_host_logic(fake, sname, which):
     import ritz_checks
     ritz_checks.check_recycling(sname, which)
+
+
+def test_gmres_step_limit_is_reported_up_front(fake):
+    """the single-CTA Givens recurrence caps a cycle at 2000 steps (complex: 1000): a larger maxiter
+    (the default is N) is refused before any work, with a pointer to RestartedGmres"""
+    import krypy_b200 as kp
+    import scipy.sparse as sp
+    N = 2500
+    ls = kp.linsys.LinearSystem(sp.identity(N, format="csr") * 2.0, np.ones(N))
+    with pytest.raises(kp.utils.ArgumentError, match="RestartedGmres"):
+        kp.linsys.Gmres(ls)                       # maxiter defaults to N = 2500 > 2000
+    with pytest.raises(kp.utils.ArgumentError):
+        kp.linsys.Gmres(kp.linsys.LinearSystem(sp.identity(N, format="csr") * (2.0 + 1j), np.ones(N)), maxiter=1001)
+    assert kp.linsys.Gmres(ls, maxiter=2000).resnorms[-1] <= 1e-5
+
+
+def test_no_reference_cycles_keep_device_memory_alive(fake):
+    """operators and finished solvers are freed by reference counting alone: a cycle would keep the CSR
+    matrix and the bases in HBM until Python's cyclic collector happens to run (found on the B200 as
+    sporadic 100 ms steps of the end-to-end bench)"""
+    import gc
+    import weakref
+    import krypy_b200 as kp
+    from krypy_b200 import problems
+    A, b = problems.laplace2d(12), problems.rhs_normal(144)
+    gc.collect()
+    gc.disable()
+    try:
+        refs = []
+        for make in (lambda ls: kp.linsys.Gmres(ls, maxiter=100, tol=1e-8, store_arnoldi=True),
+                     lambda ls: kp.linsys.Cg(ls, tol=1e-8, store_arnoldi=True),
+                     lambda ls: kp.linsys.Minres(ls, tol=1e-8),
+                     lambda ls: kp.deflation.DeflatedGmres(ls, U=np.eye(144, 2), tol=1e-8, store_arnoldi=True),
+                     lambda ls: kp.deflation.DeflatedCg(ls, U=np.eye(144, 2), tol=1e-8, store_arnoldi=True)):
+            ls = kp.linsys.LinearSystem(A, b, self_adjoint=True, positive_definite=True)
+            sol = make(ls)
+            getattr(sol, "V", None)
+            refs += [weakref.ref(sol), weakref.ref(ls), weakref.ref(ls.A)]
+            del sol, ls
+        assert all(r() is None for r in refs)
+    finally:
+        gc.enable()

@@ -428,3 +428,45 @@ def test_cg_update(ctx, n, use_d):
         np.testing.assert_allclose(zd.cpu().numpy(), z2, rtol=1e-12, atol=1e-14)
     np.testing.assert_allclose(ctx.mailbox[0], r2 @ z2, rtol=1e-12)
     np.testing.assert_allclose(ctx.mailbox[1], alpha, rtol=1e-15)
+
+
+@pytest.mark.parametrize("n", [3, 1000, 99991])
+@pytest.mark.parametrize("use_d", [False, True])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_cg_device_scalars_recurrence(ctx, n, use_d, dt):
+    """kry_cg_update_dev + kry_cg_scalars + kry_xpby_dev: one CG step whose scalars never leave the
+    device, against numpy with the same rounding points (linsys.py:627-665)"""
+    import torch
+    rng = np.random.default_rng(n + use_d)
+    p, Ap, yk, r, pold = (rng.standard_normal(n).astype(dt) for _ in range(5))
+    d = (np.abs(rng.standard_normal(n)) + 0.5).astype(dt)
+    rho, pap = 2.3, 0.7
+    st = torch.zeros(8, dtype=torch.float64, device=ctx.device)
+    st[1], st[2] = rho, pap
+    pd, Apd, ykd, rd = T(ctx, p), T(ctx, Ap), T(ctx, yk), T(ctx, r)
+    zd = ctx.empty((n,), tdt(dt))
+    ctx.cg_update_dev(Apd, pd, ykd, rd, zd if use_d else None, T(ctx, d) if use_d else None, st)
+    ctx.cg_scalars(st, 0)
+    out = ctx.empty((n,), tdt(dt))
+    ctx.xpby_dev(zd if use_d else rd, st[4:], T(ctx, pold), out)
+    ctx.sync()
+    alpha = rho / pap
+    f = np.float64
+    r2 = (r.astype(f) - alpha * Ap.astype(f)).astype(dt)
+    z2 = (d.astype(f) * r2.astype(f)).astype(dt) if use_d else r2
+    rt = 1e-12 if dt == np.float64 else 2e-6
+    np.testing.assert_allclose(ykd.cpu().numpy(), (yk.astype(f) + alpha * p.astype(f)).astype(dt), rtol=rt, atol=rt)
+    np.testing.assert_allclose(rd.cpu().numpy(), r2, rtol=rt, atol=rt)
+    s = float(r2.astype(f) @ z2.astype(f))
+    stt = st.cpu().numpy()
+    np.testing.assert_allclose(ctx.mailbox[0], s, rtol=1e-12 if dt == np.float64 else 1e-5)
+    assert stt[0] == rho and stt[3] == alpha == ctx.mailbox[1] and ctx.mailbox[2] == pap
+    raw = float(ctx.mailbox[0])
+    assert stt[1] == np.sqrt(abs(raw)) ** 2                      # the reference squares the norm
+    assert stt[4] == stt[1] / rho
+    want = ((z2.astype(f) + (stt[4] * pold.astype(f)))).astype(dt)          # numpy: z + (beta * p)
+    got = out.cpu().numpy()
+    if dt == np.float64:
+        assert np.array_equal(got, want)
+    else:
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)

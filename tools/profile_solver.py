@@ -21,7 +21,7 @@ import torch  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("config")
-    ap.add_argument("--n", type=int, default=0)
+    ap.add_argument("--grid", dest="n", type=int, default=0)
     ap.add_argument("--maxiter", type=int, default=50)
     ap.add_argument("--host", action="store_true", help="cProfile of the host layer instead of the kernel table")
     a = ap.parse_args()
