@@ -144,6 +144,18 @@ int kry_lanczos_diag_dist(kry_ctx* ctx, int dtype, long long n, const void* vpre
                           void* vnext, int world, int rank, unsigned long long* epoch_dev,
                           double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 
+/* ---- block kernels for the projector set-up (CholQR2) ------------------------------------ */
+/* kry_gram: out_dev[i*ky + j] = <X_i, Y_j> (Euclidean, fp64 accumulation) for a block X of kx and a
+ * block Y of ky vectors in ONE pass over both (krypy/utils.py:160-193 inner() with m, n > 1, as used
+ * by qr / Projection.__init__ / Ritz); kx + ky <= 64 (kx when Y == X), ceil(kx/4)*ceil(ky/4) <= 32.
+ * kry_block_trsm: Q = X R^-1 for an upper triangular d x d R_dev (row-major, d <= 32), vector-major
+ * blocks, Q may alias X: the second half of a Cholesky-QR round (replaces the column-by-column
+ * Gram-Schmidt of krypy/utils.py:698-706 for full-rank blocks). */
+int kry_gram(kry_ctx* ctx, int dtype, long long n, const void* X, long long ldx, int kx, const void* Y,
+             long long ldy, int ky, double* out_dev);
+int kry_block_trsm(kry_ctx* ctx, int dtype, long long n, const void* X, long long ldx, int d,
+                   const double* R_dev, void* Q, long long ldq);
+
 /* ---- oblique projection for deflation (one cooperative kernel) ---------- */
 /* a <- (I - V (R^-1 Q^H) W^H)^iterations a  (krypy/utils.py:604-627 with
  * :522-552; called from deflation.py:135-143).  W, V: d vectors each; Q, R:

@@ -537,3 +537,20 @@ class Context(object):
         """out = x + beta[0] * y with beta in device memory"""
         check(self.lib.kry_xpby_dev(self.h, code(x), x.numel(), x.data_ptr(), beta.data_ptr(), y.data_ptr(),
                                     out.data_ptr()))
+
+    # ---- block kernels (projector set-up) -----------------------------------------
+    @staticmethod
+    def gram_fits(kx, ky, same):
+        return ((kx if same else kx + ky) <= 64) and ((kx + 3) // 4) * ((ky + 3) // 4) <= 32
+
+    @realviews
+    def gram(self, X, kx, Y, ky, out):
+        """out[i*ky + j] = <X_i, Y_j> in one pass over both blocks (kry_gram)"""
+        check(self.lib.kry_gram(self.h, code(X), X.shape[1], X.data_ptr(), X.stride(0), int(kx), Y.data_ptr(),
+                                Y.stride(0), int(ky), out.data_ptr()))
+
+    @realviews
+    def block_trsm(self, X, d, R, Q):
+        """Q = X R^-1 (R upper triangular d x d device matrix, row-major); Q may be X"""
+        check(self.lib.kry_block_trsm(self.h, code(X), X.shape[1], X.data_ptr(), X.stride(0), int(d), R.data_ptr(),
+                                      Q.data_ptr(), Q.stride(0)))

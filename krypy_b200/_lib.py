@@ -55,6 +55,8 @@ PROTOTYPES = {
                                  c_void_p, c_void_p]),
     "kry_lanczos_diag_dist": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                       c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kry_gram": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_ll, c_int, c_void_p]),
+    "kry_block_trsm": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_ll]),
     "kry_project": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_ll, c_int, c_void_p,
                             c_void_p, c_void_p, c_int, c_void_p]),
     "kry_givens_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),

@@ -1,0 +1,215 @@
+// Block (tall-skinny) kernels for the set-up of the deflation projector (krypy/utils.py:680-707 qr,
+// :440-520 Projection.__init__, deflation.py:33-56): the reference orthonormalises an (N, d) block
+// column by column (LAPACK QR or Python MGS: d^2 dependent reductions).  Here a block is
+// orthonormalised by CholQR2 -- two rounds of  G = X^H X (ONE pass over the block),  R = chol(G) on
+// the host (d x d),  X <- X R^-1 (one read + one write of the block) -- i.e. six block passes and
+// two host synchronisations instead of d(d+1) dependent sweeps.
+//
+//   kry_gram        C = X^H Y for kx x ky <= 512 outputs in one pass over X and Y: 128-row chunks of
+//                   all vectors are staged in shared memory, every warp owns up to two 4x4 output
+//                   blocks in registers (two rows per lane and step: 8 LDS.128 feed 32 FMAs),
+//                   deterministic reduction (shuffle tree, per-CTA partials, last CTA sums in order)
+//   kry_block_trsm  Q = X R^-1, R upper triangular d x d (d <= 32): one thread per row, the row of X
+//                   in registers, forward substitution against R in shared memory
+// Both are bandwidth-sized (3.2 GFLOP on 0.64 GB at N = 4M, d = 20); no tensor cores: fp64.
+#include "kry_common.cuh"
+
+#define KRY_ENTER(ctx)                                                         \
+    KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
+    KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
+
+#define GRAM_E 128        // rows per staged chunk
+#define GRAM_LD 130       // shared-memory row stride (doubles): 16-byte aligned rows, skewed banks
+#define GRAM_MAXV 64      // kx + ky (or kx when Y == X) staged vectors at most
+#define GRAM_BPW 2        // 4x4 output blocks per warp
+#define GRAM_THREADS 512  // 16 warps x 2 blocks: up to 32 blocks = 512 outputs (e.g. 20 x 20)
+
+template <typename T>
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
+gram_kernel(long long n, const T* __restrict__ X, long long ldx, int kx, const T* __restrict__ Y, long long ldy, int ky,
+            int same, double* partials, unsigned int* ticket, double* out) {
+    extern __shared__ double sh[];               // [nvec][GRAM_LD]
+    __shared__ bool last;
+    const int nvec = same ? kx : kx + ky;
+    double* sx = sh;
+    double* sy = same ? sh : sh + (size_t)kx * GRAM_LD;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = GRAM_THREADS >> 5;
+    const int nbx = (kx + 3) >> 2, nby = (ky + 3) >> 2, nb = nbx * nby;
+    double acc[GRAM_BPW][16];
+#pragma unroll
+    for (int b = 0; b < GRAM_BPW; ++b)
+#pragma unroll
+        for (int t = 0; t < 16; ++t) acc[b][t] = 0.0;
+    const long long nchunks = (n + GRAM_E - 1) / GRAM_E;
+    for (long long c = blockIdx.x; c < nchunks; c += gridDim.x) {
+        const long long r0 = c * GRAM_E;
+        const int rows = (int)((n - r0) < GRAM_E ? (n - r0) : GRAM_E);
+        __syncthreads();                          // previous chunk fully consumed
+        // stage: vector v, row e  <-  (v < kx ? X[v] : Y[v - kx])[r0 + e]   (zero padded)
+        for (int idx = threadIdx.x; idx < nvec * GRAM_E; idx += GRAM_THREADS) {
+            const int v = idx / GRAM_E, e = idx - v * GRAM_E;
+            double val = 0.0;
+            if (e < rows) {
+                const T* src = (v < kx) ? (X + (long long)v * ldx) : (Y + (long long)(v - kx) * ldy);
+                val = (double)__ldg(src + r0 + e);
+            }
+            sh[(size_t)v * GRAM_LD + e] = val;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int bi = 0; bi < GRAM_BPW; ++bi) {
+            const int b = w + bi * nw;
+            if (b < nb) {                         // uniform per warp
+                const int a0 = (b / nby) << 2, b0 = (b % nby) << 2;
+#pragma unroll
+                for (int step = 0; step < GRAM_E / 64; ++step) {
+                    const int e = (step << 6) + (lane << 1);
+                    double2 xa[4], yb[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        const int va = a0 + i < kx ? a0 + i : kx - 1;        // (clamped rows are discarded below)
+                        const int vb = b0 + i < ky ? b0 + i : ky - 1;
+                        xa[i] = *reinterpret_cast<const double2*>(sx + (size_t)va * GRAM_LD + e);
+                        yb[i] = *reinterpret_cast<const double2*>(sy + (size_t)vb * GRAM_LD + e);
+                    }
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            acc[bi][i * 4 + j] = fma(xa[i].x, yb[j].x, acc[bi][i * 4 + j]);
+                            acc[bi][i * 4 + j] = fma(xa[i].y, yb[j].y, acc[bi][i * 4 + j]);
+                        }
+                }
+            }
+        }
+    }
+    // per-CTA partials: partials[blockIdx][kx*ky]
+    double* mine = partials + (size_t)blockIdx.x * (size_t)(kx * ky);
+#pragma unroll
+    for (int bi = 0; bi < GRAM_BPW; ++bi) {
+        const int b = w + bi * nw;
+        if (b < nb) {
+            const int a0 = (b / nby) << 2, b0 = (b % nby) << 2;
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                const double s = kry_warp_sum(acc[bi][t]);
+                const int i = a0 + (t >> 2), j = b0 + (t & 3);
+                if (lane == 0 && i < kx && j < ky) mine[i * ky + j] = s;
+            }
+        }
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(ticket, 1u);
+        last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (last) {
+        __threadfence();
+        for (int o = threadIdx.x; o < kx * ky; o += GRAM_THREADS) {
+            double s = 0.0;
+            for (int b = 0; b < (int)gridDim.x; ++b) s += __ldcg(partials + (size_t)b * (size_t)(kx * ky) + o);   // fixed order
+            out[o] = s;
+        }
+        if (threadIdx.x == 0) *ticket = 0u;
+    }
+}
+
+// Q[j] = (X[j] - sum_{l<j} R[l][j] Q[l]) / R[j][j], row by row of the (vector-major) block
+template <typename T, int DMAX>
+__global__ void __launch_bounds__(KRY_THREADS)
+block_trsm_kernel(long long n, const T* X, long long ldx, int d, const double* __restrict__ R, T* Q, long long ldq) {
+    __shared__ double Rs[DMAX * DMAX];
+    for (int i = threadIdx.x; i < d * d; i += blockDim.x) Rs[i] = R[i];
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        double q[DMAX];
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+            if (j < d) q[j] = (double)X[(long long)j * ldx + i];
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j) {
+            if (j < d) {
+                double s = q[j];
+#pragma unroll
+                for (int l = 0; l < DMAX; ++l)
+                    if (l < j) s = fma(-Rs[l * d + j], q[l], s);
+                q[j] = (double)(T)(s / Rs[j * d + j]);          // value as stored
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < DMAX; ++j)
+            if (j < d) Q[(long long)j * ldq + i] = (T)q[j];
+    }
+}
+
+template <typename T>
+static int gram_launch(kry_ctx* ctx, long long n, const T* X, long long ldx, int kx, const T* Y, long long ldy,
+                       int ky, int same, double* out) {
+    const int nvec = same ? kx : kx + ky;
+    const size_t smem = sizeof(double) * (size_t)nvec * GRAM_LD;
+    auto kern = gram_kernel<T>;
+    static thread_local size_t smem_set[16] = {0};
+    size_t& cur = smem_set[ctx->device & 15];
+    if (smem > cur) {
+        KRY_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cur = smem;
+    }
+    int occ = 0;
+    KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, GRAM_THREADS, smem));
+    KRY_REQUIRE(occ >= 1, "gram kernel does not fit on an SM");
+    long long nchunks = (n + GRAM_E - 1) / GRAM_E;
+    long long cap = (long long)ctx->sm_count * occ;
+    const long long pcap = (2LL * KRY_MAX_SLOTS * KRY_MAX_PARTIAL_BLOCKS) / ((long long)kx * ky);   // scratch doubles
+    if (cap > pcap) cap = pcap;
+    int g = (int)(nchunks < cap ? nchunks : cap);
+    if (g < 1) g = 1;
+    kern<<<g, GRAM_THREADS, smem, ctx->stream>>>(n, X, ldx, kx, Y, ldy, ky, same, ctx->d_partials, ctx->d_ticket + 12, out);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+template <typename T>
+static int trsm_launch(kry_ctx* ctx, long long n, const T* X, long long ldx, int d, const double* R, T* Q, long long ldq) {
+    long long need = (n + KRY_THREADS - 1) / KRY_THREADS;
+    long long cap = (long long)ctx->sm_count * 4;
+    int g = (int)(need < cap ? need : cap);
+    if (g < 1) g = 1;
+    if (d <= 8) block_trsm_kernel<T, 8><<<g, KRY_THREADS, 0, ctx->stream>>>(n, X, ldx, d, R, Q, ldq);
+    else if (d <= 16) block_trsm_kernel<T, 16><<<g, KRY_THREADS, 0, ctx->stream>>>(n, X, ldx, d, R, Q, ldq);
+    else if (d <= 24) block_trsm_kernel<T, 24><<<g, KRY_THREADS, 0, ctx->stream>>>(n, X, ldx, d, R, Q, ldq);
+    else block_trsm_kernel<T, 32><<<g, KRY_THREADS, 0, ctx->stream>>>(n, X, ldx, d, R, Q, ldq);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+extern "C" {
+
+int kry_gram(kry_ctx* ctx, int dtype, long long n, const void* X, long long ldx, int kx, const void* Y, long long ldy,
+             int ky, double* out_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && kx >= 1 && ky >= 1 && X && Y && out_dev, "bad arguments");
+    const int same = (X == Y && ldx == ldy && kx == ky) ? 1 : 0;
+    KRY_REQUIRE((same ? kx : kx + ky) <= GRAM_MAXV, "too many vectors for one call (kx + ky <= 64)");
+    KRY_REQUIRE(((kx + 3) / 4) * ((ky + 3) / 4) <= GRAM_BPW * (GRAM_THREADS / 32), "kx x ky too large for one call");
+    if (dtype == KRY_F64)
+        return gram_launch<double>(ctx, n, (const double*)X, ldx, kx, (const double*)Y, ldy, ky, same, out_dev);
+    if (dtype == KRY_F32)
+        return gram_launch<float>(ctx, n, (const float*)X, ldx, kx, (const float*)Y, ldy, ky, same, out_dev);
+    kry_set_error("kry_gram: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+int kry_block_trsm(kry_ctx* ctx, int dtype, long long n, const void* X, long long ldx, int d, const double* R_dev,
+                   void* Q, long long ldq) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && d >= 1 && d <= 32 && X && R_dev && Q, "bad arguments (1 <= d <= 32)");
+    if (dtype == KRY_F64) return trsm_launch<double>(ctx, n, (const double*)X, ldx, d, R_dev, (double*)Q, ldq);
+    if (dtype == KRY_F32) return trsm_launch<float>(ctx, n, (const float*)X, ldx, d, R_dev, (float*)Q, ldq);
+    kry_set_error("kry_block_trsm: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

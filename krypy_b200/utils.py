@@ -881,6 +881,12 @@ def _inner_dev(Xd, Yd, ip_B=None, out=None):
         else:
             Yd = B._apply_dev(Yd)
     if not cplx:
+        if (m > 1 and n > 1 and ctx.comm is None and Xd.dtype == Yd.dtype and Xd.shape[1] >= _BLOCK_MIN_N
+                and ctx.gram_fits(m, n, Xd.data_ptr() == Yd.data_ptr() and m == n)):
+            # block x block: ONE pass over both blocks (kry_gram) instead of n passes over X
+            G = ctx.scalars(m * n)
+            ctx.gram(Xd, m, Yd, n, G)
+            return G.reshape(m, n)
         for j in range(n):
             ctx.block_dot(Xd, m, Yd[j], out[j])
         return out.t()
@@ -1119,6 +1125,10 @@ def _qr_dev(Xd, ip_B=None, reorthos=1):
     k, N = Xd.shape
     if _is_cplx(Xd):
         return _qr_dev_z(ctx, Xd, ip_B, reorthos)
+    if _CHOLQR and 2 <= k <= 32 and N >= _BLOCK_MIN_N and ctx.comm is None and _is_identity_ip(ip_B):
+        res = _cholqr2(ctx, Xd)
+        if res is not None:
+            return res
     ld = (N + 31) // 32 * 32
     store = ctx.empty((max(k, 1), ld), Xd.dtype)
     Q = store[:k, :N]
@@ -1143,6 +1153,47 @@ def _qr_dev(Xd, ip_B=None, reorthos=1):
         R[: i + 1, i] = col
         if R[i, i] >= 1e-15:                                        # utils.py:705-706
             ctx.scale_dev(Rrows[i][i:], 1, 1.0, qi, qi)
+    return Q, R
+
+
+_CHOLQR = __import__("os").environ.get("KRY_CHOLQR", "1") not in ("0", "")
+# the one-pass block kernels (kry_gram, CholQR2) take over from the vector-by-vector sequences at
+# sizes where a pass over the block costs more than a launch; below, the r1-validated paths stay
+_BLOCK_MIN_N = int(__import__("os").environ.get("KRY_BLOCK_MIN_N", "4096"))
+
+
+def _cholqr2(ctx, Xd):
+    """Orthonormalise the (k, N) device block by two rounds of Cholesky QR (Euclidean inner product):
+    G = X^H X in one pass (kry_gram), R = chol(G) on the host, X <- X R^-1 (kry_block_trsm).  Six
+    block passes and two host synchronisations instead of the k(k+1) dependent sweeps of the
+    column-by-column Gram-Schmidt (krypy/utils.py:698-706; 67 % of the reference's deflated solve,
+    SURVEY F4).  Same factorisation as MGS up to round-off (R has a positive diagonal).  Returns None
+    -- the caller falls back to the reference's MGS, which also implements its rank-deficiency rule
+    (utils.py:705-706) -- when the block is numerically rank deficient or too ill-conditioned for
+    CholQR2 (kappa(X) >~ 1e6)."""
+    t = _device.torch()
+    k, N = Xd.shape
+    ld = (N + 31) // 32 * 32
+    store = ctx.empty((k, ld), Xd.dtype)
+    Q = store[:, :N]
+    Q.copy_(Xd)
+    G = ctx.scalars(k * k)
+    R = numpy.eye(k)
+    for rnd in range(2):
+        ctx.gram(Q, k, Q, k, G)
+        Gh = G.cpu().numpy().reshape(k, k).copy()               # synchronises
+        Gh = 0.5 * (Gh + Gh.T)
+        if not numpy.all(numpy.isfinite(Gh)):
+            return None
+        try:
+            Rr = numpy.linalg.cholesky(Gh).T
+        except numpy.linalg.LinAlgError:
+            return None
+        dg = numpy.diag(Rr)
+        if dg.min() <= (1e-6 if rnd == 0 else 0.5) * dg.max():
+            return None
+        ctx.block_trsm(Q, k, t.from_numpy(numpy.ascontiguousarray(Rr)).to(ctx.device), Q)
+        R = Rr.dot(R)
     return Q, R
 
 

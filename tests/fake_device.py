@@ -404,6 +404,25 @@ class FakeContext(object):
         self._count("xpby_dev")
         out.copy_((x.double() + float(beta[0]) * y.double()).to(out.dtype))
 
+    # ---- kry_gram / kry_block_trsm ----
+    @staticmethod
+    def gram_fits(kx, ky, same):
+        return ((kx if same else kx + ky) <= 64) and ((kx + 3) // 4) * ((ky + 3) // 4) <= 32
+
+    @realviews
+    def gram(self, X, kx, Y, ky, out):
+        self._count("gram")
+        G = X[:kx].double() @ Y[:ky].double().T
+        out[: kx * ky].copy_(G.reshape(-1))
+
+    @realviews
+    def block_trsm(self, X, d, R, Q):
+        self._count("block_trsm")
+        import scipy.linalg
+        Rm = R[: d * d].reshape(d, d).numpy()
+        Qn = scipy.linalg.solve_triangular(Rm, X[:d].double().numpy(), trans="T", lower=False)
+        Q[:d].copy_(torch.from_numpy(np.ascontiguousarray(Qn)).to(Q.dtype))
+
 
 def install(monkeypatch):
     """swap the product's device context for the test double (pytest monkeypatch fixture)"""

@@ -166,3 +166,42 @@ def test_no_reference_cycles_keep_device_memory_alive(fake):
         assert all(r() is None for r in refs)
     finally:
         gc.enable()
+
+
+def check_cholqr2_against_mgs(kp, N=300, k=7, seed=4):
+    """utils.qr by CholQR2 (block kernels) against the column-by-column MGS path: same factorisation up to
+    round-off; rank-deficient and ill-conditioned blocks fall back to MGS (utils.py:705-706 rule)"""
+    u = kp.utils
+    rng = np.random.default_rng(seed)
+    X = rng.standard_normal((N, k)) @ np.triu(rng.standard_normal((k, k)) + 3 * np.eye(k))
+    old = u._BLOCK_MIN_N
+    try:
+        u._BLOCK_MIN_N = 0
+        Q, R = u.qr(X)
+        u._BLOCK_MIN_N = 10 ** 9
+        Q0, R0 = u.qr(X)
+        np.testing.assert_allclose(Q.T @ Q, np.eye(k), atol=5e-15 * k)
+        np.testing.assert_allclose(Q @ R, X, rtol=0, atol=1e-13 * np.abs(X).max() * k)
+        assert np.allclose(np.tril(R, -1), 0) and np.all(np.diag(R) > 0)
+        np.testing.assert_allclose(R, R0, rtol=0, atol=1e-12 * np.abs(R0).max())
+        np.testing.assert_allclose(Q, Q0, rtol=0, atol=1e-11)
+        # block inner products through the one-pass Gram kernel
+        u._BLOCK_MIN_N = 0
+        Y = rng.standard_normal((N, 5))
+        np.testing.assert_allclose(u.inner(X, Y), X.T @ Y, rtol=0, atol=1e-13 * (np.abs(X).T @ np.abs(Y)).max())
+        np.testing.assert_allclose(u.inner(X, X), X.T @ X, rtol=0, atol=1e-13 * (np.abs(X).T @ np.abs(X)).max())
+        # rank deficient: the MGS fallback leaves the dependent column un-normalised like the reference
+        Xd = X.copy()
+        Xd[:, 3] = Xd[:, 1] * 2.0
+        Qd, Rd = u.qr(Xd)
+        u._BLOCK_MIN_N = 10 ** 9
+        Qd0, Rd0 = u.qr(Xd)
+        np.testing.assert_allclose(Rd, Rd0, rtol=0, atol=1e-10 * np.abs(Rd0).max())
+    finally:
+        u._BLOCK_MIN_N = old
+
+
+def test_cholqr2_host_logic(fake):
+    import krypy_b200 as kp
+    check_cholqr2_against_mgs(kp)
+    assert fake.calls.get("gram", 0) >= 4 and fake.calls.get("block_trsm", 0) >= 2

@@ -464,9 +464,48 @@ def test_cg_device_scalars_recurrence(ctx, n, use_d, dt):
     raw = float(ctx.mailbox[0])
     assert stt[1] == np.sqrt(abs(raw)) ** 2                      # the reference squares the norm
     assert stt[4] == stt[1] / rho
-    want = ((z2.astype(f) + (stt[4] * pold.astype(f)))).astype(dt)          # numpy: z + (beta * p)
+    zin = (zd if use_d else rd).cpu().numpy()                               # (the device's own z: r used an FMA)
+    want = ((zin.astype(f) + (stt[4] * pold.astype(f)))).astype(dt)         # numpy: z + (beta * p)
     got = out.cpu().numpy()
     if dt == np.float64:
         assert np.array_equal(got, want)
     else:
         np.testing.assert_allclose(got, want, rtol=2e-6, atol=2e-6)
+
+
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+@pytest.mark.parametrize("n,kx,ky", [(1, 2, 2), (127, 3, 5), (4099, 20, 20), (70001, 7, 32), (33000, 32, 4)])
+def test_gram_and_block_trsm(ctx, dt, n, kx, ky):
+    """kry_gram (X^H Y and X^H X in one pass) and kry_block_trsm (X R^-1) against numpy/scipy"""
+    import scipy.linalg
+    import torch
+    rng = np.random.default_rng(n + kx)
+    Xh, X = basis(ctx, rng, kx, n, dt)
+    Yh, Y = basis(ctx, rng, ky, n, dt)
+    out = torch.zeros(kx * ky, dtype=torch.float64, device=ctx.device)
+    ctx.gram(X, kx, Y, ky, out)
+    ref = Xh.astype(np.float64) @ Yh.astype(np.float64).T
+    scale = np.abs(Xh).astype(np.float64) @ np.abs(Yh).astype(np.float64).T + 1e-300
+    assert np.all(np.abs(out.cpu().numpy().reshape(kx, ky) - ref) <= 1e-14 * scale * max(np.log2(n + 1), 1))
+    out2 = torch.zeros(kx * kx, dtype=torch.float64, device=ctx.device)
+    ctx.gram(X, kx, X, kx, out2)                                  # same-block (syrk-like) staging
+    G = out2.cpu().numpy().reshape(kx, kx)
+    ref2 = Xh.astype(np.float64) @ Xh.astype(np.float64).T
+    assert np.all(np.abs(G - ref2) <= 1e-14 * (np.abs(Xh).astype(np.float64) @ np.abs(Xh).astype(np.float64).T + 1e-300)
+                  * max(np.log2(n + 1), 1))
+    assert np.array_equal(out2.cpu().numpy(), ctx_gram_again(ctx, X, kx))      # deterministic
+    R = np.triu(rng.standard_normal((kx, kx))) + 4.0 * np.eye(kx)
+    Q = ctx.zeros(tuple(X.shape), tdt(dt))
+    ctx.block_trsm(X, kx, T(ctx, R), Q)
+    want = scipy.linalg.solve_triangular(R, Xh.astype(np.float64), trans="T", lower=False)
+    np.testing.assert_allclose(Q.cpu().numpy(), want.astype(dt), rtol=RT64 * 100 if dt == np.float64 else RT32 * 10,
+                               atol=(1e-12 if dt == np.float64 else 1e-5) * np.abs(want).max())
+    ctx.block_trsm(X, kx, T(ctx, R), X)                           # in place
+    assert np.array_equal(X.cpu().numpy(), Q.cpu().numpy())
+
+
+def ctx_gram_again(ctx, X, kx):
+    import torch
+    o = torch.zeros(kx * kx, dtype=torch.float64, device=ctx.device)
+    ctx.gram(X, kx, X, kx, o)
+    return o.cpu().numpy()

@@ -284,3 +284,37 @@ def test_restarted_gmres_preconditioned_graph_replay(graphs):
         except ko.OracleConvergenceError as e:
             ref = e.result
     _check_history(np.array(sol.resnorms), np.array(ref.resnorms))
+
+
+def test_cholqr2_projector_setup_matches_mgs():
+    """CholQR2 set-up of the deflation projector (kry_gram + kry_block_trsm, sizes >= 4096) against the
+    column-by-column MGS path: factorisation, and the deflated history at the 1e-10 contract"""
+    import krypy_b200 as kp
+    from krypy_b200 import problems
+    import test_host_logic_cpu
+    test_host_logic_cpu.check_cholqr2_against_mgs(kp, N=5000, k=20)
+    n = 96
+    A = problems.convdiff2d(n, c=0.1)
+    N = n * n
+    b = np.ones((N, 1))
+    xs = np.arange(1, n + 1) / (n + 1.0)
+    U = np.stack([np.outer(np.sin(p * np.pi * xs), np.sin(q * np.pi * xs)).reshape(-1)
+                  for p in range(1, 4) for q in range(1, 4)], axis=1)
+    hist = {}
+    old = kp.utils._BLOCK_MIN_N
+    try:
+        for name, thr in (("cholqr2", 0), ("mgs", 10 ** 9)):
+            kp.utils._BLOCK_MIN_N = thr
+            ls = kp.linsys.LinearSystem(A, b)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                try:
+                    s = kp.deflation.DeflatedGmres(ls, U=U, maxiter=40, tol=1e-12)
+                except kp.utils.ConvergenceError as e:
+                    s = e.solver
+            hist[name] = (np.array(s.resnorms), s.E, s.UMlr)
+    finally:
+        kp.utils._BLOCK_MIN_N = old
+    _check_history(hist["cholqr2"][0], hist["mgs"][0])
+    np.testing.assert_allclose(hist["cholqr2"][1], hist["mgs"][1], rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(hist["cholqr2"][2], hist["mgs"][2], rtol=1e-9, atol=1e-12)
