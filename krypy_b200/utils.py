@@ -1125,7 +1125,8 @@ def _qr_dev(Xd, ip_B=None, reorthos=1):
     k, N = Xd.shape
     if _is_cplx(Xd):
         return _qr_dev_z(ctx, Xd, ip_B, reorthos)
-    if _CHOLQR and 2 <= k <= 32 and N >= _BLOCK_MIN_N and ctx.comm is None and _is_identity_ip(ip_B):
+    if (_CHOLQR and 2 <= k <= 32 and N >= _BLOCK_MIN_N and ctx.comm is None and _is_identity_ip(ip_B)
+            and ctx.gram_fits(k, k, True)):
         res = _cholqr2(ctx, Xd)
         if res is not None:
             return res
