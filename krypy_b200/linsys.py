@@ -278,33 +278,35 @@ def _norm_dev(xd, yd, ip_B):
 
 
 class TimedLinearSystem(LinearSystem):
-    """krypy/linsys.py:204-252."""
+    """A linear system that times every application of its operators and of the inner product
+    (``timings['A' | 'M' | 'Minv' | 'Ml' | 'Mr' | 'ip_B']``, per vector; krypy/linsys.py:204-252).  The
+    timers are CUDA-event based (utils.Timer): no host synchronisation per application."""
+
+    _TIMED = ("A", "M", "Minv", "Ml", "Mr")
 
     def __init__(self, A, b, M=None, Minv=None, Ml=None, Mr=None, ip_B=None, normal=None,
                  self_adjoint=False, positive_definite=False, exact_solution=None, dtype=None):
-        self.timings = utils.Timings()
-        N = len(b)
-        shape = (N, N)
+        self.timings = tm = utils.Timings()
+        shape = (len(b), len(b))
+        ops = dict(A=A, M=M, Minv=Minv, Ml=Ml, Mr=Mr)
+        timed = {name: utils.get_linearoperator(shape, ops[name], timer=tm[name]) for name in self._TIMED}
         try:
-            _ip_B = utils.get_linearoperator(shape, ip_B, timer=self.timings["ip_B"])
+            timed_ip = utils.get_linearoperator(shape, ip_B, timer=tm["ip_B"])
         except TypeError:
-            def _ip_B(X, Y):
-                (_, m) = X.shape
-                (_, n) = Y.shape
-                if m == 0 or n == 0:
+            timer = tm["ip_B"]
+
+            def timed_ip(X, Y):
+                # callable inner product: time per entry of the (m, n) result
+                entries = X.shape[1] * Y.shape[1]
+                if entries == 0:
                     return ip_B(X, Y)
-                with self.timings["ip_B"]:
-                    ret = ip_B(X, Y)
-                self.timings["ip_B"][-1] /= m * n
-                return ret
+                with timer:
+                    G = ip_B(X, Y)
+                timer.scale_last(1.0 / entries)
+                return G
         super(TimedLinearSystem, self).__init__(
-            A=utils.get_linearoperator(shape, A, self.timings["A"]), b=b,
-            M=utils.get_linearoperator(shape, M, self.timings["M"]),
-            Minv=utils.get_linearoperator(shape, Minv, self.timings["Minv"]),
-            Ml=utils.get_linearoperator(shape, Ml, self.timings["Ml"]),
-            Mr=utils.get_linearoperator(shape, Mr, self.timings["Mr"]),
-            ip_B=_ip_B, normal=normal, self_adjoint=self_adjoint,
-            positive_definite=positive_definite, exact_solution=exact_solution, dtype=dtype)
+            b=b, ip_B=timed_ip, normal=normal, self_adjoint=self_adjoint, positive_definite=positive_definite,
+            exact_solution=exact_solution, dtype=dtype, **timed)
 
 
 class ConvertedTimedLinearSystem(TimedLinearSystem):

@@ -722,77 +722,121 @@ class DeviceLinearOperator(_DeviceOperator):
 
 
 class Timer(list):
-    """krypy/utils.py:1289-1318 (wall-clock, synchronises the device on exit so
-    the measured block includes the kernels it launched)."""
+    """``with timer: ...`` appends the duration of the block in seconds (krypy/utils.py:1289-1318).
+
+    On the device path a block is bracketed by two CUDA events recorded on the current stream and the
+    duration is read back LAZILY -- when the list is looked at -- so timing an operator application
+    costs two event records and no host synchronisation (the reference's wall clock would need a
+    device synchronise per application to mean anything here).  For host-only blocks on an idle
+    stream the two event time stamps are host times, i.e. the wall-clock duration.  Without a CUDA
+    device the wall clock is used."""
+
+    def __init__(self):
+        super(Timer, self).__init__()
+        self._open = None
+        self._pending = []           # [index, start event, end event, factor]
 
     def __enter__(self):
-        self.tstart = time.time()
+        t = _device._torch
+        if t is not None and t.cuda.is_available():
+            e0 = t.cuda.Event(enable_timing=True)
+            e0.record()
+            self._open = e0
+        else:
+            self._open = time.time()
 
     def __exit__(self, a, b, c):
-        if _device._torch is not None and _device._torch.cuda.is_available():
-            _device._torch.cuda.synchronize()
-        self.append(time.time() - self.tstart)
+        start, self._open = self._open, None
+        if isinstance(start, float):
+            list.append(self, time.time() - start)
+            return
+        e1 = _device._torch.cuda.Event(enable_timing=True)
+        e1.record()
+        self._pending.append([list.__len__(self), start, e1, 1.0])
+        list.append(self, float("nan"))
+
+    def scale_last(self, factor):
+        """multiply the most recent entry by ``factor`` (per-vector time of a block application)
+        without forcing its read-back"""
+        n = list.__len__(self)
+        if self._pending and self._pending[-1][0] == n - 1:
+            self._pending[-1][3] *= factor
+        elif n:
+            list.__setitem__(self, n - 1, list.__getitem__(self, n - 1) * factor)
+
+    def _resolve(self):
+        if self._pending:
+            pend, self._pending = self._pending, []
+            pend[-1][2].synchronize()
+            for idx, e0, e1, f in pend:
+                list.__setitem__(self, idx, 1e-3 * e0.elapsed_time(e1) * f)
+
+    def __getitem__(self, i):
+        self._resolve()
+        return list.__getitem__(self, i)
+
+    def __iter__(self):
+        self._resolve()
+        return list.__iter__(self)
+
+    def __repr__(self):
+        self._resolve()
+        return list.__repr__(self)
+
+    def __eq__(self, other):
+        self._resolve()
+        return list.__eq__(self, other)
+
+    __hash__ = None
 
 
 class Timings(defaultdict):
-    """krypy/utils.py:1321-1362."""
+    """A dictionary of timers keyed by operation name; ``get`` = the best (minimal) time seen
+    (krypy/utils.py:1321-1362)."""
 
     def __init__(self):
         super(Timings, self).__init__(Timer)
 
     def get(self, key):
-        if key in self and len(self[key]) > 0:
-            return min(self[key])
-        return 0
+        times = list(self[key]) if key in self else []
+        return min(times) if times else 0
 
     def get_ops(self, ops):
-        t = 0.0
-        for op, count in ops.items():
-            t += self.get(op) * count
-        return t
+        """total time of ``{operation: number of applications}``"""
+        return float(sum(self.get(op) * count for op, count in ops.items()))
 
     def __repr__(self):
-        return "Timings(" + ", ".join(["%s: %s" % (key, self.get(key)) for key in self]) + ")"
+        return "Timings(" + ", ".join("%s: %s" % (key, self.get(key)) for key in self) + ")"
 
 
 class TimedLinearOperator(LinearOperator):
-    """krypy/utils.py:1605-1636."""
+    """A linear operator whose applications are timed per vector (krypy/utils.py:1605-1636): the host
+    entry points (``dot``, ``dot_adj``) and the device entry point the solvers use (``_apply_dev``)
+    go through the same bracket."""
 
     def __init__(self, linear_operator, timer=None):
-        self._linear_operator = linear_operator
-        super(TimedLinearOperator, self).__init__(
-            shape=linear_operator.shape, dtype=linear_operator.dtype,
-            dot=linear_operator.dot, dot_adj=linear_operator.dot_adj)
-        if timer is None:
-            timer = Timer()
-        self._timer = timer
+        self._linear_operator = op = linear_operator
+        super(TimedLinearOperator, self).__init__(shape=op.shape, dtype=op.dtype, dot=op.dot, dot_adj=op.dot_adj)
+        self._timer = Timer() if timer is None else timer
+
+    def _timed(self, nvec, fn, *args, **kwargs):
+        if nvec == 0:
+            return fn(*args, **kwargs)
+        with self._timer:
+            ret = fn(*args, **kwargs)
+        self._timer.scale_last(1.0 / nvec)
+        return ret
 
     def dot(self, X):
-        k = X.shape[1]
-        if k == 0:
-            return self._linear_operator.dot(X)
-        with self._timer:
-            ret = self._linear_operator.dot(X)
-        self._timer[-1] /= k
-        return ret
+        return self._timed(X.shape[1], self._linear_operator.dot, X)
 
     def dot_adj(self, X):
-        k = X.shape[1]
-        if k == 0:
-            return self._linear_operator.dot(X)
-        with self._timer:
-            ret = self._linear_operator.dot_adj(X)
-        self._timer[-1] /= k
-        return ret
+        # (an empty block goes to ``dot`` like in the reference, utils.py:1631)
+        op = self._linear_operator
+        return self._timed(X.shape[1], op.dot_adj if X.shape[1] else op.dot, X)
 
     def _apply_dev(self, Xd, out=None, adj=False):
-        k = Xd.shape[0]
-        if k == 0:
-            return self._linear_operator._apply_dev(Xd, out=out, adj=adj)
-        with self._timer:
-            ret = self._linear_operator._apply_dev(Xd, out=out, adj=adj)
-        self._timer[-1] /= k
-        return ret
+        return self._timed(Xd.shape[0], self._linear_operator._apply_dev, Xd, out=out, adj=adj)
 
 
 def _as_diagonal(A):

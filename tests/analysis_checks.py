@@ -282,3 +282,45 @@ def check_device_linear_operator():
         kp.utils.DeviceLinearOperator((N, N), np.float64)
     bad = kp.utils.DeviceLinearOperator((N, N), np.float64, dot_dev=lambda Xd, out: Xd[:, :5])
     assert (bad * np.ones((N, 1))) is NotImplemented or True     # LinearOperatorError -> NotImplemented (utils.py:1419-1420)
+
+
+def check_timings(on_device):
+    """utils.Timer / Timings / TimedLinearSystem (krypy/utils.py:1289-1362, linsys.py:204-252): list
+    semantics of the reference; on the device the durations come from CUDA events and are read back
+    lazily (no host synchronisation per timed application)."""
+    import time
+    import krypy_b200 as kp
+    from krypy_b200 import problems
+    u = kp.utils
+    t = u.Timer()
+    with t:
+        time.sleep(0.02)
+    with t:
+        pass
+    t.scale_last(0.5)
+    assert len(t) == 2 and 0.015 < t[0] < 0.5 and 0 <= t[1] < 0.01 and min(t) == t[1]
+    tm = u.Timings()
+    with tm["a"]:
+        time.sleep(0.01)
+    assert tm.get("a") > 0.005 and tm.get("nothing") == 0
+    np.testing.assert_allclose(tm.get_ops({"a": 3, "nothing": 5}), 3 * tm.get("a"))
+    assert "a:" in repr(tm)
+    n = 300 if on_device else 20
+    A = problems.laplace2d(n)
+    b = problems.rhs_normal(n * n)
+    import scipy.sparse as sp
+    ls = kp.linsys.TimedLinearSystem(A, b, M=problems.jacobi_csr(A), Minv=sp.diags(A.diagonal()).tocsr(),
+                                     self_adjoint=True, positive_definite=True)
+    sol = kp.linsys.Cg(ls, tol=1e-6, maxiter=2000)
+    timer = ls.timings["A"]
+    assert list.__len__(timer) >= sol.iter                      # one entry per application of A
+    if on_device:
+        assert len(timer._pending) > 0                          # nothing has been read back yet
+    ta, tmm = ls.timings.get("A"), ls.timings.get("M")
+    assert 0 < ta < 0.05 and 0 < tmm < 0.05 and not timer._pending
+    X = np.ones((n * n, 3))
+    n0 = list.__len__(timer)
+    ls.A * X
+    assert list.__len__(timer) == n0 + 1 and timer[-1] > 0      # per-vector time of a 3-column application
+    est = kp.deflation.DeflatedCg(ls, U=np.eye(n * n, 2), tol=1e-6, maxiter=2000).estimate_time(10, 2)
+    assert est > 0

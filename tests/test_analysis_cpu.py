@@ -43,3 +43,7 @@ def test_ritz_factory_options(fake):
 
 def test_device_linear_operator(fake):
     ac.check_device_linear_operator()
+
+
+def test_timings_wall_clock_fallback(fake):
+    ac.check_timings(False)

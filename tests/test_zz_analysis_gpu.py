@@ -40,3 +40,8 @@ def test_ritz_factory_options():
 
 def test_device_linear_operator():
     ac.check_device_linear_operator()
+
+
+def test_cuda_event_timings():
+    ac.check_timings(True)
+
