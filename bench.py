@@ -370,7 +370,7 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = peaks()
     summ = timer.summary()
     traffic = {}
-    tpath = os.path.join(ROOT, "profiles", "r1_traffic.json")     # ncu dram__bytes per launch (committed)
+    tpath = os.path.join(ROOT, "profiles", "r2_traffic.json")     # ncu dram__bytes per launch (committed)
     if os.path.exists(tpath) and n == N_GRID and world == 1:
         with open(tpath) as f:
             traffic = json.load(f)
@@ -388,7 +388,7 @@ def run_b200(args, rank, world, local_rank):
         roof = {"bound": "hbm", "kernel": "orth_kernel<double,2> (kry_orth_fused, ortho=%s)" % args.ortho,
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get("orth", {}).get("traffic_per_launch"),
-                "traffic_source": "profiles/r1_traffic.json (ncu dram__bytes_read.sum+dram__bytes_write.sum, "
+                "traffic_source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum+dram__bytes_write.sum, "
                                   "mean over the 30 launches of one GMRES(30) cycle)" if traffic else None,
                 "peak_source": peak_src, "launches": o["launches"],
                 "avg_launch_ms": o["ms_total"] / max(o["launches"], 1),
