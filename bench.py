@@ -263,6 +263,18 @@ def config_dict(args, world):
 # ---------------------------------------------------------------------------------------
 # B200 arm
 # ---------------------------------------------------------------------------------------
+def orth_bytes(nq, nv, passes, algo, has_next):
+    """algorithmic bytes of one Gram-Schmidt launch (fp64).  kry_orth_fused: Vdot once + Vsub once per pass (nv
+    vectors each), q read twice + written once per pass, + the normalised store (read q, write v_next) --
+    SURVEY 8d "[2(k+1)+3]Ns + 2Ns".  algo 100 = kry_dist_update_scale (row-partitioned fused step): V once, q
+    read once, v_next written once; algo 101 = kry_dist_dot with want_sq, its first kernel."""
+    if algo == 101:          # kry_dist_dot with <q,q>: V once, q once
+        return (nv + 1) * nq * 8.0
+    if algo == 100:
+        return (nv + 2) * nq * 8.0
+    return (passes * (2 * nv + 3) + (2 if has_next else 0)) * nq * 8.0
+
+
 def run_b200(args, rank, world, local_rank):
     import numpy as np
     import torch
@@ -383,9 +395,12 @@ def run_b200(args, rank, world, local_rank):
         # written once per pass, + phase C (read q, write v_next): SURVEY 8d "[2(k+1)+3]Ns + 2Ns"
         by = 0.0
         for (nq, nv, passes, algo, has_next) in o["meta"]:
-            by += (passes * (2 * nv + 3) + (2 if has_next else 0)) * nq * 8.0
+            by += orth_bytes(nq, nv, passes, algo, has_next)
+        fused2 = any(m[3] == 100 for m in o["meta"])
         ach = by / (o["ms_total"] * 1e-3) / 1e9
-        roof = {"bound": "hbm", "kernel": "orth_kernel<double,2> (kry_orth_fused, ortho=%s)" % args.ortho,
+        roof = {"bound": "hbm", "kernel": ("dist_dot_kernel + dist_update_scale_kernel (kry_dist_dot with <w,w>, "
+                                           "kry_dist_update_scale: one cross-GPU wait per Arnoldi step)" if fused2 else
+                                           "orth_kernel<double,2> (kry_orth_fused, ortho=%s)" % args.ortho),
                 "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                 "traffic": traffic.get("orth", {}).get("traffic_per_launch"),
                 "traffic_source": "profiles/r2_traffic.json (ncu dram__bytes_read.sum+dram__bytes_write.sum, "
@@ -396,14 +411,23 @@ def run_b200(args, rank, world, local_rank):
                 "share_of_step": (o["ms_total"] / ms) if world == 1 else None,
                 "timing": "CUDA events in the timed region" if world == 1 else
                           "CUDA events in one eager cycle after the timed region (timed region replays CUDA "
-                          "graphs); split kernels + NVLink peer all-reduces, per-rank bytes"}
+                          "graphs); " + ("SpMV + two Gram-Schmidt kernels per Arnoldi step, one NVLink peer all-reduce" if fused2 else
+                                         "split kernels + NVLink peer all-reduces") + ", per-rank bytes"}
     if "orth" in summ:
         # per-k profile of the fused Gram-Schmidt kernel: average microseconds and algorithmic GB/s by
         # the number of basis vectors involved (shows the small-k inefficiency; A/B of KRY_ORTH_SMALLK)
         try:
             by_nv = {}
+            held = None          # (the one-wait step brackets its two Gram-Schmidt kernels separately: one entry per step)
             for t_ms, (nq, nv, passes, algo, has_next) in zip(summ["orth"]["ms"], summ["orth"]["meta"]):
-                by_nv.setdefault(int(nv), []).append((t_ms, (passes * (2 * nv + 3) + (2 if has_next else 0)) * nq * 8.0))
+                ent = (t_ms, orth_bytes(nq, nv, passes, algo, has_next))
+                if algo == 101:
+                    held = ent
+                    continue
+                if algo == 100 and held is not None:
+                    ent = (ent[0] + held[0], ent[1] + held[1])
+                    held = None
+                by_nv.setdefault(int(nv), []).append(ent)
             extra["orth_by_nv"] = {str(nv): {"us": round(1e3 * sum(t for t, _ in v) / len(v), 1),
                                              "GBs": round(sum(b for _, b in v) / sum(t for t, _ in v) / 1e6, 0)}
                                    for nv, v in sorted(by_nv.items())}
@@ -411,7 +435,9 @@ def run_b200(args, rank, world, local_rank):
             extra["orth_by_nv"] = {"error": repr(exc)}
     if "spmv" in summ:
         s = summ["spmv"]
-        by = sum(nnz * 12.0 + 4.0 * (nr + 1) + 2.0 * nr * 8.0 for (nr, nnz) in s["meta"])
+        # (a third entry: vectors of the multi-dot epilogue, read once each)
+        by = sum(m[1] * 12.0 + 4.0 * (m[0] + 1) + 2.0 * m[0] * 8.0 + (m[2] * m[0] * 8.0 if len(m) > 2 else 0.0)
+                 for m in s["meta"])
         ach = by / (s["ms_total"] * 1e-3) / 1e9
         extra["roofline_spmv"] = {"bound": "hbm", "kernel": "spmv_staged_kernel<double,8> (kry_spmv_csr)",
                                   "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,

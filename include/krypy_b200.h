@@ -270,7 +270,8 @@ int kry_peer_barrier(kry_ctx* ctx, int world, int rank, unsigned long long* epoc
 /* The phases of kry_orth_fused (krypy/utils.py:1012-1045) for a row-partitioned basis; the
  * global sums travel inside the producing/consuming kernels (P2P stores + release flag in the
  * producer's last CTA, acquire + rank-order sum in every CTA of the consumer):
- *   kry_dist_dot    c_local = V^H q (nv <= 64), published to all peers
+ *   kry_dist_dot    c_local = V^H q (and, want_sq, <q, q> as sum number nv; nv + want_sq <= 64), published
+ *                   to all peers
  *   kry_dist_update c = global sum; h_acc_dev[j] += c_j; q -= V c; want_nrm: publishes ||q||^2
  *   kry_dist_scale  nrm = sqrt(global sum) -> nrm_out_dev[0]; vnext = q / nrm (vnext may be NULL)
  *   kry_dist_halo   handshake (every rank's vector is complete) + kry_halo_gather
@@ -284,7 +285,7 @@ int kry_orth_fused_dist(kry_ctx* ctx, int dtype, long long n, const void* Vdot, 
                         void* vnext, int world, int rank, unsigned long long* epoch_dev,
                         double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
 int kry_dist_dot(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
-                 int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                 int want_sq, int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
                  unsigned long long* const* peer_flags_dev);
 int kry_dist_update(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, void* q,
                     double* h_acc_dev, int want_nrm, int world, int rank, unsigned long long* epoch_dev,
@@ -308,6 +309,35 @@ int kry_dist_scale_haloq(kry_ctx* ctx, int dtype, long long n, const void* q, vo
                          const int* halo_peer, const int* halo_off, void* halo_dst, int world, int rank,
                          unsigned long long* epoch_dev, double* const* peer_slots_dev,
                          unsigned long long* const* peer_flags_dev);
+/* ONE-WAIT Arnoldi step for row-partitioned block classical Gram-Schmidt: kry_spmv_csr, kry_dist_dot with
+ * want_sq (publishes the local V^H w and <w, w>, w = A v_k), kry_dist_update_scale -- three kernels, one
+ * cross-GPU wait, q written once and never rewritten.
+ *   kry_dist_update_scale acquires the peers' partials (the step's only cross-GPU wait), c = rank-order sums,
+ *                        nrm^2 = <w,w> - sum c_j^2 (exact norm through a second exchange inside the kernel when
+ *                        that difference cancels below 1e-3 <w,w>), vnext = (q - V c) / nrm in one sweep
+ *                        (utils.py:1026-1045; q is not modified), h_acc[0..nv) += c, nrm_out[0] = nrm, the halo
+ *                        of vnext from the peers' q and the halo entries of V this rank holds at
+ *                        V[j * ldv + halo_base + i] (bitwise the owners' values), and -- k_givens >= 0 -- the
+ *                        GMRES Givens / Hessenberg update of kry_givens_update (linsys.py:982-993) in one extra
+ *                        CTA beside the sweep (requires k_givens + 1 == nv and nrm_out == h_acc + nv).
+ *   kry_spmv_csr_mdot    y = A x (utils.py:968) with c[j] = <B[j], y> (j < nb) and c[nb] = <y, y> (want_sq) taken
+ *                        in the SpMV epilogue while each row's result is in a register; world > 1: the local sums
+ *                        are published like kry_dist_dot does; world == 1: they go to out_dev (the deflation
+ *                        projector's <W, A v>, deflation.py:135-143).  Staged short-row path only (<= 15 entries
+ *                        per row on average, 16-byte aligned arrays), nb <= 32; otherwise KRY_ERR_UNSUPPORTED.
+ *                        Measured slower than SpMV + block dot below 16 vectors (profiles/r2_mdot_kernel.txt):
+ *                        not used by the solvers. */
+int kry_spmv_csr_mdot(kry_ctx* ctx, int dtype, long long nrows, long long ncols, long long nnz, const int* rowptr,
+                      const int* colidx, const void* vals, const void* x, void* y, const void* B, long long ldb,
+                      int nb, int want_sq, double* out_dev, int world, int rank, unsigned long long* epoch_dev,
+                      double* const* peer_slots_dev, unsigned long long* const* peer_flags_dev);
+int kry_dist_update_scale(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
+                          void* vnext, double* h_acc_dev, double* nrm_out_dev, long long nhalo,
+                          const void* const* peer_q_dev, long long q_elem_offset, const int* halo_peer,
+                          const int* halo_off, long long halo_base, void* halo_dst, int k_givens, double* rcol_dev,
+                          double* cs_dev, double* y_dev, long long mailbox_off, int world, int rank,
+                          unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                          unsigned long long* const* peer_flags_dev);
 int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev,
                   long long elem_offset, const int* halo_peer, const int* halo_off, void* dst, int world,
                   int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,

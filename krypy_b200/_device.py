@@ -396,7 +396,7 @@ class Context(object):
                 while j < nv:
                     c = min(64, int(nv) - j)
                     lastc = (p == int(passes) - 1) and (j + c == int(nv))
-                    check(lib.kry_dist_dot(self.h, dt, n, Vdot.data_ptr() + j * ld * es, ld, c, q.data_ptr(),
+                    check(lib.kry_dist_dot(self.h, dt, n, Vdot.data_ptr() + j * ld * es, ld, c, q.data_ptr(), 0,
                                            w, r, ep, sl, fl))
                     check(lib.kry_dist_update(self.h, dt, n, Vsub.data_ptr() + j * ld * es, ld, c, q.data_ptr(),
                                               hbase + 8 * j, 1 if (lastc and nrm is not None) else 0,
@@ -438,6 +438,68 @@ class Context(object):
             self.block_dot(q.reshape(1, -1), 1, q, nrm, 1, None)
             if vnext is not None:
                 self.scale_dev(nrm, 1, 1.0, q, vnext)
+
+    def spmv_mdot(self, A, x, y, B, nb, want_sq, out=None):
+        """y = A x with c[j] = <B[j], y> (j < nb) and c[nb] = <y, y> in the SpMV epilogue (kry_spmv_csr_mdot).
+        Single GPU: the sums go to ``out``; row-partitioned: the local sums are published to the peers
+        (consumer: dist_update_scale).  Returns False when the matrix is not on the staged short-row path."""
+        from ._lib import KRY_ERR_UNSUPPORTED
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            res = []
+            tm.bracket("spmv", (A.shape[0], A.nnz, int(nb)),
+                       lambda: res.append(self.spmv_mdot(A, x, y, B, nb, want_sq, out)))
+            self.timer = tm
+            return res[0]
+        c = self.comm
+        if c is not None:
+            w, r = c.world, c.rank
+            ep, sl, fl = c.epoch_dev.data_ptr(), c.slots.peer_table.data_ptr(), c.flags.peer_table.data_ptr()
+        else:
+            w, r, ep, sl, fl = 1, 0, None, None, None
+        rc = self.lib.kry_spmv_csr_mdot(self.h, code(A.vals), A.shape[0], A.shape[1], A.nnz, A.rowptr.data_ptr(),
+                                        A.colidx.data_ptr(), A.vals.data_ptr(), x.data_ptr(), y.data_ptr(),
+                                        _p(B), B.stride(0) if B is not None else 0, int(nb), int(want_sq), _p(out),
+                                        w, r, ep, sl, fl)
+        if rc == KRY_ERR_UNSUPPORTED:
+            return False
+        check(rc)
+        return True
+
+    def dist_dot_sq(self, V, nv, q):
+        """local V^H q and <q, q> published to the peers (kry_dist_dot with want_sq); consumer: dist_update_scale"""
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            tm.bracket("orth", (q.numel(), int(nv), 1, 101, False), lambda: self.dist_dot_sq(V, nv, q))
+            self.timer = tm
+            return
+        c = self.comm
+        check(self.lib.kry_dist_dot(self.h, code(q), q.numel(), V.data_ptr(), V.stride(0), int(nv), q.data_ptr(), 1,
+                                    c.world, c.rank, c.epoch_dev.data_ptr(), c.slots.peer_table.data_ptr(),
+                                    c.flags.peer_table.data_ptr()))
+
+    def dist_update_scale(self, V, nv, q, vnext, h_ptr, nrm, halo, halo_q, halo_base, givens=None):
+        """the rest of a row-partitioned block-CGS Arnoldi step after dist_dot_sq (kry_dist_update_scale):
+        ``halo`` = (peer table, offset, halo_peer, halo_off, nhalo, dst) of vnext (DistCsrOperator._halo_args),
+        ``halo_q`` = (peer table, element offset) of q, ``givens`` = (k, rcol, cs, y, mailbox offset) or None"""
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            tm.bracket("orth", (q.numel(), int(nv), 1, 100, True),      # algo 100: the fused two-kernel step
+                       lambda: self.dist_update_scale(V, nv, q, vnext, h_ptr, nrm, halo, halo_q, halo_base, givens))
+            self.timer = tm
+            return
+        c = self.comm
+        _, _, hp, ho, nhalo, dst = halo
+        q_tab, q_off = halo_q
+        if givens is None:
+            gk, rcol, cs, y, off = -1, None, None, None, 0
+        else:
+            gk, rcol, cs, y, off = givens
+        check(self.lib.kry_dist_update_scale(
+            self.h, code(q), q.numel(), V.data_ptr(), V.stride(0), int(nv), q.data_ptr(), vnext.data_ptr(),
+            h_ptr, nrm.data_ptr(), nhalo, q_tab, q_off, hp, ho, int(halo_base), dst, int(gk), _p(rcol), _p(cs), _p(y),
+            int(off), c.world, c.rank, c.epoch_dev.data_ptr(), c.slots.peer_table.data_ptr(),
+            c.flags.peer_table.data_ptr()))
 
     def lanczos_diag(self, vprev, vk, bdiag, q, pre_coef, h3, vnext):
         """fused Lanczos step for a diagonal inner-product matrix (kry_lanczos_diag)"""

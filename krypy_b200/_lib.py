@@ -84,7 +84,7 @@ PROTOTYPES = {
     "kry_orth_fused_dist": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int,
                                     c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                     c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
-    "kry_dist_dot": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_void_p,
+    "kry_dist_dot": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_int, c_int, c_int, c_void_p,
                              c_void_p, c_void_p]),
     "kry_dist_update": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_int, c_int,
                                 c_int, c_void_p, c_void_p, c_void_p]),
@@ -94,6 +94,11 @@ PROTOTYPES = {
                                     c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "kry_dist_scale_haloq": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_ll, c_void_p, c_ll,
                                      c_void_p, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kry_spmv_csr_mdot": (c_int, [c_void_p, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p]),
+    "kry_dist_update_scale": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_int, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_void_p, c_int,
+                                      c_void_p, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "kry_dist_halo": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_ll, c_void_p, c_void_p, c_void_p, c_int, c_int,
                               c_void_p, c_void_p, c_void_p]),
     "kry_small_qr_apply": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -124,6 +129,9 @@ def load():
         fn.argtypes = args
     _lib = lib
     return lib
+
+
+KRY_ERR_UNSUPPORTED = -3      # include/krypy_b200.h
 
 
 def check(rc):

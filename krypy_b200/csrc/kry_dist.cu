@@ -28,7 +28,7 @@
 // ---------------------------------------------------------------------------
 template <typename T, int VEC>
 __global__ void __launch_bounds__(KRY_THREADS, 2)
-dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, const T* q, double* partials,
+dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, const T* q, int want_sq, double* partials,
                 unsigned int* ticket, PeerArgs pa) {
     __shared__ double red[ORTH_JT * 8];
     __shared__ double fin[PEER_SLOT];
@@ -38,6 +38,33 @@ dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, con
         const int nt = nv - jb < ORTH_JT ? nv - jb : ORTH_JT;
         dots_dispatch<T, VEC>(nt, V + (long long)jb * ldv, ldv, q, n, red, partials, 0, jb);
     }
+    if (want_sq) {
+        // <q, q> as one more sum (slot nv): the norm after the update follows from it (kry_dist_update_scale)
+        const long long nvec = n / VEC;
+        const long long stride = (long long)gridDim.x * blockDim.x;
+        long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+        double acc = 0.0;
+        for (; i + 3 * stride < nvec; i += 4 * stride) {
+            double qv[4][VEC];
+#pragma unroll
+            for (int r = 0; r < 4; ++r) VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) acc = fma(qv[r][u], qv[r][u], acc);
+        }
+        for (; i < nvec; i += stride) {
+            double qv[VEC];
+            VecIO<T, VEC>::loadrw(q, i, qv);
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) acc = fma(qv[u], qv[u], acc);
+        }
+        if (blockIdx.x == 0)
+            for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) acc = fma((double)q[e], (double)q[e], acc);
+        const double sq = kry_block_sum(acc, red);
+        if (threadIdx.x == 0) partial_slot(partials, 0, nv)[blockIdx.x] = sq;
+    }
+    const int nred = nv + (want_sq ? 1 : 0);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -49,7 +76,7 @@ dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, con
         __threadfence();
         {   // final local sums: one warp per basis vector, lanes stride over the CTAs (fixed order)
             const int lane = threadIdx.x & 31, w = threadIdx.x >> 5, nw = blockDim.x >> 5;
-            for (int j = w; j < nv; j += nw) {
+            for (int j = w; j < nred; j += nw) {
                 double v = 0.0;
                 for (int b = lane; b < (int)gridDim.x; b += 32)
                     v += __ldcg(partials + (long long)j * KRY_MAX_PARTIAL_BLOCKS + b);
@@ -58,7 +85,7 @@ dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, con
             }
         }
         __syncthreads();
-        peer_publish(pa, E + 1ull, fin, nv);
+        peer_publish(pa, E + 1ull, fin, nred);
         if (threadIdx.x == 0) {
             *pa.epoch_dev = E + 1ull;
             *ticket = 0u;
@@ -181,6 +208,150 @@ dist_scale_kernel(long long n, const T* q, T* vnext, double* nrm_out, PeerArgs p
     if (blockIdx.x == 0)
         for (long long i = nvec * VEC + threadIdx.x; i < n; i += blockDim.x)
             vnext[i] = (T)(nrm > 0.0 ? (double)q[i] / nrm : 0.0);
+}
+
+// ---------------------------------------------------------------------------
+// K2f: the rest of a block-CGS Arnoldi step after kry_spmv_csr_mdot, with ONE cross-GPU wait:
+//   acquire the peers' partials of [V^H w, <w, w>]  (w = A v_k, untouched in q),
+//   c = rank-order sums,  ||w - V c||^2 = <w, w> - sum c_j^2  (V orthonormal),
+//   v_next = (w - V c) / nrm in one sweep (w is read once, nothing is written back to q),
+//   halo of v_next = (w_halo - V_halo c) / nrm from the peers' w (complete since they published) and the
+//   halo entries of v_0..v_k this rank already holds behind its basis rows -- the same fma sequence as
+//   the owner's sweep, so the copy is bitwise the owner's value -- no second handshake,
+//   and (k_givens >= 0) the GMRES Givens / Hessenberg update in one EXTRA CTA (the last one), which runs
+//   beside the sweep instead of as a kernel of its own on the critical path.
+// Guard: the difference above cancels when w lies almost in span(V).  If it keeps less than 1e-3 of
+// <w, w> (or is not finite) every CTA of every rank -- the decision is taken on bitwise identical numbers
+// -- computes the local ||w - V c||^2 exactly, the last one publishes it (epoch + 1), all acquire, and the
+// sweep runs with the exact norm.  The sweep CTAs wait for each other only in that case, therefore the grid
+// is sized to be co-resident.
+// ---------------------------------------------------------------------------
+#include "kry_givens_dev.cuh"
+
+template <typename T>
+struct UpdScaleArgs {
+    long long n;
+    const T* V;
+    long long ldv;
+    int nv;
+    const T* q;
+    T* vnext;
+    double* h_acc;        // h[0..nv) += c, h[nv] = nrm   (nrm_out == h_acc + nv for the solvers)
+    double* nrm_out;
+    long long nhalo;
+    const T* const* peer_q;        // peer pointer table of the region q lives in
+    long long q_elem_offset;
+    const int* halo_peer;
+    const int* halo_off;
+    long long halo_base;           // element offset of the halo part inside a basis row (== block)
+    T* halo_dst;
+    int k_givens;                  // >= 0: Givens update of column k in the extra CTA
+    double *rcol, *cs, *y, *mailbox;
+    double* partials;
+    unsigned int* ticket;
+    PeerArgs pa;
+};
+
+#define DUS_GUARD 1e-3
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(KRY_THREADS, 2) dist_update_scale_kernel(UpdScaleArgs<T> a) {
+    __shared__ double sm[32];
+    __shared__ double c_s[PEER_SLOT];
+    __shared__ double stage[PEER_MAX_RANKS * PEER_SLOT];
+    __shared__ double gsh[3 * PEER_SLOT + 8];
+    __shared__ double nrm_s;
+    __shared__ int okflag, guard_s;
+    __shared__ bool last;
+    const PeerArgs& pa = a.pa;
+    const int nv = a.nv;
+    const unsigned long long E = dld_volatile_u64(pa.epoch_dev);     // the epoch kry_spmv_csr_mdot published
+    const bool ok = peer_wait(pa, E, &okflag);
+    {
+        const double* mine = pa.slots[pa.rank] + (size_t)(E & 1ull) * (size_t)pa.world * PEER_SLOT;
+        for (int idx = threadIdx.x; idx < pa.world * (nv + 1); idx += blockDim.x) {
+            const int r = idx / (nv + 1), j = idx - r * (nv + 1);
+            stage[r * PEER_SLOT + j] = dld_volatile_f64(mine + (size_t)r * PEER_SLOT + j);
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j <= nv; j += blockDim.x) {
+            double sum = 0.0;
+            for (int r = 0; r < pa.world; ++r) sum += stage[r * PEER_SLOT + j];        // rank order
+            c_s[j] = ok ? sum : nan_f64();
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double ww = c_s[nv];
+            double est = ww;
+            for (int j = 0; j < nv; ++j) est = fma(-c_s[j], c_s[j], est);              // fixed order
+            const bool fine = (est >= DUS_GUARD * ww) && (ww >= 0.0) && (est <= ww);   // (false for NaN)
+            guard_s = (fine || !ok) ? 0 : 1;
+            nrm_s = ok ? sqrt(est > 0.0 ? est : 0.0) : nan_f64();
+        }
+        __syncthreads();
+    }
+    const int extra = a.k_givens >= 0 ? 1 : 0;
+    const int nsweep = (int)gridDim.x - extra;
+    const bool sweeper = (int)blockIdx.x < nsweep;
+    // (the extra CTA is the LAST one and takes no elements: the sweeps stride over nsweep CTAs)
+    double nrm = nrm_s;
+    if (guard_s) {
+        // ---- rare: heavy cancellation, take the exact norm with one more exchange ----
+        if (sweeper) {
+            const double part = update_scale_dispatch<T, VEC>(a.V, a.ldv, nv, c_s, a.q, (T*)nullptr, a.n, 1.0, false, nsweep);
+            const double s = kry_block_sum(part, sm);
+            if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                unsigned int t = atomicAdd(a.ticket, 1u);
+                last = (t == (unsigned int)nsweep - 1u);
+            }
+            __syncthreads();
+            if (last) {
+                __threadfence();
+                double v = 0.0;
+                for (int b = threadIdx.x; b < nsweep; b += blockDim.x) v += __ldcg(a.partials + b);
+                const double tot = kry_block_sum(v, sm);
+                __syncthreads();
+                if (threadIdx.x == 0) gsh[0] = tot;
+                __syncthreads();
+                peer_publish(pa, E + 1ull, gsh, 1);
+                if (threadIdx.x == 0) {
+                    *pa.epoch_dev = E + 1ull;
+                    *a.ticket = 0u;
+                }
+            }
+        }
+        const bool ok2 = peer_wait(pa, E + 1ull, &okflag);
+        if (threadIdx.x == 0) nrm_s = ok2 ? sqrt(fabs(peer_sum(pa, E + 1ull, 0))) : nan_f64();
+        __syncthreads();
+        nrm = nrm_s;
+    }
+    if (!sweeper || (extra == 0 && blockIdx.x == 0)) {
+        // coefficients and norm of the step: h += c, h[nv] = nrm
+        if (a.h_acc)
+            for (int j = threadIdx.x; j < nv; j += blockDim.x) a.h_acc[j] += c_s[j];
+        if (threadIdx.x == 0) a.nrm_out[0] = nrm;
+    }
+    if (!sweeper) {
+        __syncthreads();
+        givens_body(a.k_givens, a.h_acc, a.rcol, a.cs, a.y, a.mailbox, gsh);
+        return;
+    }
+    // ---- halo of v_next first: the remote loads' latency overlaps with the local sweep ----
+    {
+        const long long stride = (long long)nsweep * blockDim.x;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nhalo; i += stride) {
+            const T* src = a.peer_q[__ldg(a.halo_peer + i)] + a.q_elem_offset;
+            double w = (double)*(const volatile T*)(src + __ldg(a.halo_off + i));
+            const T* vh = a.V + a.halo_base + i;
+            for (int j = 0; j < nv; ++j) w = fma(-c_s[j], (double)vh[(long long)j * a.ldv], w);
+            w = round_as<T>(w);
+            a.halo_dst[i] = ok ? (T)(nrm > 0.0 ? w / nrm : 0.0) : (T)nan_f64();
+        }
+    }
+    update_scale_dispatch<T, VEC>(a.V, a.ldv, nv, c_s, a.q, a.vnext, a.n, nrm, true, nsweep);
 }
 
 // ---------------------------------------------------------------------------
@@ -308,15 +479,16 @@ static int make_peer(PeerArgs& pa, int world, int rank, unsigned long long* epoc
 }
 
 template <typename T>
-static int dist_dot_launch(kry_ctx* ctx, long long n, const T* V, long long ldv, int nv, const T* q, PeerArgs pa) {
+static int dist_dot_launch(kry_ctx* ctx, long long n, const T* V, long long ldv, int nv, const T* q, int want_sq,
+                           PeerArgs pa) {
     const int W = VecWidth<T>::value;
     bool al = kry_aligned16(V) && kry_aligned16(q) && (ldv % W == 0);
     if (al)
         dist_dot_kernel<T, W><<<dgrid(ctx, n / W, 2), KRY_THREADS, 0, ctx->stream>>>(
-            n, V, ldv, nv, q, ctx->d_partials, ctx->d_ticket + 4, pa);
+            n, V, ldv, nv, q, want_sq, ctx->d_partials, ctx->d_ticket + 4, pa);
     else
         dist_dot_kernel<T, 1><<<dgrid(ctx, n, 2), KRY_THREADS, 0, ctx->stream>>>(
-            n, V, ldv, nv, q, ctx->d_partials, ctx->d_ticket + 4, pa);
+            n, V, ldv, nv, q, want_sq, ctx->d_partials, ctx->d_ticket + 4, pa);
     KRY_LAUNCHED(ctx);
     return KRY_OK;
 }
@@ -350,18 +522,80 @@ static int dist_scale_launch(kry_ctx* ctx, long long n, const T* q, T* vnext, do
     return KRY_OK;
 }
 
+template <typename T, int VEC>
+static int update_scale_launch(kry_ctx* ctx, UpdScaleArgs<T>& a) {
+    auto kern = dist_update_scale_kernel<T, VEC>;
+    static thread_local int occ[16] = {0};
+    int& o = occ[ctx->device & 15];
+    if (o == 0) {
+        int nb = 0;
+        KRY_CHECK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, KRY_THREADS, 0));
+        KRY_REQUIRE(nb >= 1, "kernel does not fit on an SM");
+        o = nb > 2 ? 2 : nb;       // two CTAs per SM carry the sweep (as in the cooperative kernels)
+    }
+    const int extra = a.k_givens >= 0 ? 1 : 0;
+    // all CTAs co-resident (the guard path waits for the other CTAs of the grid through the peers)
+    long long cap = (long long)ctx->sm_count * o - extra;
+    if (cap > KRY_MAX_PARTIAL_BLOCKS) cap = KRY_MAX_PARTIAL_BLOCKS;
+    long long need = (a.n / VEC + KRY_THREADS - 1) / KRY_THREADS;
+    if (need < 1) need = 1;
+    const int g = (int)(need < cap ? need : cap);
+    kern<<<g + extra, KRY_THREADS, 0, ctx->stream>>>(a);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+template <typename T>
+static int update_scale_dtype(kry_ctx* ctx, long long n, const void* V, long long ldv, int nv, const void* q,
+                              void* vnext, double* h_acc_dev, double* nrm_out_dev, long long nhalo,
+                              const void* const* peer_q_dev, long long q_elem_offset, const int* halo_peer,
+                              const int* halo_off, long long halo_base, void* halo_dst, int k_givens, double* rcol_dev,
+                              double* cs_dev, double* y_dev, long long mailbox_off, const PeerArgs& pa) {
+    UpdScaleArgs<T> a;
+    a.n = n;
+    a.V = (const T*)V;
+    a.ldv = ldv;
+    a.nv = nv;
+    a.q = (const T*)q;
+    a.vnext = (T*)vnext;
+    a.h_acc = h_acc_dev;
+    a.nrm_out = nrm_out_dev;
+    a.nhalo = nhalo;
+    a.peer_q = (const T* const*)peer_q_dev;
+    a.q_elem_offset = q_elem_offset;
+    a.halo_peer = halo_peer;
+    a.halo_off = halo_off;
+    a.halo_base = halo_base;
+    a.halo_dst = (T*)halo_dst;
+    a.k_givens = k_givens;
+    a.rcol = rcol_dev;
+    a.cs = cs_dev;
+    a.y = y_dev;
+    a.mailbox = ctx->d_mailbox + mailbox_off;
+    a.partials = ctx->d_partials + (size_t)KRY_MAX_SLOTS * KRY_MAX_PARTIAL_BLOCKS;
+    a.ticket = ctx->d_ticket + 14;
+    a.pa = pa;
+    const int W = VecWidth<T>::value;
+    const bool al = kry_aligned16(V) && kry_aligned16(q) && kry_aligned16(vnext) && (ldv % W == 0);
+    if (al) return update_scale_launch<T, VecWidth<T>::value>(ctx, a);
+    return update_scale_launch<T, 1>(ctx, a);
+}
+
 extern "C" {
 
 int kry_dist_dot(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
-                 int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                 int want_sq, int world, int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
                  unsigned long long* const* peer_flags_dev) {
     KRY_ENTER(ctx);
-    KRY_REQUIRE(n >= 0 && nv >= 1 && nv <= PEER_SLOT && V && q, "bad arguments (1 <= nv <= 64)");
+    KRY_REQUIRE(n >= 0 && nv >= 1 && nv + (want_sq ? 1 : 0) <= PEER_SLOT && V && q,
+                "bad arguments (1 <= nv, nv + want_sq <= 64)");
     PeerArgs pa;
     int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
     if (rc) return rc;
-    if (dtype == KRY_F64) return dist_dot_launch<double>(ctx, n, (const double*)V, ldv, nv, (const double*)q, pa);
-    if (dtype == KRY_F32) return dist_dot_launch<float>(ctx, n, (const float*)V, ldv, nv, (const float*)q, pa);
+    if (dtype == KRY_F64)
+        return dist_dot_launch<double>(ctx, n, (const double*)V, ldv, nv, (const double*)q, want_sq ? 1 : 0, pa);
+    if (dtype == KRY_F32)
+        return dist_dot_launch<float>(ctx, n, (const float*)V, ldv, nv, (const float*)q, want_sq ? 1 : 0, pa);
     kry_set_error("kry_dist_dot: unsupported dtype %d", dtype);
     return KRY_ERR_UNSUPPORTED;
 }
@@ -477,6 +711,35 @@ int kry_dist_scale_haloq(kry_ctx* ctx, int dtype, long long n, const void* q, vo
     }
     KRY_LAUNCHED(ctx);
     return KRY_OK;
+}
+
+int kry_dist_update_scale(kry_ctx* ctx, int dtype, long long n, const void* V, long long ldv, int nv, const void* q,
+                          void* vnext, double* h_acc_dev, double* nrm_out_dev, long long nhalo,
+                          const void* const* peer_q_dev, long long q_elem_offset, const int* halo_peer,
+                          const int* halo_off, long long halo_base, void* halo_dst, int k_givens, double* rcol_dev,
+                          double* cs_dev, double* y_dev, long long mailbox_off, int world, int rank,
+                          unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                          unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(n >= 0 && nv >= 1 && nv < PEER_SLOT && V && q && vnext && nrm_out_dev, "bad arguments (1 <= nv <= 63)");
+    KRY_REQUIRE(nhalo >= 0, "negative halo size");
+    KRY_REQUIRE(nhalo == 0 || (peer_q_dev && halo_peer && halo_off && halo_dst), "NULL halo argument");
+    KRY_REQUIRE(k_givens < 0 || (k_givens + 1 == nv && h_acc_dev && nrm_out_dev == h_acc_dev + nv && rcol_dev &&
+                                 cs_dev && y_dev && mailbox_off >= 0 && mailbox_off + 2 * (long long)k_givens + 5 <= KRY_MAILBOX_DOUBLES),
+                "Givens tail: k + 1 == nv, nrm_out == h_acc + nv, state arrays and a mailbox window required");
+    PeerArgs pa;
+    int rc = make_peer(pa, world, rank, epoch_dev, peer_slots_dev, peer_flags_dev);
+    if (rc) return rc;
+    if (dtype == KRY_F64)
+        return update_scale_dtype<double>(ctx, n, V, ldv, nv, q, vnext, h_acc_dev, nrm_out_dev, nhalo, peer_q_dev,
+                                          q_elem_offset, halo_peer, halo_off, halo_base, halo_dst, k_givens, rcol_dev,
+                                          cs_dev, y_dev, mailbox_off, pa);
+    if (dtype == KRY_F32)
+        return update_scale_dtype<float>(ctx, n, V, ldv, nv, q, vnext, h_acc_dev, nrm_out_dev, nhalo, peer_q_dev,
+                                         q_elem_offset, halo_peer, halo_off, halo_base, halo_dst, k_givens, rcol_dev,
+                                         cs_dev, y_dev, mailbox_off, pa);
+    kry_set_error("kry_dist_update_scale: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
 }
 
 int kry_dist_halo(kry_ctx* ctx, int dtype, long long nhalo, const void* const* peer_bases_dev, long long elem_offset,

@@ -4,73 +4,16 @@
 // results go to device state and to the pinned host mailbox in parallel.
 #include "kry_common.cuh"
 #include "kry_small_core.h"
+#include "kry_givens_dev.cuh"
 
 #define KRY_ENTER(ctx)                                                         \
     KRY_REQUIRE((ctx) != nullptr, "ctx is NULL");                              \
     KRY_CHECK_CUDA(cudaSetDevice((ctx)->device))
 
-// BLAS drotg (reference BLAS 3.10 / OpenBLAS >= 0.3.20 algorithm), returns c, s
-// with r = sigma*hypot(a,b), sigma = sign of the larger-magnitude input.
-// krypy/utils.py:421-424 takes (c, s) from scipy.linalg.blas.drotg.
-__device__ __forceinline__ void kry_drotg(double a, double b, double& c, double& s) {
-    const double safmin = 2.2250738585072014e-308, safmax = 4.4942328371557898e+307;
-    const double anorm = fabs(a), bnorm = fabs(b);
-    if (bnorm == 0.0) {
-        c = 1.0;
-        s = 0.0;
-    } else if (anorm == 0.0) {
-        c = 0.0;
-        s = 1.0;
-    } else {
-        const double scl = fmin(safmax, fmax(safmin, fmax(anorm, bnorm)));
-        const double sigma = (anorm > bnorm) ? copysign(1.0, a) : copysign(1.0, b);
-        const double as = a / scl, bs = b / scl;
-        const double r = sigma * (scl * sqrt(__dadd_rn(__dmul_rn(as, as), __dmul_rn(bs, bs))));
-        c = a / r;
-        s = b / r;
-    }
-}
-
-// G = [[c, s], [-s, c]] applied to (x0, x1): numpy.dot(G, x), utils.py:434-436
-__device__ __forceinline__ void kry_rot(double c, double s, double& x0, double& x1) {
-    const double t0 = __dadd_rn(__dmul_rn(c, x0), __dmul_rn(s, x1));
-    const double t1 = __dadd_rn(__dmul_rn(-s, x0), __dmul_rn(c, x1));
-    x0 = t0;
-    x1 = t1;
-}
-
 __global__ void __launch_bounds__(128) givens_kernel(int k, double* hcol, double* rcol, double* cs, double* y,
                                                      double* mailbox) {
     extern __shared__ double sh[];
-    double* r = sh;              // k+2
-    double* rot = sh + (k + 2);  // 2k
-    for (int i = threadIdx.x; i < k + 2; i += blockDim.x) r[i] = hcol[i];
-    for (int i = threadIdx.x; i < 2 * k; i += blockDim.x) rot[i] = cs[i];
-    __syncthreads();
-    // raw Hessenberg column goes to the host (invariant-subspace test, H attribute)
-    for (int i = threadIdx.x; i < k + 2; i += blockDim.x) {
-        mailbox[1 + i] = r[i];
-        hcol[i] = 0.0;   // h accumulates with += (reorthogonalisation): leave it zeroed
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < k; ++i) kry_rot(rot[2 * i], rot[2 * i + 1], r[i], r[i + 1]);   // linsys.py:985-986
-        double c, s;
-        kry_drotg(r[k], r[k + 1], c, s);                                                  // linsys.py:989
-        cs[2 * k] = c;
-        cs[2 * k + 1] = s;
-        kry_rot(c, s, r[k], r[k + 1]);                                                    // linsys.py:990
-        double y0 = y[k], y1 = y[k + 1];
-        kry_rot(c, s, y0, y1);                                                            // linsys.py:991
-        y[k] = y0;
-        y[k + 1] = y1;
-        mailbox[0] = fabs(y1);                                                            // linsys.py:993
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < k + 2; i += blockDim.x) {
-        rcol[i] = r[i];
-        mailbox[k + 3 + i] = r[i];
-    }
+    givens_body(k, hcol, rcol, cs, y, mailbox, sh);
 }
 
 __global__ void __launch_bounds__(128) tri_solve_kernel(int k, const double* R, long long ldr, const double* y,

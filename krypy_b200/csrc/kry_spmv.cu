@@ -119,11 +119,34 @@ __device__ __forceinline__ TileRows load_tile_rows(const int* __restrict__ rowpt
     return r;
 }
 
-template <typename T, int CPR, int STAGES, bool DOT>
-__global__ void __launch_bounds__(SPMV_THREADS)
+// Multi-vector dot epilogue (NACC > 0: up to NACC vectors): c[j] = <B[j], y> for j < nb and, when want_sq,
+// c[nb] = <y, y>, accumulated by the thread that produces y[row] while the row's result is still in a
+// register -- the Arnoldi step's V^H (A v) / the deflation projector's W^H (A v) without re-reading A v.
+// The basis entries of the row are requested BEFORE the thread waits for the tile's matrix data, so their
+// latency overlaps with the TMA stage and the x gathers.  Deterministic: fixed shuffle tree, fixed warp
+// order, per-CTA partials summed in CTA order by the last CTA.  Row-partitioned runs (pa.world > 1): the
+// last CTA stores the local sums straight into every peer's slot array and releases its flag (epoch + 1),
+// exactly as kry_dist_dot does.
+// MEASURED (B200, profiles/r2_mdot_kernel.txt): the accumulators cost the occupancy the x gathers live on
+// (72 / 96 / 168 registers against 32), so the fused kernel only ties SpMV + block dot for >= 16 vectors
+// and loses below; a second design (y tile in shared memory, one warp per vector, 56-72 registers) was
+// slower still.  The solvers therefore keep the two-kernel form; this entry point stays for callers whose
+// dot basis is wide and for the record.
+template <typename T>
+struct MDotArgs {
+    const T* B;
+    long long ldb;
+    int nb, want_sq;
+    double* out;        // pa.world == 1: the nb (+1) sums
+    PeerArgs pa;
+};
+
+template <typename T, int CPR, int STAGES, bool DOT, int NACC>
+__global__ void __launch_bounds__(SPMV_THREADS, (NACC == 16 ? 2 : 0))
 spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowptr,
                    const int* __restrict__ colidx, const T* __restrict__ vals, const T* __restrict__ x, T* y,
-                   const T* __restrict__ w, double* partials, unsigned int* ticket, double* dot_out) {
+                   const T* __restrict__ w, double* partials, unsigned int* ticket, double* dot_out,
+                   MDotArgs<T> md) {
     typedef SpmvCfg<T, CPR, STAGES> Cfg;
     const int CAP = Cfg::CAP;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -149,6 +172,9 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
     __syncthreads();
 
     double dot_acc = 0.0;
+    double macc[NACC > 0 ? NACC : 1], msq = 0.0;
+#pragma unroll
+    for (int t = 0; t < (NACC > 0 ? NACC : 1); ++t) macc[t] = 0.0;
     if (tid >= SPMV_R) {
         // ---------------- producer warp: one elected lane drives the TMA ring ----------------
         if (tid == SPMV_R && nmine > 0) {
@@ -205,6 +231,12 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
             T* sv = reinterpret_cast<T*>(stage_base + (size_t)st * Cfg::STAGE_BYTES);
             int* sc = reinterpret_cast<int*>(stage_base + (size_t)st * Cfg::STAGE_BYTES + (size_t)CAP * sizeof(T));
             double sum = 0.0;
+            double bv[NACC > 0 ? NACC : 1];
+            if (NACC > 0) {
+#pragma unroll
+                for (int t = 0; t < NACC; ++t)
+                    bv[t] = (t < md.nb && row < r1) ? (double)__ldg(md.B + (long long)t * md.ldb + row) : 0.0;
+            }
             mbar_wait(&full[st], parity);
             if (staged) {
                 const int e_bulk = e_al < nnz_al ? e_al : nnz_al;
@@ -244,6 +276,12 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
             if (row < r1) {
                 if (y) y[row] = (T)sum;
                 if (DOT) dot_acc = fma((double)__ldg(w + row), (double)(T)sum, dot_acc);
+                if (NACC > 0) {
+                    const double ys = (double)(T)sum;           // the value as stored
+#pragma unroll
+                    for (int t = 0; t < NACC; ++t) macc[t] = fma(bv[t], ys, macc[t]);
+                    msq = fma(ys, ys, msq);
+                }
             }
             // this warp is done with slot st: let the producer refill it
             __syncwarp();
@@ -252,6 +290,58 @@ spmv_staged_kernel(long long nrows, long long nnz, const int* __restrict__ rowpt
         }
     }
     if (DOT) finish_dot(dot_acc, partials, ticket, dot_out, red_sm, &last_flag);
+    if (NACC > 0) {
+        __shared__ double mred[(NACC > 0 ? NACC + 1 : 1) * 8];
+        __shared__ double mfin[PEER_SLOT];
+        const int nred = md.nb + (md.want_sq ? 1 : 0);
+        const int lane = tid & 31, wp = tid >> 5;
+        if (tid < SPMV_R) {
+#pragma unroll
+            for (int t = 0; t < NACC; ++t) {
+                if (t < md.nb) {                              // uniform
+                    const double sj = kry_warp_sum(macc[t]);
+                    if (lane == 0) mred[t * 8 + wp] = sj;
+                }
+            }
+            if (md.want_sq) {
+                const double sq = kry_warp_sum(msq);
+                if (lane == 0) mred[md.nb * 8 + wp] = sq;
+            }
+        }
+        __syncthreads();
+        if (tid < nred) {
+            double sj = 0.0;
+            for (int ww = 0; ww < SPMV_R / 32; ++ww) sj += mred[tid * 8 + ww];      // fixed warp order
+            partials[(size_t)tid * KRY_MAX_PARTIAL_BLOCKS + blockIdx.x] = sj;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+            unsigned int tk = atomicAdd(ticket, 1u);
+            last_flag = (tk == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (last_flag) {
+            __threadfence();
+            const int nw = SPMV_THREADS >> 5;
+            for (int j = wp; j < nred; j += nw) {             // one warp per sum, lanes stride over the CTAs
+                double v = 0.0;
+                for (int b = lane; b < (int)gridDim.x; b += 32)
+                    v += __ldcg(partials + (size_t)j * KRY_MAX_PARTIAL_BLOCKS + b);
+                v = kry_warp_sum(v);
+                if (lane == 0) mfin[j] = v;
+            }
+            __syncthreads();
+            if (md.pa.world > 1) {
+                const unsigned long long E = dld_volatile_u64(md.pa.epoch_dev);
+                peer_publish(md.pa, E + 1ull, mfin, nred);
+                if (tid == 0) *md.pa.epoch_dev = E + 1ull;
+            } else {
+                if (tid < nred) md.out[tid] = mfin[tid];
+            }
+            if (tid == 0) *ticket = 0u;
+        }
+    }
 }
 
 template <typename T, bool DOT>
@@ -289,11 +379,11 @@ static int spmv_stage_override() {   // tuning knob: KRY_SPMV_STAGES=2|3|4
     return v;
 }
 
-template <typename T, int CPR, int STAGES, bool DOT>
-static int launch_staged(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
-                         const T* vals, const T* x, T* y, const T* w, double* dot_out) {
+template <typename T, int CPR, int STAGES, bool DOT, int NACC>
+static int launch_staged_md(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
+                            const T* vals, const T* x, T* y, const T* w, double* dot_out, const MDotArgs<T>& md) {
     typedef SpmvCfg<T, CPR, STAGES> Cfg;
-    auto kern = spmv_staged_kernel<T, CPR, STAGES, DOT>;
+    auto kern = spmv_staged_kernel<T, CPR, STAGES, DOT, NACC>;
     static thread_local int occ[16] = {0};
     int& o = occ[ctx->device & 15];
     if (o == 0) {
@@ -309,9 +399,43 @@ static int launch_staged(kry_ctx* ctx, long long nrows, long long nnz, const int
     int g = (int)(ntiles < cap ? ntiles : cap);
     if (g < 1) g = 1;
     kern<<<g, SPMV_THREADS, Cfg::SMEM_BYTES, ctx->stream>>>(nrows, nnz, rowptr, colidx, vals, x, y, w,
-                                                            ctx->d_partials, ctx->d_ticket + 1, dot_out);
+                                                            ctx->d_partials, ctx->d_ticket + (NACC > 0 ? 13 : 1),
+                                                            dot_out, md);
     KRY_LAUNCHED(ctx);
     return KRY_OK;
+}
+
+template <typename T, int CPR, int STAGES, bool DOT>
+static int launch_staged(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
+                         const T* vals, const T* x, T* y, const T* w, double* dot_out) {
+    MDotArgs<T> md;
+    memset(&md, 0, sizeof(md));
+    return launch_staged_md<T, CPR, STAGES, DOT, 0>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, w, dot_out, md);
+}
+
+// multi-dot epilogue: accumulator tile (8 / 16 / 32 registers) by the number of vectors; deeper TMA ring
+// where the register tile leaves a single CTA per SM
+template <typename T, int CPR>
+static int launch_mdot_cpr(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
+                           const T* vals, const T* x, T* y, const MDotArgs<T>& md) {
+    if (md.nb <= 8)
+        return launch_staged_md<T, CPR, 2, false, 8>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, nullptr, nullptr, md);
+    if (md.nb <= 16)
+        return launch_staged_md<T, CPR, 3, false, 16>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, nullptr, nullptr, md);
+    return launch_staged_md<T, CPR, 4, false, 32>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, nullptr, nullptr, md);
+}
+
+template <typename T>
+static int spmv_mdot_dispatch(kry_ctx* ctx, long long nrows, long long nnz, const int* rowptr, const int* colidx,
+                              const T* vals, const T* x, T* y, const MDotArgs<T>& md) {
+    const double avg = nrows > 0 ? (double)nnz / (double)nrows : 0.0;
+    const bool al = kry_aligned16(vals) && kry_aligned16(colidx);
+    if (al && avg <= 5.5) return launch_mdot_cpr<T, 6>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, md);
+    if (al && avg <= 7.5) return launch_mdot_cpr<T, 8>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, md);
+    if (al && avg <= 15.0) return launch_mdot_cpr<T, 16>(ctx, nrows, nnz, rowptr, colidx, vals, x, y, md);
+    kry_set_error("kry_spmv_csr_mdot: only the staged short-row path (<= 15 entries per row on average, 16-byte "
+                  "aligned matrix arrays) carries the multi-dot epilogue");
+    return KRY_ERR_UNSUPPORTED;
 }
 
 template <typename T, int CPR, bool DOT>
@@ -374,5 +498,49 @@ extern "C" int kry_spmv_csr(kry_ctx* ctx, int dtype, long long nrows, long long 
                                            (float*)y, nullptr, nullptr);
     }
     kry_set_error("kry_spmv_csr: unsupported dtype %d", dtype);
+    return KRY_ERR_UNSUPPORTED;
+}
+
+// y = A x and c[j] = <B[j], y> (j < nb), c[nb] = <y, y> (want_sq) in ONE pass: the dots are taken while each
+// row's result is still in the register of the thread that computed it.
+//   world == 1: the sums go to out_dev[0 .. nb + want_sq)
+//   world  > 1: row-partitioned run; the local sums are stored into every peer's slot array and this
+//               rank's flag is released with epoch + 1 (no wait here: the consumer, kry_dist_update_scale
+//               or kry_dist_update, acquires)
+// Replaces utils.py:968 (A v_k) + the k+1 inner products of utils.py:1015 (block classical Gram-Schmidt),
+// and deflation.py:135-143 / utils.py:604-627 (<W, A v> of the projector) when B = W.
+extern "C" int kry_spmv_csr_mdot(kry_ctx* ctx, int dtype, long long nrows, long long ncols, long long nnz,
+                                 const int* rowptr, const int* colidx, const void* vals, const void* x, void* y,
+                                 const void* B, long long ldb, int nb, int want_sq, double* out_dev, int world,
+                                 int rank, unsigned long long* epoch_dev, double* const* peer_slots_dev,
+                                 unsigned long long* const* peer_flags_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(nrows >= 1 && ncols >= 0 && nnz >= 0, "bad size");
+    KRY_REQUIRE(nnz < 2147483647LL, "nnz must fit int32 row pointers");
+    KRY_REQUIRE(rowptr && x && y, "NULL argument");
+    KRY_REQUIRE(nnz == 0 || (colidx && vals), "NULL matrix arrays");
+    KRY_REQUIRE(nb >= 0 && nb <= 32 && nb + (want_sq ? 1 : 0) >= 1, "0 <= nb <= 32 dot vectors (+ the square) per call");
+    KRY_REQUIRE(nb == 0 || B, "NULL dot basis");
+    KRY_REQUIRE(world >= 1 && world <= PEER_MAX_RANKS && rank >= 0 && rank < world, "bad world/rank");
+    KRY_REQUIRE(world > 1 ? (epoch_dev && peer_slots_dev && peer_flags_dev) : (out_dev != nullptr),
+                "world > 1 needs the peer tables, world == 1 an output array");
+    PeerArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    pa.world = world;
+    pa.rank = rank;
+    pa.epoch_dev = epoch_dev;
+    pa.slots = peer_slots_dev;
+    pa.flags = peer_flags_dev;
+    if (dtype == KRY_F64) {
+        MDotArgs<double> md = {(const double*)B, ldb, nb, want_sq ? 1 : 0, out_dev, pa};
+        return spmv_mdot_dispatch<double>(ctx, nrows, nnz, rowptr, colidx, (const double*)vals, (const double*)x,
+                                          (double*)y, md);
+    }
+    if (dtype == KRY_F32) {
+        MDotArgs<float> md = {(const float*)B, ldb, nb, want_sq ? 1 : 0, out_dev, pa};
+        return spmv_mdot_dispatch<float>(ctx, nrows, nnz, rowptr, colidx, (const float*)vals, (const float*)x,
+                                         (float*)y, md);
+    }
+    kry_set_error("kry_spmv_csr_mdot: unsupported dtype %d", dtype);
     return KRY_ERR_UNSUPPORTED;
 }

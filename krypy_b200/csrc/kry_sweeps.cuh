@@ -278,6 +278,86 @@ __device__ __forceinline__ double update_dispatch(const T* V, long long ldv, int
     }
 }
 
+// vnext = (q - V c) / nrm in ONE sweep (q is only read): the Gram-Schmidt update of update_pass followed by
+// the normalised store of scale_pass, element by element with the same roundings (q - V c is rounded to T
+// before the division, as if it had been stored).  Returns this thread's share of ||q - V c||^2 (of the
+// rounded values).  store == false: the norm only.  CTAs [0, nblk) take part (grid-stride map over nblk CTAs).
+template <typename T, int VEC, int R>
+__device__ __forceinline__ double update_scale_pass(const T* __restrict__ V, long long ldv, int cnt, const double* c_s,
+                                                    const T* q, T* vnext, long long n, double nrm, bool store, int nblk) {
+    const int nfull = cnt - R;
+    const long long nvec = n / VEC;
+    const long long stride = (long long)nblk * blockDim.x;      // CTAs [0, nblk) sweep
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double nrm2 = 0.0;
+    constexpr int U = (R >= 1 && R <= 4) ? orth_unroll(R) : 1;
+    if (U > 1 && nfull == 0) {
+        for (; i + (U - 1) * stride < nvec; i += U * stride) {
+            double qv[U][VEC], vv[U][R > 0 ? R : 1][VEC];
+#pragma unroll
+            for (int r = 0; r < U; ++r) {
+                VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
+#pragma unroll
+                for (int t = 0; t < R; ++t) VecIO<T, VEC>::load(V + (long long)t * ldv, i + r * stride, vv[r][t]);
+            }
+#pragma unroll
+            for (int r = 0; r < U; ++r) {
+#pragma unroll
+                for (int t = 0; t < R; ++t) {
+                    const double c = c_s[t];
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) qv[r][u] = fma(-c, vv[r][t][u], qv[r][u]);
+                }
+#pragma unroll
+                for (int u = 0; u < VEC; ++u) {
+                    const double v = round_as<T>(qv[r][u]);
+                    nrm2 = fma(v, v, nrm2);
+                    qv[r][u] = nrm > 0.0 ? v / nrm : 0.0;
+                }
+                if (store) VecIO<T, VEC>::store(vnext, i + r * stride, qv[r]);
+            }
+        }
+    }
+    for (; i < nvec; i += stride) {
+        double qv[VEC];
+        VecIO<T, VEC>::loadrw(q, i, qv);
+        update_pack<T, VEC, R, false>(V, ldv, nfull, c_s, i, qv);
+#pragma unroll
+        for (int u = 0; u < VEC; ++u) {
+            const double v = round_as<T>(qv[u]);
+            nrm2 = fma(v, v, nrm2);
+            qv[u] = nrm > 0.0 ? v / nrm : 0.0;
+        }
+        if (store) VecIO<T, VEC>::store(vnext, i, qv);
+    }
+    if (blockIdx.x == 0) {   // scalar tail
+        for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) {
+            double qe = (double)q[e];
+            for (int j = 0; j < cnt; ++j) qe = fma(-c_s[j], (double)V[(long long)j * ldv + e], qe);
+            qe = round_as<T>(qe);
+            nrm2 = fma(qe, qe, nrm2);
+            if (store) vnext[e] = (T)(nrm > 0.0 ? qe / nrm : 0.0);
+        }
+    }
+    return nrm2;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ double update_scale_dispatch(const T* V, long long ldv, int cnt, const double* c_s,
+                                                        const T* q, T* vnext, long long n, double nrm, bool store,
+                                                        int nblk) {
+    switch (cnt & 7) {
+        case 1: return update_scale_pass<T, VEC, 1>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        case 2: return update_scale_pass<T, VEC, 2>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        case 3: return update_scale_pass<T, VEC, 3>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        case 4: return update_scale_pass<T, VEC, 4>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        case 5: return update_scale_pass<T, VEC, 5>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        case 6: return update_scale_pass<T, VEC, 6>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        case 7: return update_scale_pass<T, VEC, 7>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+        default: return update_scale_pass<T, VEC, 0>(V, ldv, cnt, c_s, q, vnext, n, nrm, store, nblk);
+    }
+}
+
 // vnext = q / nrm (0 when nrm == 0), four loads in flight per thread
 template <typename T, int VEC>
 __device__ __forceinline__ void scale_pass(const T* q, T* vnext, long long n, double nrm) {

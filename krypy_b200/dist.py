@@ -171,6 +171,10 @@ class PeerComm(object):
         # gather the halo of v_{k+1} from the peers' un-normalised q (one cross-GPU wait less per
         # Arnoldi step; KRY_DIST_HALO_FROM_Q=0: from their v_{k+1} rows after a second handshake)
         self.halo_from_q = os.environ.get("KRY_DIST_HALO_FROM_Q", "1") not in ("0", "")
+        # block-CGS Arnoldi step with ONE cross-GPU wait (kry_dist_dot with <w,w> + kry_dist_update_scale: norm
+        # from <w,w> - sum c^2 with an exact-norm guard; update + normalised store + halo + Givens in one kernel);
+        # KRY_DIST_FUSED=0: dot / update / scale+halo / Givens as four kernels with two waits
+        self.fused_step = os.environ.get("KRY_DIST_FUSED", "1") not in ("0", "")
         self.barrier_sync()
 
     def all_gather_object(self, obj):
@@ -369,6 +373,39 @@ class DistCsrOperator(utils._DeviceOperator):
             return None
         return reg.peer_table.data_ptr(), (vec.data_ptr() - reg.base) // es
 
+    def _extended(self, x, hp, ho):
+        """the extended vector [x | halo] of a local segment ``x`` (1-D view) with its halo in place: ``x`` is
+        staged into a peer-mapped buffer if it does not live in one, and the halo is gathered unless the
+        Gram-Schmidt step that produced ``x`` did that already"""
+        comm, ctx, pl = self.comm, self.comm.ctx, self.plan
+        es = x.element_size()
+        td = x.dtype
+        reg = comm.find_region(x.data_ptr(), pl.ext * es)
+        if reg is None:
+            comm.halo_ready = None
+            buf = self._exchange_buffer(td)
+            self._napply += 1
+            ctx.axpby(1.0, x, 0.0, None, buf[0][: pl.nloc])
+            x = buf[0]
+            reg = comm.find_region(x.data_ptr(), pl.ext * es)
+        off = (x.data_ptr() - reg.base) // es
+        xext = reg.view(td)[off: off + pl.ext]
+        if comm.halo_ready is not None and comm.halo_ready == x.data_ptr():
+            comm.halo_ready = None           # the Gram-Schmidt step that produced x gathered its halo already
+        elif comm.reduce == "peer":
+            # one kernel: flag handshake (every rank's segment of this vector is complete) + P2P gather
+            check(ctx.lib.kry_dist_halo(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(), off,
+                                        hp.data_ptr(), ho.data_ptr(), xext.data_ptr() + pl.block * es,
+                                        comm.world, comm.rank, comm.epoch_dev.data_ptr(),
+                                        comm.slots.peer_table.data_ptr(), comm.flags.peer_table.data_ptr()))
+        else:
+            comm.barrier()
+            if pl.nhalo:
+                check(ctx.lib.kry_halo_gather(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(),
+                                              off, hp.data_ptr(), ho.data_ptr(), None,
+                                              xext.data_ptr() + pl.block * es))
+        return xext
+
     def _apply_dev(self, Xd, out=None, adj=False, dot_out=None):
         if adj:
             raise utils.LinearOperatorError("dot_adj undefined for a row-partitioned operator")
@@ -379,31 +416,7 @@ class DistCsrOperator(utils._DeviceOperator):
         if out is None:
             out = ctx.empty((k, pl.nloc), Xd.dtype)
         for j in range(k):
-            x = Xd[j]
-            reg = comm.find_region(x.data_ptr(), pl.ext * es)
-            if reg is None:
-                comm.halo_ready = None
-                buf = self._exchange_buffer(Xd.dtype)
-                self._napply += 1
-                ctx.axpby(1.0, x, 0.0, None, buf[0][: pl.nloc])
-                x = buf[0]
-                reg = comm.find_region(x.data_ptr(), pl.ext * es)
-            off = (x.data_ptr() - reg.base) // es
-            xext = reg.view(Xd.dtype)[off: off + pl.ext]
-            if comm.halo_ready is not None and comm.halo_ready == x.data_ptr():
-                comm.halo_ready = None           # the Gram-Schmidt step that produced x gathered its halo already
-            elif comm.reduce == "peer":
-                # one kernel: flag handshake (every rank's segment of this vector is complete) + P2P gather
-                check(ctx.lib.kry_dist_halo(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(), off,
-                                            hp.data_ptr(), ho.data_ptr(), xext.data_ptr() + pl.block * es,
-                                            comm.world, comm.rank, comm.epoch_dev.data_ptr(),
-                                            comm.slots.peer_table.data_ptr(), comm.flags.peer_table.data_ptr()))
-            else:
-                comm.barrier()
-                if pl.nhalo:
-                    check(ctx.lib.kry_halo_gather(ctx.h, _device.code(xext), pl.nhalo, reg.peer_table.data_ptr(),
-                                                  off, hp.data_ptr(), ho.data_ptr(), None,
-                                                  xext.data_ptr() + pl.block * es))
+            xext = self._extended(Xd[j], hp, ho)
             if dot_out is not None:
                 ctx.spmv(A, xext, out[j], w=xext[: pl.nloc], dot_out=dot_out)   # (+ peer all-reduce of the dot)
             else:

@@ -905,21 +905,26 @@ class Gmres(_KrylovSolver):
         def off_of(k):
             return (k & 1) * HALF if lookahead else 0
 
+        def step(k):
+            # Arnoldi step (linsys.py:978) + Givens / Hessenberg update (linsys.py:982-991); row-partitioned
+            # block-CGS runs fold the latter into the step's last kernel
+            tail = None if cplx else (rcol, cs, y, off_of(k))
+            if not ar._enqueue(k, givens=tail):
+                givens(k, ar._hcol, rcol, cs, y, off_of(k))
+
         def launch(k):
             g = ws.graphs.get(k) if use_graphs else None
             if g is None and use_graphs and ws_warm:
                 g = t.cuda.CUDAGraph()
                 with t.cuda.graph(g):
                     ctx.use_current_stream()
-                    ar._enqueue(k)
-                    givens(k, ar._hcol, rcol, cs, y, off_of(k))
+                    step(k)
                 ctx.use_current_stream()
                 ws.graphs[k] = g
             if g is not None:
                 g.replay()
             else:
-                ar._enqueue(k)                                             # linsys.py:978
-                givens(k, ar._hcol, rcol, cs, y, off_of(k))                # linsys.py:982-991
+                step(k)
             events[k & 1].record()
 
         launched = -1

@@ -1784,11 +1784,44 @@ class Arnoldi(object):
         return float(self._tmp[0].item())
 
     # -- one step, enqueue only ---------------------------------------------------
-    def _enqueue(self, k):
+    def _enqueue_dist_fused(self, k, givens):
+        """Row-partitioned block-CGS step with ONE cross-GPU wait (see dist.PeerComm.fused_step): SpMV,
+        kry_dist_dot with <w, w> (the local V^H w and <w, w>, w = A v_k, published to the peers) and
+        kry_dist_update_scale (acquire, norm from <w, w> - sum c^2 with an exact-norm guard, update +
+        normalised store in one sweep, halo of v_{k+1}, Givens update in an extra CTA).  Returns None when the
+        step does not qualify, else whether the Givens update was part of it."""
+        ctx = self._ctx
+        comm, op = ctx.comm, self._halo_op
+        if (comm is None or op is None or not getattr(comm, "fused_step", False) or comm.reduce != "peer"
+                or self._q2 is None or self._algo != KRY_ORTH_CGS or self._passes != 1 or not self._euclid
+                or self.M is not None or self._cplx or self.ortho in ("lanczos", "house") or k + 2 > 64):
+            return None
+        Vt = self._Vt
+        vnext = Vt[k + 1]
+        hal = op._halo_args(vnext)
+        q = self._q2[1 + (k & 1)]
+        halq = op._halo_src_args(q[0]) if hal is not None else None
+        if halq is None:
+            return None
+        self.A._apply_dev(self._Vd[k:k + 1], out=q)                # utils.py:968
+        ctx.dist_dot_sq(Vt, k + 1, q[0])
+        fold = givens is not None
+        ctx.dist_update_scale(Vt, k + 1, q[0], vnext, self._hcol.data_ptr(), self._hcol[k + 1:], hal, halq,
+                              op.plan.block, givens=((k,) + tuple(givens)) if fold else None)
+        comm.halo_ready = vnext.data_ptr()
+        return fold
+
+    def _enqueue(self, k, givens=None):
         """Launch the kernels of Arnoldi step k (utils.py:964-1045) without any
         host synchronisation.  Results: h[0..k] accumulated into self._hcol (or
-        self._lz for Lanczos), H[k+1,k] in hcol[k+1] (lz[2]), V[k+1] (P[k+1]) stored."""
+        self._lz for Lanczos), H[k+1,k] in hcol[k+1] (lz[2]), V[k+1] (P[k+1]) stored.
+        ``givens`` = (rcol, cs, y, mailbox offset): the caller's Givens update of column k may be folded
+        into the step's last kernel; returns True when it was (the caller then skips its own launch)."""
         ctx = self._ctx
+        if ctx.comm is not None:
+            folded = self._enqueue_dist_fused(k, givens)
+            if folded is not None:
+                return folded
         V, P = self._Vd, self._Pd
         # Vt/Pt: the rows the kernels work on.  Real: the basis itself.  Complex: twin storage,
         # rows nr*j (+1) = v_j (i v_j); coefficients are nr doubles each (interleaved re/im).

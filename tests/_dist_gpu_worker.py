@@ -80,6 +80,41 @@ def main():
         check(sol.resnorms, ref.resnorms)
         assert np.abs(sol.xk[:, 0] - ref.xk[part.lo:part.hi, 0]).max() < 1e-9 * np.abs(ref.xk).max()
 
+    # the one-wait step (kry_dist_dot with <w,w> + kry_dist_update_scale: norm from <w,w> - sum c^2, Givens
+    # update in the extra CTA) and the four-kernel sequence give the same history to rounding
+    hist = {}
+    for fused in (True, False):
+        comm.fused_step = fused
+        try:
+            sol = kp.linsys.Gmres(ls, maxiter=30, tol=1e-14, ortho="cgs")
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+        hist[fused] = (np.array(sol.resnorms), sol.xk[:, 0].copy(), sol.arnoldi.H.copy())
+    comm.fused_step = True
+    check(hist[True][0], hist[False][0])
+    assert np.abs(hist[True][1] - hist[False][1]).max() < 1e-10 * np.abs(hist[False][1]).max()
+    assert np.abs(hist[True][2] - hist[False][2]).max() < 1e-11 * np.abs(hist[False][2]).max()
+    try:
+        ref = ko.gmres(ko.System(A, b), maxiter=30, tol=1e-14)
+    except ko.OracleConvergenceError as e:
+        ref = e.result
+    check(hist[True][0], ref.resnorms)
+
+    # cancellation guard of the fused step: three distinct eigenvalues, so A v_2 lies in span(v_0, v_1, v_2)
+    # and <w,w> - sum c^2 is pure rounding -- the kernel must take the exact norm (a second exchange inside
+    # the kernel), which makes the host see the invariant subspace exactly like the reference does
+    import scipy.sparse as sp
+    N = 3001
+    D = sp.diags(1.0 + (np.arange(N) % 3)).tocsr()
+    b = problems.rhs_normal(N)
+    part = kd.RowPartition(N, world, rank)
+    lsd = kd.DistLinearSystem(kd.local_rows(D, part), b[part.lo:part.hi], part)
+    sol = kp.linsys.Gmres(lsd, maxiter=10, tol=1e-12, ortho="cgs")
+    ref = ko.gmres(ko.System(D, b), maxiter=10, tol=1e-12)
+    check(sol.resnorms, ref.resnorms)
+    assert len(sol.resnorms) == 4 and sol.resnorms[-1] < 1e-13
+    assert np.abs(sol.xk[:, 0] - ref.xk[part.lo:part.hi, 0]).max() < 1e-12
+
     A = problems.poisson3d(12)
     N = A.shape[0]
     b = problems.rhs_normal(N)

@@ -117,6 +117,45 @@ def test_spmv_dot_epilogue_stencil(ctx):
     np.testing.assert_allclose(out.item(), p.dot(Ap), rtol=RT64)
 
 
+@pytest.mark.parametrize("nb", [0, 1, 5, 8, 9, 16, 17, 31, 32])
+@pytest.mark.parametrize("dt", [np.float64, np.float32])
+def test_spmv_mdot_epilogue(ctx, nb, dt):
+    """kry_spmv_csr_mdot: y bit-identical to the plain SpMV, c[j] = <B[j], y>, c[nb] = <y, y> (all three
+    accumulator tiles, all three staged row-length classes)"""
+    from krypy_b200 import problems
+    rng = np.random.default_rng(100 + nb)
+    rt = RT64 if dt == np.float64 else RT32
+    for A in (problems.laplace2d(61, dtype=dt), problems.poisson3d(17, dtype=dt),
+              sp.random(3000, 3000, density=12.0 / 3000, format="csr", random_state=rng, dtype=dt)):
+        A = sp.csr_matrix(A)
+        A.sort_indices()
+        N = A.shape[0]
+        x = rng.standard_normal(N).astype(dt)
+        B = rng.standard_normal((max(nb, 1), N)).astype(dt)
+        Ad = ctx.upload_csr(A, tdt(dt))
+        xd, yd, y0 = T(ctx, x), ctx.empty((N,), tdt(dt)), ctx.empty((N,), tdt(dt))
+        Bd = T(ctx, B)
+        out = ctx.scalars(nb + 1)
+        assert ctx.spmv_mdot(Ad, xd, yd, Bd, nb, 1, out) is True
+        ctx.spmv(Ad, xd, y0)
+        y = yd.cpu().numpy()
+        assert np.array_equal(y, y0.cpu().numpy())
+        y64 = y.astype(np.float64)
+        ref = np.concatenate([B[:nb].astype(np.float64) @ y64, [y64 @ y64]])
+        scale = np.concatenate([np.linalg.norm(B[:nb].astype(np.float64), axis=1) * np.linalg.norm(y64),
+                                [y64 @ y64]])
+        assert np.all(np.abs(out.cpu().numpy() - ref) <= 50 * RT64 * scale), (nb, dt)
+        # deterministic: a second launch gives the same bits
+        out2 = ctx.scalars(nb + 1)
+        ctx.spmv_mdot(Ad, xd, yd, Bd, nb, 1, out2)
+        assert np.array_equal(out.cpu().numpy(), out2.cpu().numpy())
+    # long rows: no staged path, the caller is told (no launch, no fallback inside the library)
+    Al = sp.random(500, 500, density=0.2, format="csr", random_state=rng, dtype=dt)
+    Ad = ctx.upload_csr(Al, tdt(dt))
+    assert ctx.spmv_mdot(Ad, T(ctx, x[:500].copy()), ctx.empty((500,), tdt(dt)), T(ctx, B[:, :500].copy()),
+                         min(nb, 1), 1, ctx.scalars(2)) is False
+
+
 def test_gemv_diag(ctx):
     rng = np.random.default_rng(8)
     for dt, rt in ((np.float64, RT64), (np.float32, RT32)):
