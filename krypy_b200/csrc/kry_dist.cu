@@ -30,39 +30,17 @@ template <typename T, int VEC>
 __global__ void __launch_bounds__(KRY_THREADS, 2)
 dist_dot_kernel(long long n, const T* __restrict__ V, long long ldv, int nv, const T* q, int want_sq, double* partials,
                 unsigned int* ticket, PeerArgs pa) {
-    __shared__ double red[ORTH_JT * 8];
+    __shared__ double red[(ORTH_JT + 1) * 8];
     __shared__ double fin[PEER_SLOT];
     __shared__ bool last;
     const unsigned long long E = dld_volatile_u64(pa.epoch_dev);
     for (int jb = 0; jb < nv; jb += ORTH_JT) {
         const int nt = nv - jb < ORTH_JT ? nv - jb : ORTH_JT;
-        dots_dispatch<T, VEC>(nt, V + (long long)jb * ldv, ldv, q, n, red, partials, 0, jb);
-    }
-    if (want_sq) {
-        // <q, q> as one more sum (slot nv): the norm after the update follows from it (kry_dist_update_scale)
-        const long long nvec = n / VEC;
-        const long long stride = (long long)gridDim.x * blockDim.x;
-        long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-        double acc = 0.0;
-        for (; i + 3 * stride < nvec; i += 4 * stride) {
-            double qv[4][VEC];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) VecIO<T, VEC>::loadrw(q, i + r * stride, qv[r]);
-#pragma unroll
-            for (int r = 0; r < 4; ++r)
-#pragma unroll
-                for (int u = 0; u < VEC; ++u) acc = fma(qv[r][u], qv[r][u], acc);
-        }
-        for (; i < nvec; i += stride) {
-            double qv[VEC];
-            VecIO<T, VEC>::loadrw(q, i, qv);
-#pragma unroll
-            for (int u = 0; u < VEC; ++u) acc = fma(qv[u], qv[u], acc);
-        }
-        if (blockIdx.x == 0)
-            for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) acc = fma((double)q[e], (double)q[e], acc);
-        const double sq = kry_block_sum(acc, red);
-        if (threadIdx.x == 0) partial_slot(partials, 0, nv)[blockIdx.x] = sq;
+        // <q, q> rides along with the last tile as one more sum (slot nv): no pass of its own
+        if (want_sq && jb + nt == nv)
+            dots_dispatch<T, VEC, true>(nt, V + (long long)jb * ldv, ldv, q, n, red, partials, 0, jb);
+        else
+            dots_dispatch<T, VEC, false>(nt, V + (long long)jb * ldv, ldv, q, n, red, partials, 0, jb);
     }
     const int nred = nv + (want_sq ? 1 : 0);
     __threadfence();
@@ -339,17 +317,23 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) dist_update_scale_kernel(UpdSc
         givens_body(a.k_givens, a.h_acc, a.rcol, a.cs, a.y, a.mailbox, gsh);
         return;
     }
-    // ---- halo of v_next first: the remote loads' latency overlaps with the local sweep ----
-    {
-        const long long stride = (long long)nsweep * blockDim.x;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.nhalo; i += stride) {
-            const T* src = a.peer_q[__ldg(a.halo_peer + i)] + a.q_elem_offset;
-            double w = (double)*(const volatile T*)(src + __ldg(a.halo_off + i));
-            const T* vh = a.V + a.halo_base + i;
-            for (int j = 0; j < nv; ++j) w = fma(-c_s[j], (double)vh[(long long)j * a.ldv], w);
-            w = round_as<T>(w);
-            a.halo_dst[i] = ok ? (T)(nrm > 0.0 ? w / nrm : 0.0) : (T)nan_f64();
+    // ---- halo of v_next first, dealt round-robin to the sweep CTAs (entry i -> CTA i % nsweep): a few
+    //      threads per CTA issue the remote loads and the sweep of the other warps hides their latency ----
+    for (long long i = (long long)threadIdx.x * nsweep + blockIdx.x; i < a.nhalo; i += (long long)blockDim.x * nsweep) {
+        const T* src = a.peer_q[__ldg(a.halo_peer + i)] + a.q_elem_offset;
+        double w = (double)*(const volatile T*)(src + __ldg(a.halo_off + i));
+        const T* vh = a.V + a.halo_base + i;
+        int j = 0;
+        for (; j + 8 <= nv; j += 8) {
+            double vv[8];
+#pragma unroll
+            for (int t = 0; t < 8; ++t) vv[t] = (double)__ldg(vh + (long long)(j + t) * a.ldv);
+#pragma unroll
+            for (int t = 0; t < 8; ++t) w = fma(-c_s[j + t], vv[t], w);        // the owner's fma order
         }
+        for (; j < nv; ++j) w = fma(-c_s[j], (double)__ldg(vh + (long long)j * a.ldv), w);
+        w = round_as<T>(w);
+        a.halo_dst[i] = ok ? (T)(nrm > 0.0 ? w / nrm : 0.0) : (T)nan_f64();
     }
     update_scale_dispatch<T, VEC>(a.V, a.ldv, nv, c_s, a.q, a.vnext, a.n, nrm, true, nsweep);
 }

@@ -65,8 +65,10 @@ __device__ __forceinline__ void reduce_store(double (&acc)[NT], double* red /*[1
     }
 }
 
-// acc[t] += <V[t], q> over this thread's elements, t < NT (1 <= NT <= 16), one pass over q
-template <typename T, int VEC, int NT>
+// acc[t] += <V[t], q> over this thread's elements, t < NT (1 <= NT <= 16), one pass over q.
+// SQ: <q, q> as one more sum in slot slot0 + NT (row-partitioned one-wait step: the norm after the update
+// follows from it); red then holds (NT + 1) * 8 doubles.
+template <typename T, int VEC, int NT, bool SQ = false>
 __device__ __forceinline__ void dots_pass(const T* __restrict__ V, long long ldv, const T* q, long long n,
                                           double* red, double* partials, int buf, int slot0) {
     constexpr int U = orth_unroll(NT);
@@ -74,9 +76,9 @@ __device__ __forceinline__ void dots_pass(const T* __restrict__ V, long long ldv
     const long long nvec = n / VEC;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    double acc[NT];
+    double acc[NT + (SQ ? 1 : 0)];
 #pragma unroll
-    for (int t = 0; t < NT; ++t) acc[t] = 0.0;
+    for (int t = 0; t < NT + (SQ ? 1 : 0); ++t) acc[t] = 0.0;
     if (U > 1) {
         for (; i + (U - 1) * stride < nvec; i += U * stride) {
             double qv[U][VEC], vv[U][B0][VEC];
@@ -87,11 +89,16 @@ __device__ __forceinline__ void dots_pass(const T* __restrict__ V, long long ldv
                 for (int t = 0; t < B0; ++t) VecIO<T, VEC>::load(V + (long long)t * ldv, i + r * stride, vv[r][t]);
             }
 #pragma unroll
-            for (int r = 0; r < U; ++r)
+            for (int r = 0; r < U; ++r) {
 #pragma unroll
                 for (int t = 0; t < B0; ++t)
 #pragma unroll
                     for (int u = 0; u < VEC; ++u) acc[t] = fma(vv[r][t][u], qv[r][u], acc[t]);
+                if (SQ) {
+#pragma unroll
+                    for (int u = 0; u < VEC; ++u) acc[NT] = fma(qv[r][u], qv[r][u], acc[NT]);
+                }
+            }
         }
     }
     for (; i < nvec; i += stride) {
@@ -115,22 +122,27 @@ __device__ __forceinline__ void dots_pass(const T* __restrict__ V, long long ldv
 #pragma unroll
                 for (int u = 0; u < VEC; ++u) acc[B0 + t] = fma(vv[t][u], qv[u], acc[B0 + t]);
         }
+        if (SQ) {
+#pragma unroll
+            for (int u = 0; u < VEC; ++u) acc[NT] = fma(qv[u], qv[u], acc[NT]);
+        }
     }
     if (blockIdx.x == 0) {   // scalar tail
         for (long long e = nvec * VEC + threadIdx.x; e < n; e += blockDim.x) {
             const double qe = (double)q[e];
 #pragma unroll
             for (int t = 0; t < NT; ++t) acc[t] = fma((double)V[(long long)t * ldv + e], qe, acc[t]);
+            if (SQ) acc[NT] = fma(qe, qe, acc[NT]);
         }
     }
-    reduce_store<NT>(acc, red, partials, buf, slot0);
+    reduce_store<NT + (SQ ? 1 : 0)>(acc, red, partials, buf, slot0);
 }
 
-template <typename T, int VEC>
+template <typename T, int VEC, bool SQ = false>
 __device__ __forceinline__ void dots_dispatch(int nt, const T* V, long long ldv, const T* q, long long n, double* red,
                                               double* partials, int buf, int slot0) {
     switch (nt) {
-#define KRY_DOTS_CASE(NT) case NT: dots_pass<T, VEC, NT>(V, ldv, q, n, red, partials, buf, slot0); break;
+#define KRY_DOTS_CASE(NT) case NT: dots_pass<T, VEC, NT, SQ>(V, ldv, q, n, red, partials, buf, slot0); break;
         KRY_DOTS_CASE(1) KRY_DOTS_CASE(2) KRY_DOTS_CASE(3) KRY_DOTS_CASE(4) KRY_DOTS_CASE(5) KRY_DOTS_CASE(6)
         KRY_DOTS_CASE(7) KRY_DOTS_CASE(8) KRY_DOTS_CASE(9) KRY_DOTS_CASE(10) KRY_DOTS_CASE(11) KRY_DOTS_CASE(12)
         KRY_DOTS_CASE(13) KRY_DOTS_CASE(14) KRY_DOTS_CASE(15) KRY_DOTS_CASE(16)

@@ -6,11 +6,12 @@ Convergence control stays on the host (one pinned-mailbox read per iteration);
 operator applies, Gram-Schmidt, Givens/Hessenberg updates, solution updates and
 residual norms are device kernels.
 """
+import os
 import warnings
 
 import numpy
 
-from . import _cplx, _device, utils
+from . import _cplx, _device, _lib, utils
 from .utils import _ctx, _is_dev
 
 __all__ = ["LinearSystem", "Cg", "Minres", "Gmres", "RestartedGmres", "TimedLinearSystem",
@@ -902,7 +903,22 @@ class Gmres(_KrylovSolver):
         lookahead = (not self.explicit_residual and ls.exact_solution is None and not is_lanczos
                      and 2 * nr * (m + 2) + 1 <= HALF)
 
+        # Whole-cycle graph (row-partitioned restarted runs, from the third cycle over one workspace on): ALL
+        # maxiter steps of the cycle are one CUDA graph with one mailbox record per step -- look-ahead taken to
+        # its end.  An Arnoldi step never depends on the host's decisions, so steps past the one the host stops
+        # at are speculative work that nothing reads (as with the one-step look-ahead).  The host synchronises
+        # once per cycle and books the records of the steps that neither converge nor look invariant in bulk.
+        # Measured on 8 B200 (C2): 92 us/step inside the cycle graph against 115 us paced by the host
+        # (profiles/r2_cycle_graph_probe.txt).  KRY_CYCLE_GRAPH=0 keeps the per-step graphs.
+        rec = [2 * nr * (j + 2) + 1 for j in range(m)]
+        cyc_offs = numpy.concatenate([[0], numpy.cumsum(rec)]).astype(numpy.int64)
+        cycle_mode = (use_graphs and lookahead and ws.uses >= 3 and not cplx
+                      and int(cyc_offs[-1]) <= _lib.KRY_MAILBOX_DOUBLES
+                      and os.environ.get("KRY_CYCLE_GRAPH", "1") not in ("0", ""))
+
         def off_of(k):
+            if cycle_mode:
+                return int(cyc_offs[k])
             return (k & 1) * HALF if lookahead else 0
 
         def step(k):
@@ -930,6 +946,21 @@ class Gmres(_KrylovSolver):
         launched = -1
         k = -1
         _mark(self, "arnoldi_init")
+        if cycle_mode:
+            g = ws.graphs.get("cycle")
+            if g is None:
+                g = t.cuda.CUDAGraph()
+                with t.cuda.graph(g):
+                    ctx.use_current_stream()
+                    for j in range(m):
+                        step(j)
+                ctx.use_current_stream()
+                ws.graphs["cycle"] = g
+            g.replay()
+            events[0].record()
+            launched = m - 1
+            events[0].synchronize()
+            self._book_cycle_records(ar, mb, cyc_offs, m)
         while (self.resnorms[-1] > self.tol and ar.iter < ar.maxiter and not ar.invariant):
             k = self.iter = ar.iter
             if k == ar.maxiter - 1:
@@ -953,7 +984,8 @@ class Gmres(_KrylovSolver):
             if lookahead and k + 1 < ar.maxiter and launched < k + 1:
                 launch(k + 1)
                 launched = k + 1
-            events[k & 1].synchronize()
+            if not cycle_mode:
+                events[k & 1].synchronize()
             off = off_of(k)
             resid = float(mb[off])
             nh = nr * (k + 2)
@@ -972,6 +1004,47 @@ class Gmres(_KrylovSolver):
             self._discard_speculative()
         if self.__dict__.get("_xk_dev") is None:
             self.xk = self._get_xk(y if ar.iter > 0 else None)
+
+    def _book_cycle_records(self, ar, mb, offs, m):
+        """Whole-cycle graph: books, in bulk, the mailbox records of the leading steps of the cycle that need no
+        decision -- the updated residual stays above the tolerance, the step is not the last one and the
+        invariant-subspace test (utils.py:1035-1039) is far from firing.  Exactly what the loop below does
+        step by step (H, R, resnorms, the running Frobenius norm, iteration counters); it continues with the
+        first step that is not that simple."""
+        ls = self.linear_system
+        resid = mb[offs[:m]] / ls.MMlb_norm
+        stop = numpy.nonzero(~(resid > self.tol))[0]                   # (also catches NaN)
+        kb = min(int(stop[0]) if stop.size else m, m - 1)
+        if kb <= 0:
+            return
+        idx = self._ws.bufs.get(("cycle_index", m))
+        if idx is None:
+            # positions of H[:j+2, j] / R[:j+2, j] inside the mailbox, column after column
+            rows = numpy.concatenate([numpy.arange(j + 2) for j in range(m)])
+            cols = numpy.concatenate([numpy.full(j + 2, j) for j in range(m)])
+            hpos = numpy.concatenate([offs[j] + 1 + numpy.arange(j + 2) for j in range(m)])
+            rpos = numpy.concatenate([offs[j] + 1 + (j + 2) + numpy.arange(j + 2) for j in range(m)])
+            ends = numpy.cumsum([j + 2 for j in range(m)])
+            idx = self._ws.bufs[("cycle_index", m)] = (rows, cols, hpos, rpos, ends)
+        rows, cols, hpos, rpos, ends = idx
+        hvals = mb[hpos[: ends[kb - 1]]]
+        col2 = numpy.add.reduceat(hvals * hvals, numpy.concatenate([[0], ends[: kb - 1]]))
+        hfro2 = ar._hfro2 + numpy.cumsum(col2)
+        hk = mb[offs[:kb] + 1 + numpy.arange(1, kb + 1)]               # H[j+1, j]
+        sus = numpy.nonzero(~(hk > 1e-14 * numpy.sqrt(hfro2)))[0]      # invariant-looking (or NaN) steps
+        if sus.size:
+            kb = int(sus[0])
+            if kb <= 0:
+                return
+        ne = int(ends[kb - 1])
+        ar.H[rows[:ne], cols[:ne]] = mb[hpos[:ne]]
+        self.R[rows[:ne], cols[:ne]] = mb[rpos[:ne]]
+        ar._hfro2 = float(hfro2[kb - 1])
+        ar.iter = kb
+        self.iter = kb - 1
+        self.xk = None
+        self._last_residual = None
+        self.resnorms.extend(float(v) for v in resid[:kb])
 
     def _discard_speculative(self):
         """hook: a look-ahead Arnoldi step was enqueued but not consumed"""

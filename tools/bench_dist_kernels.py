@@ -49,20 +49,41 @@ def graph_time(fn, reps=50):
     return e0.elapsed_time(e1) * 1e3 / reps
 
 print("per-rank rows %d (N=%d / 8), nhalo %d" % (nloc, N, pl.nhalo))
-for k in (2, 10, 20, 28):
+q2 = ctx.alloc_basis(2, nloc, torch.float64, op)
+qq = q2[0:1, :nloc]; qq.normal_()
+rcol, cs, y = ctx.scalars(64), ctx.scalars(128), ctx.scalars(64)
+ks = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else list(range(0, 30))
+tot = {"spmv": 0.0, "dot": 0.0, "k2": 0.0, "old": 0.0, "ideal": 0.0}
+for k in ks:
     nv = k + 1
-    t_spmv = graph_time(lambda: op._apply_dev(Vd[k:k + 1], out=q))
-    t_dot = graph_time(lambda: check(lib.kry_dist_dot(ctx.h, 1, nloc, V.data_ptr(), ld, nv, q.data_ptr(), w, r, ep, sl, fl)))
-    def upd():
-        check(lib.kry_dist_dot(ctx.h, 1, nloc, V.data_ptr(), ld, nv, q.data_ptr(), w, r, ep, sl, fl))
+    vnext = Vd[k + 1]
+    hal = op._halo_args(vnext)
+    halq = op._halo_src_args(qq[0])
+    t_spmv = graph_time(lambda: op._apply_dev(Vd[k:k + 1], out=qq))
+    t_dot = graph_time(lambda: ctx.dist_dot_sq(Vd, nv, qq[0]))
+    # (K2 alone replays against the flags / slots the last dot left behind: no wait, same arithmetic)
+    t_k2 = graph_time(lambda: ctx.dist_update_scale(Vd, nv, qq[0], vnext, h.data_ptr(), h[nv:], hal, halq, pl.block,
+                                                     givens=(k, rcol, cs, y, 0)))
+    nohalo = (hal[0], hal[1], hal[2], hal[3], 0, hal[5])
+    t_k2_plain = graph_time(lambda: ctx.dist_update_scale(Vd, nv, qq[0], vnext, h.data_ptr(), h[nv:], nohalo, halq, pl.block,
+                                                           givens=None))
+    t_k2_halo = graph_time(lambda: ctx.dist_update_scale(Vd, nv, qq[0], vnext, h.data_ptr(), h[nv:], hal, halq, pl.block,
+                                                          givens=None))
+    t_k2_giv = graph_time(lambda: ctx.dist_update_scale(Vd, nv, qq[0], vnext, h.data_ptr(), h[nv:], nohalo, halq, pl.block,
+                                                         givens=(k, rcol, cs, y, 0)))
+    t_upd_old = graph_time(lambda: check(lib.kry_dist_update(ctx.h, 1, nloc, V.data_ptr(), ld, nv, q.data_ptr(), h.data_ptr(), 1, w, r, ep, sl, fl)))
+    print("      K2 variants: plain %5.1f | +halo %5.1f | +givens %5.1f | old update kernel alone %5.1f" % (t_k2_plain, t_k2_halo, t_k2_giv, t_upd_old))
+    def old():
+        check(lib.kry_dist_dot(ctx.h, 1, nloc, V.data_ptr(), ld, nv, q.data_ptr(), 0, w, r, ep, sl, fl))
         check(lib.kry_dist_update(ctx.h, 1, nloc, V.data_ptr(), ld, nv, q.data_ptr(), h.data_ptr(), 1, w, r, ep, sl, fl))
-    t_du = graph_time(upd)
-    def full():
-        upd()
         check(lib.kry_dist_scale(ctx.h, 1, nloc, q.data_ptr(), V.data_ptr() + (k + 1) * ld * es, nrm.data_ptr(), w, r, ep, sl, fl))
-    t_full = graph_time(full)
-    ideal_orth = (2 * nv + 5) * 8 * nloc / 6540.5e9 * 1e6
-    ideal_spmv = (A.nnz * 12 + 4 * nloc + 16 * nloc) / 6540.5e9 * 1e6
-    print("k=%2d: halo+spmv %.1f us (ideal %.1f) | dot %.1f | dot+update %.1f | dot+update+scale %.1f (ideal %.1f)"
-          % (k, t_spmv, ideal_spmv, t_dot, t_du, t_full, ideal_orth))
+    t_old = graph_time(old)
+    ideal = ((nv + 1) + (nv + 2)) * 8 * nloc / 6538.9e9 * 1e6
+    ideal_spmv = (A.nnz * 12 + 4 * nloc + 16 * nloc) / 6538.9e9 * 1e6
+    for key, v in (("spmv", t_spmv), ("dot", t_dot), ("k2", t_k2), ("old", t_old), ("ideal", ideal + ideal_spmv)):
+        tot[key] += v
+    print("k=%2d: halo+spmv %5.1f (ideal %4.1f) | dot+sq %5.1f | update_scale+halo+givens %5.1f | sum %5.1f (ideal %4.1f) | "
+          "old dot+update+scale %5.1f" % (k, t_spmv, ideal_spmv, t_dot, t_k2, t_dot + t_k2, ideal, t_old))
+print("sum over k: spmv %.1f  dot %.1f  k2 %.1f  => step total %.1f us (ideal %.1f); old orth kernels %.1f"
+      % (tot["spmv"], tot["dot"], tot["k2"], tot["spmv"] + tot["dot"] + tot["k2"], tot["ideal"], tot["old"]))
 dist.destroy_process_group()
