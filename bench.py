@@ -300,7 +300,7 @@ def run_b200(args, rank, world, local_rank):
         ls = kp.linsys.LinearSystem(A, b)
         ws = kp.utils.SolverWorkspace()
         make_solver = lambda x0, r0=None: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho,
-                                                          _workspace=ws, _x0_residual=r0)
+                                                          _workspace=ws, _x0_residual=r0, _prelaunch=True)
     else:
         from krypy_b200 import dist as kdist
         part = kdist.RowPartition(N, world, rank)
@@ -309,7 +309,7 @@ def run_b200(args, rank, world, local_rank):
         ls = kdist.DistLinearSystem(A, b, part)
         ws = kp.utils.SolverWorkspace()      # persistent buffers + one CUDA graph per Arnoldi step
         make_solver = lambda x0, r0=None: kp.linsys.Gmres(ls, x0=x0, maxiter=RESTART, tol=TOL, ortho=args.ortho,
-                                                          _workspace=ws, _x0_residual=r0)
+                                                          _workspace=ws, _x0_residual=r0, _prelaunch=True)
 
     carry = {"r": None}
 

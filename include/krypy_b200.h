@@ -180,6 +180,11 @@ int kry_givens_update(kry_ctx* ctx, int k, double* hcol_dev, double* rcol_dev,
  * (scipy.linalg.solve_triangular, linsys.py:946) */
 int kry_tri_solve(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const double* y_dev,
                   double* out_dev);
+/* the same with R stored column after column (entry (i, j) at Rt_dev[j * ldr + i]): the layout the Givens
+ * update leaves on the device when step j's rcol_dev is row j of one array -- the solution update of a
+ * restart cycle (linsys.py:941-949) then needs no host copy of R */
+int kry_tri_solve_t(kry_ctx* ctx, int k, const double* Rt_dev, long long ldr, const double* y_dev,
+                    double* out_dev);
 /* Complex twins (complex numbers interleaved re/im in double arrays; krypy/utils.py:419-427:
  * drotg when both entries are real-valued, zrotg otherwise).  hcol_dev, rcol_dev, y_dev hold
  * k+2 complex numbers; cs_dev 4 doubles per rotation [c, flag, s_re, s_im].

@@ -555,6 +555,10 @@ class Context(object):
     def tri_solve(self, k, R, y, out):
         check(self.lib.kry_tri_solve(self.h, int(k), R.data_ptr(), R.stride(0), y.data_ptr(), out.data_ptr()))
 
+    def tri_solve_t(self, k, Rt, y, out):
+        """tri_solve with R held column after column on the device (row j of ``Rt`` = column j of R)"""
+        check(self.lib.kry_tri_solve_t(self.h, int(k), Rt.data_ptr(), Rt.stride(0), y.data_ptr(), out.data_ptr()))
+
     def givens_update_z(self, k, hcol, rcol, cs, y, off=0):
         """complex twin of givens_update: hcol/rcol/y hold k+2 interleaved complex numbers,
         cs 4 doubles per rotation"""

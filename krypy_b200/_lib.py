@@ -61,6 +61,7 @@ PROTOTYPES = {
                             c_void_p, c_void_p, c_int, c_void_p]),
     "kry_givens_update": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "kry_tri_solve": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
+    "kry_tri_solve_t": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
     "kry_givens_update_z": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_int]),
     "kry_tri_solve_z": (c_int, [c_void_p, c_int, c_void_p, c_ll, c_void_p, c_void_p]),
     "kry_minres_recur": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_int]),

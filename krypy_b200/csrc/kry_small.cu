@@ -16,6 +16,9 @@ __global__ void __launch_bounds__(128) givens_kernel(int k, double* hcol, double
     givens_body(k, hcol, rcol, cs, y, mailbox, sh);
 }
 
+// TR: R is stored column after column (entry (i, j) at R[j * ldr + i]) -- the layout the Givens kernel leaves
+// behind when every step's rcol points at its own row of a device-resident array
+template <bool TR>
 __global__ void __launch_bounds__(128) tri_solve_kernel(int k, const double* R, long long ldr, const double* y,
                                                         double* out) {
     extern __shared__ double sh[];
@@ -30,7 +33,8 @@ __global__ void __launch_bounds__(128) tri_solve_kernel(int k, const double* R, 
             x[j] = xj;
         }
         __syncthreads();
-        for (int i = threadIdx.x; i < j; i += blockDim.x) x[i] = fma(-xj, R[(long long)i * ldr + j], x[i]);
+        for (int i = threadIdx.x; i < j; i += blockDim.x)
+            x[i] = fma(-xj, TR ? R[(long long)j * ldr + i] : R[(long long)i * ldr + j], x[i]);
         __syncthreads();
     }
     for (int i = threadIdx.x; i < k; i += blockDim.x) out[i] = x[i];
@@ -164,7 +168,18 @@ int kry_tri_solve(kry_ctx* ctx, int k, const double* R_dev, long long ldr, const
     if (k == 0) return KRY_OK;
     KRY_REQUIRE(R_dev && y_dev && out_dev, "NULL argument");
     KRY_REQUIRE(k <= 6000, "k too large");
-    tri_solve_kernel<<<1, 128, sizeof(double) * (size_t)k, ctx->stream>>>(k, R_dev, ldr, y_dev, out_dev);
+    tri_solve_kernel<false><<<1, 128, sizeof(double) * (size_t)k, ctx->stream>>>(k, R_dev, ldr, y_dev, out_dev);
+    KRY_LAUNCHED(ctx);
+    return KRY_OK;
+}
+
+int kry_tri_solve_t(kry_ctx* ctx, int k, const double* Rt_dev, long long ldr, const double* y_dev, double* out_dev) {
+    KRY_ENTER(ctx);
+    KRY_REQUIRE(k >= 0 && ldr >= k, "bad arguments");
+    if (k == 0) return KRY_OK;
+    KRY_REQUIRE(Rt_dev && y_dev && out_dev, "NULL argument");
+    KRY_REQUIRE(k <= 6000, "k too large");
+    tri_solve_kernel<true><<<1, 128, sizeof(double) * (size_t)k, ctx->stream>>>(k, Rt_dev, ldr, y_dev, out_dev);
     KRY_LAUNCHED(ctx);
     return KRY_OK;
 }

@@ -214,8 +214,9 @@ class LinearSystem(object):
         return view
 
     # -- device residual -------------------------------------------------------
-    def _get_residual_dev(self, zd, compute_norm=False):
-        """(M Ml (b - A z), Ml (b - A z)[, norm]) on device blocks (linsys.py:130-161)."""
+    def _get_residual_dev(self, zd, compute_norm=False, before_sync=None):
+        """(M Ml (b - A z), Ml (b - A z)[, norm]) on device blocks (linsys.py:130-161).
+        ``before_sync(MMlr, Mlr, norm_dev)``: see _norm_dev."""
         if zd is None:
             if compute_norm:
                 return self._MMlb_dev, self._Mlb_dev, self.MMlb_norm
@@ -227,7 +228,8 @@ class LinearSystem(object):
         Mlr = self.Ml._apply_dev(r)
         MMlr = self.M._apply_dev(Mlr)
         if compute_norm:
-            return MMlr, Mlr, _norm_dev(Mlr, MMlr, self.ip_B)
+            hook = None if before_sync is None else (lambda nd: before_sync(MMlr, Mlr, nd))
+            return MMlr, Mlr, _norm_dev(Mlr, MMlr, self.ip_B, hook)
         return MMlr, Mlr
 
     def get_residual(self, z, compute_norm=False):
@@ -270,11 +272,26 @@ class LinearSystem(object):
         return ret + "}"
 
 
-def _norm_dev(xd, yd, ip_B):
-    """sqrt(<x, y>_B) of single-vector device blocks; one host synchronisation."""
+def _norm_dev(xd, yd, ip_B, before_sync=None):
+    """sqrt(<x, y>_B) of single-vector device blocks; one host synchronisation.  ``before_sync(norm_dev)``
+    runs after the reduction is enqueued and before the host waits for it (work the device result does not
+    gate: deferred bookkeeping, the speculative launch of the next restart cycle)."""
     ctx = _ctx()
     tmp = ctx.scalars(1)
     utils._ip_coef(xd, xd if yd is None else yd, ip_B, tmp, post=1)
+    if before_sync is not None:
+        # the read-back is enqueued BEFORE the hook's work (which may be a whole restart cycle), so the host
+        # gets the norm as soon as the reduction is done and runs ahead of the device from here on
+        t = _device.torch()
+        host = ctx.__dict__.get("_pinned_norm")
+        if host is None:
+            host = ctx.__dict__["_pinned_norm"] = t.zeros(1, dtype=t.float64).pin_memory()
+        host.copy_(tmp, non_blocking=True)
+        ev = ctx.event()
+        ev.record()
+        before_sync(tmp)
+        ev.synchronize()
+        return numpy.float64(host[0].item())
     return numpy.float64(tmp[0].item())
 
 
@@ -432,7 +449,11 @@ class _KrylovSolver(object):
                 or self.iter + 1 == self.maxiter):
             if self.__dict__.get("_xk_dev") is None:
                 self.xk = self._get_xk(yk)
-            MMlrk, Mlrk, rkn = ls._get_residual_dev(self.__dict__["_xk_dev"], compute_norm=True)
+            hook = self.__dict__.pop("_before_residual_sync", None)
+            if hook is not None:
+                MMlrk, Mlrk, rkn = ls._get_residual_dev(self.__dict__["_xk_dev"], compute_norm=True, before_sync=hook)
+            else:
+                MMlrk, Mlrk, rkn = ls._get_residual_dev(self.__dict__["_xk_dev"], compute_norm=True)
             self._last_residual = (MMlrk, Mlrk, rkn)
             self.resnorms.append(rkn / ls.MMlb_norm)
             if self.resnorms[-1] > self.tol:
@@ -809,9 +830,12 @@ class Gmres(_KrylovSolver):
     and the block variants 'cgs' / 'cgs2' (see utils.Arnoldi).
     """
 
-    def __init__(self, linear_system, ortho="mgs", _workspace=None, **kwargs):
+    def __init__(self, linear_system, ortho="mgs", _workspace=None, _prelaunch=False, **kwargs):
         self.ortho = ortho
         self._ws = _workspace
+        # (restart driver) another cycle follows over the same workspace unless this one converges: the end of
+        # this cycle may launch it speculatively, see _solve
+        self._prelaunch = bool(_prelaunch)
         super(Gmres, self).__init__(linear_system, **kwargs)
 
     def __repr__(self):
@@ -822,19 +846,25 @@ class Gmres(_KrylovSolver):
     V = _LazyBasis("V", fallback=lambda self: self.arnoldi.V)
     P = _LazyBasis("P")
 
-    def _get_xk(self, y):
-        """krypy/linsys.py:941-949: y is a device vector holding y[:k] (or None)."""
+    def _get_xk(self, y, k=None):
+        """krypy/linsys.py:941-949: y is a device vector holding y[:k] (or None); k defaults to the
+        number of Arnoldi steps booked so far."""
         x0d = self.__dict__["_x0_dev"]
         if y is None:
             return x0d
         ctx = self._ctx
-        k = self.arnoldi.iter
+        if k is None:
+            k = self.arnoldi.iter
         if k > 0:
             t = _device.torch()
             ar = self.arnoldi
             nr = ar._nr
-            yy = ctx.scalars(nr * k)
-            if ar._cplx:
+            Rt = self.__dict__.get("_Rt_dev")
+            yy = ctx.scalars(nr * k) if Rt is None else self._ws.tensor("yy", (Rt.shape[0],),
+                                                                        lambda: ctx.scalars(Rt.shape[0]))
+            if Rt is not None:
+                ctx.tri_solve_t(k, Rt, y, yy)                              # R never left the device
+            elif ar._cplx:
                 Rk = t.from_numpy(_cplx.to_pairs(self.R[:k, :k])).to(ctx.device)   # (k, 2k) interleaved
                 ctx.tri_solve_z(k, Rk, y, yy)
             else:
@@ -866,25 +896,35 @@ class Gmres(_KrylovSolver):
                 "Gmres on the device path supports at most %d steps per cycle (maxiter=%d; the default is "
                 "N): pass maxiter<=%d or use RestartedGmres(ls, maxiter=m, max_restarts=r)"
                 % (cap, self.maxiter, cap))
+        m = self.maxiter
+        ws = self._ws
+        # a cycle the previous solver over this workspace launched speculatively for exactly this start
+        pre = None
+        if ws is not None:
+            pre, ws.prelaunched = getattr(ws, "prelaunched", None), None
+            if pre is not None and not (pre["Mlr"] is self.__dict__.get("_Mlr0_dev") and pre["m"] == m
+                                        and pre["ortho"] == self.ortho and pre["ls"] is ls
+                                        and not self.explicit_residual and not self.store_arnoldi):
+                pre = None              # (not this start: the usual set-up below overwrites what it left)
         self.arnoldi = ar = utils.Arnoldi(
             self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
             Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype,
-            _workspace=self._ws)
-        m = self.maxiter
-        ws = self._ws
+            _workspace=self._ws, _prelaunched=pre is not None)
         self.R = numpy.zeros([m + 1, m], dtype=utils._common_type([self.dtype, numpy.float64]))
         cplx, nr = ar._cplx, ar._nr            # complex: every small quantity is an interleaved pair
         if ws is not None:
             self._y_dev = y = ws.tensor("y", (nr * (m + 2),), lambda: ctx.scalars(nr * (m + 2)))
             cs = ws.tensor("cs", (2 * nr * (m + 1),), lambda: ctx.scalars(2 * nr * (m + 1)))
             rcol = ws.tensor("rcol", (nr * (m + 2),), lambda: ctx.scalars(nr * (m + 2)))
-            y.zero_()
+            if pre is None:
+                y.zero_()
         else:
             self._y_dev = y = ctx.scalars(nr * (m + 2))
             cs = ctx.scalars(2 * nr * (m + 1))
             rcol = ctx.scalars(nr * (m + 2))
         givens = ctx.givens_update_z if cplx else ctx.givens_update
-        y[0:1].fill_(float(self.MMlr0_norm))                               # linsys.py:969
+        if pre is None:
+            y[0:1].fill_(float(self.MMlr0_norm))                           # linsys.py:969
         # CUDA graphs: from the second cycle over the same workspace on, step k is one graph launch
         use_graphs = (ws is not None and type(self) is Gmres and ws.graphs_enabled(ctx)
                       and self.ortho not in ("lanczos", "house"))
@@ -921,12 +961,19 @@ class Gmres(_KrylovSolver):
                 return int(cyc_offs[k])
             return (k & 1) * HALF if lookahead else 0
 
+        # graph runs keep R on the device: step k's rotated column goes to row k of Rt (column after column),
+        # and the solution update solves against it in place (kry_tri_solve_t) instead of uploading the host copy
+        Rt = None
+        if use_graphs and not cplx:
+            Rt = self._Rt_dev = ws.tensor("Rt", (m, m + 2), lambda: ctx.zeros((m, m + 2), t.float64))
+
         def step(k):
             # Arnoldi step (linsys.py:978) + Givens / Hessenberg update (linsys.py:982-991); row-partitioned
             # block-CGS runs fold the latter into the step's last kernel
-            tail = None if cplx else (rcol, cs, y, off_of(k))
+            rk_dev = rcol if Rt is None else Rt[k]
+            tail = None if cplx else (rk_dev, cs, y, off_of(k))
             if not ar._enqueue(k, givens=tail):
-                givens(k, ar._hcol, rcol, cs, y, off_of(k))
+                givens(k, ar._hcol, rk_dev, cs, y, off_of(k))
 
         def launch(k):
             g = ws.graphs.get(k) if use_graphs else None
@@ -948,19 +995,83 @@ class Gmres(_KrylovSolver):
         _mark(self, "arnoldi_init")
         if cycle_mode:
             g = ws.graphs.get("cycle")
-            if g is None:
-                g = t.cuda.CUDAGraph()
-                with t.cuda.graph(g):
+            if pre is not None and g is not None:
+                pre["event"].synchronize()                     # launched by the previous cycle's solver
+            else:
+                if g is None:
+                    g = t.cuda.CUDAGraph()
+                    with t.cuda.graph(g):
+                        ctx.use_current_stream()
+                        for j in range(m):
+                            step(j)
                     ctx.use_current_stream()
-                    for j in range(m):
-                        step(j)
-                ctx.use_current_stream()
-                ws.graphs["cycle"] = g
-            g.replay()
-            events[0].record()
+                    ws.graphs["cycle"] = g
+                g.replay()
+                events[0].record()
+                events[0].synchronize()
             launched = m - 1
-            events[0].synchronize()
-            self._book_cycle_records(ar, mb, cyc_offs, m)
+            resid_all = mb[cyc_offs[:m]] / ls.MMlb_norm
+            if m >= 2 and bool(numpy.all(resid_all[:m - 1] > self.tol)):
+                # The usual cycle: no step before the last one meets the tolerance.  The device work of the cycle's
+                # end (solution update, explicit residual, its norm and the read-back of that norm) is enqueued
+                # FIRST, for all m steps; while it runs the host books the records (H, R, history, invariance
+                # test), launches the next cycle speculatively on the device-side norm when the restart driver
+                # announced one, and only then waits for the norm.  If the bookkeeping finds a step that needs a
+                # decision after all (an invariant-looking subspace), the early results are dropped and the
+                # step-by-step loop below takes over -- nothing has been overwritten at that point.
+                can_pre = (self._prelaunch and Rt is not None and ar.M is None and ar._euclid
+                           and not self.store_arnoldi and os.environ.get("KRY_PRELAUNCH", "1") not in ("0", ""))
+                state = {"ok": False}
+
+                def before_sync(MMlr, Mlr, nrm_dev):
+                    snap = mb[: int(cyc_offs[m])].copy()        # the next cycle reuses the record slots
+                    if can_pre and MMlr is Mlr and self._no_invariance_in_sight(ar, snap, cyc_offs, m):
+                        # nothing below can end the cycle early any more: the next cycle goes first
+                        y.zero_()
+                        y[0:1].copy_(nrm_dev[0:1])
+                        ctx.scale_dev(nrm_dev, 1, 1.0, Mlr[0], ar._Vd[0])          # v_0 = r / ||r||
+                        if ctx.comm is not None:
+                            ctx.comm.halo_ready = None
+                        g.replay()
+                        ev = ctx.event()
+                        ev.record()
+                        ws.prelaunched = dict(Mlr=Mlr, m=m, ortho=self.ortho, ls=ls, event=ev)
+                    fill = self._book_cycle_records(ar, snap, cyc_offs, m)
+                    if fill is None:
+                        return
+                    kl = m - 1
+                    off = off_of(kl)
+                    nh = kl + 2
+                    hcol = snap[off + 1:off + 1 + nh].copy()
+                    self.R[: kl + 2, kl] = snap[off + 1 + nh:off + 1 + 2 * nh]
+                    self.iter = kl
+                    _mark(self, "last_iteration_begin")
+                    ar._finish(kl, hcol)
+                    fill()
+                    state["ok"] = True
+
+                xk_early = self._get_xk(y, k=m)
+                MMlrk, Mlrk, rkn = ls._get_residual_dev(xk_early, compute_norm=True, before_sync=before_sync)
+                if state["ok"]:
+                    # krypy/linsys.py:430-493 for the last iteration of the cycle
+                    k = m - 1
+                    self.xk = xk_early
+                    self._last_residual = (MMlrk, Mlrk, rkn)
+                    self.resnorms.append(rkn / ls.MMlb_norm)
+                    if self.resnorms[-1] > self.tol:
+                        self._finalize()
+                        raise utils.ConvergenceError(
+                            ("No convergence in last iteration "
+                             "(maxiter: %s, residual: %s)." % (self.maxiter, self.resnorms[-1])), self)
+                else:
+                    self.xk = None
+                    self._last_residual = None
+            else:
+                fill = self._book_cycle_records(ar, mb, cyc_offs, m)
+                if fill is not None:
+                    fill()
+        elif pre is not None:
+            raise RuntimeError("speculative cycle without a cycle graph")      # (cannot happen: same conditions)
         while (self.resnorms[-1] > self.tol and ar.iter < ar.maxiter and not ar.invariant):
             k = self.iter = ar.iter
             if k == ar.maxiter - 1:
@@ -1005,18 +1116,34 @@ class Gmres(_KrylovSolver):
         if self.__dict__.get("_xk_dev") is None:
             self.xk = self._get_xk(y if ar.iter > 0 else None)
 
+    def _no_invariance_in_sight(self, ar, mb, offs, m):
+        """cheap sufficient condition for "the invariant-subspace test (utils.py:1035-1039) fires at no step of
+        this cycle": every H[j+1, j] stays above 1e-14 times the Frobenius norm of the WHOLE Hessenberg matrix
+        (an upper bound of the norm the test uses at step j)"""
+        idx = self._ws.bufs.get(("cycle_hpos", m))
+        if idx is None:
+            hpos = numpy.concatenate([offs[j] + 1 + numpy.arange(j + 2) for j in range(m)])
+            sub = numpy.array([offs[j] + 1 + j + 1 for j in range(m)])
+            idx = self._ws.bufs[("cycle_hpos", m)] = (hpos, sub)
+        hpos, sub = idx
+        h = mb[hpos]
+        total = ar._hfro2 + float(numpy.dot(h, h))
+        return bool(numpy.all(mb[sub] > 1e-14 * numpy.sqrt(total)))
+
     def _book_cycle_records(self, ar, mb, offs, m):
         """Whole-cycle graph: books, in bulk, the mailbox records of the leading steps of the cycle that need no
         decision -- the updated residual stays above the tolerance, the step is not the last one and the
-        invariant-subspace test (utils.py:1035-1039) is far from firing.  Exactly what the loop below does
-        step by step (H, R, resnorms, the running Frobenius norm, iteration counters); it continues with the
-        first step that is not that simple."""
+        invariant-subspace test (utils.py:1035-1039) is far from firing.  Exactly what the loop in _solve does
+        step by step (H, R, resnorms, the running Frobenius norm, iteration counters); the loop continues with
+        the first step that is not that simple.  In the usual case (all steps but the last) only the counters
+        are set here and a callable is returned that fills H, R and the history later, while the device is busy
+        with the end of the cycle; otherwise everything is done at once and None is returned."""
         ls = self.linear_system
         resid = mb[offs[:m]] / ls.MMlb_norm
         stop = numpy.nonzero(~(resid > self.tol))[0]                   # (also catches NaN)
         kb = min(int(stop[0]) if stop.size else m, m - 1)
         if kb <= 0:
-            return
+            return None
         idx = self._ws.bufs.get(("cycle_index", m))
         if idx is None:
             # positions of H[:j+2, j] / R[:j+2, j] inside the mailbox, column after column
@@ -1035,16 +1162,27 @@ class Gmres(_KrylovSolver):
         if sus.size:
             kb = int(sus[0])
             if kb <= 0:
-                return
+                return None
         ne = int(ends[kb - 1])
-        ar.H[rows[:ne], cols[:ne]] = mb[hpos[:ne]]
-        self.R[rows[:ne], cols[:ne]] = mb[rpos[:ne]]
         ar._hfro2 = float(hfro2[kb - 1])
         ar.iter = kb
         self.iter = kb - 1
         self.xk = None
         self._last_residual = None
-        self.resnorms.extend(float(v) for v in resid[:kb])
+        hist = [float(v) for v in resid[:kb]]
+        self.resnorms.append(hist[-1])          # (the loop condition looks at the latest entry)
+        rvals = mb[rpos[:ne]]                           # (fancy indexing copies: safe against the next cycle's records)
+        pos = len(self.resnorms) - 1
+
+        ar.H[rows[:ne], cols[:ne]] = hvals[:ne]         # (the invariance test of the next step may look at H)
+
+        def fill():
+            self.R[rows[:ne], cols[:ne]] = rvals
+            self.resnorms[pos:pos + 1] = hist
+        if kb == m - 1:
+            return fill
+        fill()
+        return None
 
     def _discard_speculative(self):
         """hook: a look-ahead Arnoldi step was enqueued but not consumed"""
@@ -1082,6 +1220,8 @@ class _RestartedSolver(object):
             try:
                 if xk_dev is not None:
                     kwargs.update({"x0": xk_dev})        # stays in HBM between cycles
+                if Solver is Gmres:
+                    kwargs["_prelaunch"] = restart < max_restarts      # another cycle follows unless this one converges
                 sol = Solver(linear_system, **kwargs)
             except utils.ConvergenceError as e:
                 sol = e.solver

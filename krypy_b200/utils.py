@@ -1631,7 +1631,10 @@ class Arnoldi(object):
     """
 
     def __init__(self, A, v, maxiter=None, ortho="mgs", M=None, Mv=None, Mv_norm=None, ip_B=None,
-                 dtype=None, _workspace=None):
+                 dtype=None, _workspace=None, _prelaunched=False):
+        """``_prelaunched`` (linsys.Gmres over a workspace): the steps of this Arnoldi process are already
+        running on the device (the previous restart cycle wrote v_0 and launched them); only the host side is
+        set up here, no device buffer is touched."""
         ctx = self._ctx = _ctx()
         ws = self._ws = _workspace
         t = _device.torch()
@@ -1718,8 +1721,9 @@ class Arnoldi(object):
             self._tmp = ws.tensor("tmp", (4,), lambda: ctx.scalars(4))
             self._lz = ws.tensor("lz", (3,), lambda: ctx.scalars(3))
             self._lz_st = ws.tensor("lz_st", (16,), lambda: ctx.scalars(16))
-            for buf in (self._hcol_store, self._tmp, self._lz, self._lz_st):
-                buf.zero_()
+            if not _prelaunched:
+                for buf in (self._hcol_store, self._tmp, self._lz, self._lz_st):
+                    buf.zero_()
         else:
             self._q = ctx.empty((1, N), td)
             self._hcol_store = ctx.scalars(nr * (self.maxiter + 2 + 8))
@@ -1735,6 +1739,9 @@ class Arnoldi(object):
         self._hcol = self._hcol_store[nr:]      # one leading zero: H[-1, 0] of linsys.py:828
         self._hfro2 = 0.0
 
+        if _prelaunched:
+            self.vnorm = Mv_norm
+            return
         # first basis vector: utils.py:923-952
         vd = v if v_dev_in else ctx.to_block(numpy.asarray(v), td)
         if vd.dtype != td:

@@ -324,6 +324,11 @@ class FakeContext(object):
         yc = y.numpy()[:2 * k].copy().view(np.complex128)
         out.numpy()[:2 * k] = scipy.linalg.solve_triangular(Rc, yc).view(np.float64)
 
+    def tri_solve_t(self, k, Rt, y, out):
+        import scipy.linalg
+        self._count("tri_solve_t")
+        out[: int(k)] = torch.from_numpy(scipy.linalg.solve_triangular(Rt.numpy()[:k, :k].T, y.numpy()[:k]))
+
     def tri_solve(self, k, R, y, out):
         import scipy.linalg
         self._count("tri_solve")

@@ -411,6 +411,13 @@ def test_tri_solve(ctx):
         out = ctx.scalars(k)
         ctx.tri_solve(k, T(ctx, R), T(ctx, y), out)
         np.testing.assert_allclose(out.cpu().numpy(), scipy.linalg.solve_triangular(R, y), rtol=1e-11)
+        # column-after-column storage with a padded leading dimension (the device-resident R of a restart cycle):
+        # the same operations in the same order, so the same bits
+        Rt = np.zeros((k, k + 2))
+        Rt[:, :k] = R.T
+        out_t = ctx.scalars(k)
+        ctx.tri_solve_t(k, T(ctx, Rt), T(ctx, y), out_t)
+        assert np.array_equal(out_t.cpu().numpy(), out.cpu().numpy())
 
 
 def test_minres_recur_and_update(ctx):

@@ -33,7 +33,7 @@ def main():
 
     def cycle(x0, r0):
         try:
-            s = kp.linsys.Gmres(ls, x0=x0, maxiter=m, tol=1e-13, ortho="cgs", _workspace=ws, _x0_residual=r0)
+            s = kp.linsys.Gmres(ls, x0=x0, maxiter=m, tol=1e-13, ortho="cgs", _workspace=ws, _x0_residual=r0, _prelaunch=True)
         except kp.utils.ConvergenceError as e:
             s = e.solver
         return s
