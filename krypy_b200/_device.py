@@ -171,6 +171,7 @@ class Context(object):
         check(lib.kry_device_info(h, info))
         self.sm_count, self.cc, self.l2_bytes = int(info[0]), int(info[1]), int(info[2])
         self.orth_blocks = int(info[5])
+        self.cycle_ahead = True    # linsys.Gmres may enqueue whole restart cycles ahead of the host (real device only)
         self.timer = None          # set to a KernelTimer by bench.py
         self.comm = None           # set to a dist.PeerComm: reductions become global sums
         self._tmpc = None

@@ -904,8 +904,12 @@ class Gmres(_KrylovSolver):
             pre, ws.prelaunched = getattr(ws, "prelaunched", None), None
             if pre is not None and not (pre["Mlr"] is self.__dict__.get("_Mlr0_dev") and pre["m"] == m
                                         and pre["ortho"] == self.ortho and pre["ls"] is ls
-                                        and not self.explicit_residual and not self.store_arnoldi):
-                pre = None              # (not this start: the usual set-up below overwrites what it left)
+                                        and not self.explicit_residual and not self.store_arnoldi
+                                        and type(self) is Gmres
+                                        and os.environ.get("KRY_CYCLE_AHEAD", "1") not in ("0", "")):
+                # not this start: the usual set-up below is enqueued behind the stale cycle and overwrites
+                # what it left
+                pre = None
         self.arnoldi = ar = utils.Arnoldi(
             self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
             Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype,
@@ -943,28 +947,31 @@ class Gmres(_KrylovSolver):
         lookahead = (not self.explicit_residual and ls.exact_solution is None and not is_lanczos
                      and 2 * nr * (m + 2) + 1 <= HALF)
 
-        # Whole-cycle graph (row-partitioned restarted runs, from the third cycle over one workspace on): ALL
-        # maxiter steps of the cycle are one CUDA graph with one mailbox record per step -- look-ahead taken to
-        # its end.  An Arnoldi step never depends on the host's decisions, so steps past the one the host stops
-        # at are speculative work that nothing reads (as with the one-step look-ahead).  The host synchronises
-        # once per cycle and books the records of the steps that neither converge nor look invariant in bulk.
-        # Measured on 8 B200 (C2): 92 us/step inside the cycle graph against 115 us paced by the host
-        # (profiles/r2_cycle_graph_probe.txt).  KRY_CYCLE_GRAPH=0 keeps the per-step graphs.
+        # Whole cycle ahead (restarted runs, from the third cycle over one workspace on): ALL maxiter steps of
+        # the cycle are enqueued at once -- as ONE CUDA graph where graphs are on (row-partitioned runs), step by
+        # step otherwise -- with one mailbox record per step: look-ahead taken to its end.  An Arnoldi step never
+        # depends on the host's decisions, so steps past the one the host stops at are speculative work that
+        # nothing reads (as with the one-step look-ahead).  The host synchronises once per cycle and books the
+        # records of the steps that neither converge nor look invariant in bulk.  Measured on 8 B200 (C2):
+        # 92 us/step inside the cycle graph against 115 us paced by the host
+        # (profiles/r2_cycle_graph_probe.txt).  KRY_CYCLE_AHEAD=0 keeps the step-by-step pace.
         rec = [2 * nr * (j + 2) + 1 for j in range(m)]
         cyc_offs = numpy.concatenate([[0], numpy.cumsum(rec)]).astype(numpy.int64)
-        cycle_mode = (use_graphs and lookahead and ws.uses >= 3 and not cplx
+        cycle_mode = (ws is not None and type(self) is Gmres and getattr(ctx, "cycle_ahead", False)
+                      and self.ortho not in ("lanczos", "house") and lookahead and ws.uses >= 3 and not cplx
                       and int(cyc_offs[-1]) <= _lib.KRY_MAILBOX_DOUBLES
-                      and os.environ.get("KRY_CYCLE_GRAPH", "1") not in ("0", ""))
+                      and os.environ.get("KRY_CYCLE_AHEAD", "1") not in ("0", ""))
 
         def off_of(k):
             if cycle_mode:
                 return int(cyc_offs[k])
             return (k & 1) * HALF if lookahead else 0
 
-        # graph runs keep R on the device: step k's rotated column goes to row k of Rt (column after column),
+        # restarted runs keep R on the device: step k's rotated column goes to row k of Rt (column after column),
         # and the solution update solves against it in place (kry_tri_solve_t) instead of uploading the host copy
         Rt = None
-        if use_graphs and not cplx:
+        if (ws is not None and type(self) is Gmres and getattr(ctx, "cycle_ahead", False) and not cplx
+                and self.ortho not in ("lanczos", "house")):
             Rt = self._Rt_dev = ws.tensor("Rt", (m, m + 2), lambda: ctx.zeros((m, m + 2), t.float64))
 
         def step(k):
@@ -993,11 +1000,10 @@ class Gmres(_KrylovSolver):
         launched = -1
         k = -1
         _mark(self, "arnoldi_init")
-        if cycle_mode:
-            g = ws.graphs.get("cycle")
-            if pre is not None and g is not None:
-                pre["event"].synchronize()                     # launched by the previous cycle's solver
-            else:
+        def launch_cycle():
+            """all m steps of a cycle over the workspace's buffers: one graph replay, or m eager steps"""
+            if use_graphs:
+                g = ws.graphs.get("cycle")
                 if g is None:
                     g = t.cuda.CUDAGraph()
                     with t.cuda.graph(g):
@@ -1007,8 +1013,18 @@ class Gmres(_KrylovSolver):
                     ctx.use_current_stream()
                     ws.graphs["cycle"] = g
                 g.replay()
-                events[0].record()
-                events[0].synchronize()
+            else:
+                for j in range(m):
+                    step(j)
+            ev = ctx.event()
+            ev.record()
+            return ev
+
+        if cycle_mode:
+            if pre is not None:
+                pre["event"].synchronize()                     # launched by the previous cycle's solver
+            else:
+                launch_cycle().synchronize()
             launched = m - 1
             resid_all = mb[cyc_offs[:m]] / ls.MMlb_norm
             if m >= 2 and bool(numpy.all(resid_all[:m - 1] > self.tol)):
@@ -1019,8 +1035,11 @@ class Gmres(_KrylovSolver):
                 # announced one, and only then waits for the norm.  If the bookkeeping finds a step that needs a
                 # decision after all (an invariant-looking subspace), the early results are dropped and the
                 # step-by-step loop below takes over -- nothing has been overwritten at that point.
+                # (speculation only while the cycle's last updated residual is well above the tolerance: the
+                #  explicit residual then cannot meet it, and no cycle is ever launched for nothing)
                 can_pre = (self._prelaunch and Rt is not None and ar.M is None and ar._euclid
-                           and not self.store_arnoldi and os.environ.get("KRY_PRELAUNCH", "1") not in ("0", ""))
+                           and not self.store_arnoldi and bool(resid_all[m - 1] > 2.0 * self.tol)
+                           and os.environ.get("KRY_PRELAUNCH", "1") not in ("0", ""))
                 state = {"ok": False}
 
                 def before_sync(MMlr, Mlr, nrm_dev):
@@ -1032,10 +1051,7 @@ class Gmres(_KrylovSolver):
                         ctx.scale_dev(nrm_dev, 1, 1.0, Mlr[0], ar._Vd[0])          # v_0 = r / ||r||
                         if ctx.comm is not None:
                             ctx.comm.halo_ready = None
-                        g.replay()
-                        ev = ctx.event()
-                        ev.record()
-                        ws.prelaunched = dict(Mlr=Mlr, m=m, ortho=self.ortho, ls=ls, event=ev)
+                        ws.prelaunched = dict(Mlr=Mlr, m=m, ortho=self.ortho, ls=ls, event=launch_cycle())
                     fill = self._book_cycle_records(ar, snap, cyc_offs, m)
                     if fill is None:
                         return
@@ -1071,7 +1087,7 @@ class Gmres(_KrylovSolver):
                 if fill is not None:
                     fill()
         elif pre is not None:
-            raise RuntimeError("speculative cycle without a cycle graph")      # (cannot happen: same conditions)
+            raise RuntimeError("a speculative cycle was accepted outside the cycle-ahead mode")      # (same conditions)
         while (self.resnorms[-1] > self.tol and ar.iter < ar.maxiter and not ar.invariant):
             k = self.iter = ar.iter
             if k == ar.maxiter - 1:
