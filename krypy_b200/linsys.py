@@ -285,7 +285,8 @@ def _norm_dev(xd, yd, ip_B, before_sync=None):
         t = _device.torch()
         host = ctx.__dict__.get("_pinned_norm")
         if host is None:
-            host = ctx.__dict__["_pinned_norm"] = t.zeros(1, dtype=t.float64).pin_memory()
+            host = t.zeros(1, dtype=t.float64)
+            host = ctx.__dict__["_pinned_norm"] = host.pin_memory() if t.cuda.is_available() else host
         host.copy_(tmp, non_blocking=True)
         ev = ctx.event()
         ev.record()
@@ -910,6 +911,8 @@ class Gmres(_KrylovSolver):
                 # not this start: the usual set-up below is enqueued behind the stale cycle and overwrites
                 # what it left
                 pre = None
+        if pre is not None:
+            ws.prelaunch_hits = getattr(ws, "prelaunch_hits", 0) + 1
         self.arnoldi = ar = utils.Arnoldi(
             self.MlAMr, self.__dict__["_Mlr0_dev"], maxiter=self.maxiter, ortho=self.ortho, M=ls.M,
             Mv=self.__dict__["_MMlr0_dev"], Mv_norm=self.MMlr0_norm, ip_B=ls.ip_B, dtype=self.dtype,
@@ -1232,6 +1235,7 @@ class _RestartedSolver(object):
         xk_dev = None
         if Solver is Gmres and "_workspace" not in kwargs:
             kwargs["_workspace"] = utils.SolverWorkspace()
+        self._workspace = kwargs.get("_workspace")
         while restart == 0 or (self.resnorms[-1] > tol and restart <= max_restarts):
             try:
                 if xk_dev is not None:

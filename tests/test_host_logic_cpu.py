@@ -205,3 +205,131 @@ def test_cholqr2_host_logic(fake):
     import krypy_b200 as kp
     check_cholqr2_against_mgs(kp)
     assert fake.calls.get("gram", 0) >= 4 and fake.calls.get("block_trsm", 0) >= 2
+
+
+# ---------------------------------------------------------------- restart cycles enqueued ahead of the host
+def _restarted_vs_oracle(kp, A, b, m, restarts, tol, M=None):
+    from oracle import krylov_oracle as ko
+    ls = kp.linsys.LinearSystem(A, b, M=M)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        try:
+            sol = kp.linsys.RestartedGmres(ls, maxiter=m, max_restarts=restarts, tol=tol, ortho="cgs")
+        except kp.utils.ConvergenceError as e:
+            sol = e.solver
+        try:
+            ref = ko.restarted_gmres(ko.System(A, b, M=M), maxiter=m, max_restarts=restarts, tol=tol)
+        except ko.OracleConvergenceError as e:
+            ref = e.result
+    return sol, ref
+
+
+@pytest.mark.parametrize("withM", [False, True])
+@pytest.mark.parametrize("tol,restarts", [(1e-14, 4), (1e-6, 60)])
+def test_cycle_ahead_mode_over_the_double(fake, monkeypatch, tol, restarts, withM):
+    """linsys.Gmres from the third restart cycle on: all steps of a cycle enqueued at once, records booked in
+    bulk, the cycle's end enqueued before the bookkeeping, the next cycle launched speculatively on the
+    device-side norm (a real-device feature, switched on for the double here).  Same histories, solution, H
+    and R as the step-by-step pace and as the oracle; the 1e-6 case converges in the middle of such a cycle."""
+    import krypy_b200 as kp
+    from krypy_b200 import problems
+    import scipy.sparse as sp
+    n = 24
+    A = problems.laplace2d(n)
+    rng = np.random.default_rng(3)
+    dM = sp.diags(1.0 / (4.0 + rng.random(n * n))).tocsr() if withM else None
+    b = rng.standard_normal((n * n, 1))
+    fake.cycle_ahead = False
+    base, ref = _restarted_vs_oracle(kp, A, b, 8, restarts, tol, dM)
+    calls_base = dict(fake.calls)
+    fake.reset_launch_count()
+    fake.cycle_ahead = True
+    sol, _ = _restarted_vs_oracle(kp, A, b, 8, restarts, tol, dM)
+    assert fake.calls.get("tri_solve_t", 0) > 0 and calls_base.get("tri_solve_t", 0) == 0      # the mode was on
+    hits = getattr(sol._workspace, "prelaunch_hits", 0)
+    ncycles = (len(sol.resnorms) - 1 + 7) // 8
+    # cycles 4.. of a solve without M start from a cycle their predecessor launched speculatively
+    # (one less when the cycle before the last ended within 2 tol: no speculation that close to convergence)
+    assert (hits == 0) if withM else (max(ncycles - 4, 0) <= hits <= max(ncycles - 3, 0)), (hits, ncycles)
+    assert np.array_equal(np.array(sol.resnorms), np.array(base.resnorms))                      # bit for bit
+    assert np.array_equal(sol.xk, base.xk)
+    last, last0 = sol._last, base._last
+    assert np.array_equal(last.R, last0.R) and np.array_equal(last.arnoldi.H, last0.arnoldi.H)
+    assert last.iter == last0.iter and last.arnoldi.iter == last0.arnoldi.iter
+    _check_history(np.array(sol.resnorms), np.array(ref.resnorms))
+    if tol > 1e-10:
+        assert sol.resnorms[-1] <= tol and (len(sol.resnorms) - 1) % 8 != 0
+    # speculation is announced by the restart driver only: a cycle launched for a solve that then converges
+    # would be garbage nobody reads, but none is launched once the updated residual is within 2 tol
+    monkeypatch.setenv("KRY_PRELAUNCH", "0")
+    fake.reset_launch_count()
+    sol2, _ = _restarted_vs_oracle(kp, A, b, 8, restarts, tol, dM)
+    assert np.array_equal(np.array(sol2.resnorms), np.array(base.resnorms))
+    assert getattr(sol2._workspace, "prelaunch_hits", 0) == 0
+
+
+def test_cycle_records_bulk_booking_stops_at_the_first_step_that_needs_a_decision(fake):
+    """Gmres._book_cycle_records / _no_invariance_in_sight on a synthetic mailbox: convergence in the middle,
+    an invariant-looking step, NaN -- the bulk path books exactly the steps before, the loop takes the rest"""
+    import krypy_b200 as kp
+    m = 6
+    offs = np.concatenate([[0], np.cumsum([2 * (j + 2) + 1 for j in range(m)])]).astype(np.int64)
+    rng = np.random.default_rng(5)
+
+    def mailbox(resid, sub):
+        mb = np.zeros(int(offs[-1]))
+        for j in range(m):
+            o = offs[j]
+            mb[o] = resid[j]
+            mb[o + 1:o + 1 + j + 2] = rng.standard_normal(j + 2)
+            mb[o + 1 + j + 1] = sub[j]                       # H[j+1, j]
+            mb[o + 1 + j + 2:o + 1 + 2 * (j + 2)] = rng.standard_normal(j + 2)
+        return mb
+
+    class _Ls(object):
+        MMlb_norm = 2.0
+
+    def solver():
+        s = object.__new__(kp.linsys.Gmres)
+        s.linear_system = _Ls()
+        s.tol = 1e-3
+        s.resnorms = [1.0]
+        s.R = np.zeros((m + 1, m))
+        s._ws = kp.utils.SolverWorkspace(graphs="off")
+        ar = type("A", (), {})()
+        ar.H = np.zeros((m + 1, m))
+        ar._hfro2 = 0.0
+        ar.iter = 0
+        return s, ar
+
+    # (1) nothing special: all but the last step are booked, the fills are deferred
+    s, ar = solver()
+    mb = mailbox([1.0, 0.8, 0.6, 0.4, 0.2, 0.1], [1.0] * m)
+    assert s._no_invariance_in_sight(ar, mb, offs, m)
+    fill = s._book_cycle_records(ar, mb, offs, m)
+    assert fill is not None and ar.iter == m - 1 and s.iter == m - 2
+    assert np.all(s.R == 0.0) and len(s.resnorms) == 2
+    fill()
+    assert s.resnorms == [1.0] + [v / 2.0 for v in (1.0, 0.8, 0.6, 0.4, 0.2)]
+    for j in range(m - 1):
+        assert np.array_equal(ar.H[: j + 2, j], mb[offs[j] + 1:offs[j] + 1 + j + 2])
+        assert np.array_equal(s.R[: j + 2, j], mb[offs[j] + 1 + j + 2:offs[j] + 1 + 2 * (j + 2)])
+    assert np.all(ar.H[:, m - 1] == 0.0) and np.all(s.R[:, m - 1] == 0.0)
+    assert np.isclose(ar._hfro2, sum(float(np.sum(ar.H[:, j] ** 2)) for j in range(m - 1)))
+    # (2) the updated residual meets the tolerance at step 3: steps 0..2 in bulk, at once
+    s, ar = solver()
+    mb = mailbox([1.0, 0.8, 0.6, 1e-3, 0.2, 0.1], [1.0] * m)
+    assert s._book_cycle_records(ar, mb, offs, m) is None and ar.iter == 3 and len(s.resnorms) == 4
+    assert np.any(s.R[:, 2] != 0.0) and np.all(s.R[:, 3] == 0.0)
+    # (3) an invariant-looking subspace at step 2 (tiny H[3, 2]) and (4) NaN: the bulk path stops before
+    for bad in (1e-16, np.nan):
+        s, ar = solver()
+        sub = [1.0] * m
+        sub[2] = bad
+        mb = mailbox([1.0, 0.8, 0.6, 0.4, 0.2, 0.1], sub)
+        assert not s._no_invariance_in_sight(ar, mb, offs, m)
+        assert s._book_cycle_records(ar, mb, offs, m) is None and ar.iter == 2 and len(s.resnorms) == 3
+    # (5) convergence at step 0: nothing is booked
+    s, ar = solver()
+    mb = mailbox([1e-4, 0.8, 0.6, 0.4, 0.2, 0.1], [1.0] * m)
+    assert s._book_cycle_records(ar, mb, offs, m) is None and ar.iter == 0 and s.resnorms == [1.0]
