@@ -963,7 +963,9 @@ class Gmres(_KrylovSolver):
         cycle_mode = (ws is not None and type(self) is Gmres and getattr(ctx, "cycle_ahead", False)
                       and self.ortho not in ("lanczos", "house") and lookahead and ws.uses >= 3 and not cplx
                       and int(cyc_offs[-1]) <= _lib.KRY_MAILBOX_DOUBLES
-                      and os.environ.get("KRY_CYCLE_AHEAD", "1") not in ("0", ""))
+                      and os.environ.get("KRY_CYCLE_AHEAD", "1") not in ("0", "")
+                      # (nothing to run ahead when the start already meets the tolerance or is the zero vector)
+                      and (pre is not None or (self.resnorms[-1] > self.tol and not ar.invariant)))
 
         def off_of(k):
             if cycle_mode:
