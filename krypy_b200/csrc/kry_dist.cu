@@ -279,26 +279,28 @@ __global__ void __launch_bounds__(KRY_THREADS, 2) dist_update_scale_kernel(UpdSc
             const double part = update_scale_dispatch<T, VEC>(a.V, a.ldv, nv, c_s, a.q, (T*)nullptr, a.n, 1.0, false, nsweep);
             const double s = kry_block_sum(part, sm);
             if (threadIdx.x == 0) a.partials[blockIdx.x] = s;
+        }
+        // every CTA of the grid (the extra one too: it has read the epoch by now) takes a ticket; the last
+        // one sums the sweepers' partials, publishes and advances the epoch
+        __threadfence();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            unsigned int t = atomicAdd(a.ticket, 1u);
+            last = (t == gridDim.x - 1u);
+        }
+        __syncthreads();
+        if (last) {
             __threadfence();
+            double v = 0.0;
+            for (int b = threadIdx.x; b < nsweep; b += blockDim.x) v += __ldcg(a.partials + b);
+            const double tot = kry_block_sum(v, sm);
             __syncthreads();
+            if (threadIdx.x == 0) gsh[0] = tot;
+            __syncthreads();
+            peer_publish(pa, E + 1ull, gsh, 1);
             if (threadIdx.x == 0) {
-                unsigned int t = atomicAdd(a.ticket, 1u);
-                last = (t == (unsigned int)nsweep - 1u);
-            }
-            __syncthreads();
-            if (last) {
-                __threadfence();
-                double v = 0.0;
-                for (int b = threadIdx.x; b < nsweep; b += blockDim.x) v += __ldcg(a.partials + b);
-                const double tot = kry_block_sum(v, sm);
-                __syncthreads();
-                if (threadIdx.x == 0) gsh[0] = tot;
-                __syncthreads();
-                peer_publish(pa, E + 1ull, gsh, 1);
-                if (threadIdx.x == 0) {
-                    *pa.epoch_dev = E + 1ull;
-                    *a.ticket = 0u;
-                }
+                *pa.epoch_dev = E + 1ull;
+                *a.ticket = 0u;
             }
         }
         const bool ok2 = peer_wait(pa, E + 1ull, &okflag);
