@@ -257,7 +257,15 @@ def config_dict(args, world):
                         "b=default_rng(0).standard_normal; one step = one 30-iteration cycle" % (n, n * n),
             "N": n * n, "restart": RESTART, "tol": TOL, "ortho": args.ortho,
             "partition": "single GPU" if world == 1 else "row-partitioned over %d GPUs" % world,
-            "l2": "inputs larger than L2 (basis 2.5 GB, A 0.64 GB vs 126 MB L2): no flush needed"}
+            "l2": "inputs larger than L2 (basis 2.5 GB, A 0.64 GB vs 126 MB L2): no flush needed",
+            "pacing": ("restart cycles as linsys.RestartedGmres runs them: from the third cycle over one workspace on, "
+                       "all 30 steps of a cycle are enqueued ahead of the host (%s), one host synchronisation per "
+                       "cycle, and the next cycle is launched on the device-side residual norm before the host has "
+                       "read it (every timed step still waits for its own cycle's records, explicit residual and "
+                       "x_k; the cycle launched at the end of the last timed step is inside the timed region, the "
+                       "one the first timed step starts from was launched by the last warm-up step)"
+                       % ("eager launches with live per-kernel CUDA events" if world == 1 else
+                          "one CUDA graph per cycle; one cross-GPU wait per Arnoldi step"))}
 
 
 # ---------------------------------------------------------------------------------------
