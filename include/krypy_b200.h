@@ -68,6 +68,13 @@ void        kry_reset_launch_count(kry_ctx* ctx);
 int kry_spmv_csr(kry_ctx* ctx, int dtype, long long nrows, long long ncols, long long nnz,
                  const int* rowptr, const int* colidx, const void* vals,
                  const void* x, void* y, const void* w_dev, double* dot_out_dev);
+/* y = A x for CSR A on COMPLEX128 vectors x, y (re, im interleaved), natively: vals is complex128
+ * (vals_complex != 0, 20 bytes per entry) or float64 (a real matrix applied to complex vectors, 12 bytes
+ * per entry) -- scipy csr_matvec on complex data behind krypy/utils.py:1593-1594.  The real-embedding
+ * path moves 48 bytes per entry.  Per row the products are summed in storage order, each product and sum
+ * rounded separately. */
+int kry_spmv_csr_z(kry_ctx* ctx, int vals_complex, long long nrows, long long ncols, long long nnz,
+                   const int* rowptr, const int* colidx, const void* vals, const void* x, void* y);
 /* y = A x for a dense row-major m x n matrix (numpy.ndarray.dot,
  * krypy/utils.py:1593-1594; BASELINE config 1 and the reference's N<=100 tests) */
 int kry_gemv_dense(kry_ctx* ctx, int dtype, long long m, long long n,
@@ -126,6 +133,18 @@ int kry_orth_fused(kry_ctx* ctx, int dtype, long long n, const void* Vdot, const
                    long long ldv, int j0, int nv, void* q, int passes, int algo,
                    const void* pre_vec, const double* pre_coef_dev,
                    double* h_dev, double* nrm_dev, void* vnext);
+
+/* The same step on COMPLEX128 vectors, natively (csrc/kry_cplx.cu): n complex elements per vector
+ * (re, im interleaved, 16-byte aligned), ldv in complex elements, h_dev[2j], h_dev[2j+1] += Re, Im of
+ * c_j = <Vdot_j, q> = sum_i conj(Vdot_j[i]) q[i] (the reference's inner product, krypy/utils.py:183
+ * X.T.conj() @ Y, as used by Arnoldi.advance utils.py:1012-1029 on complex data -- half of the
+ * reference's own test matrix, test/test_linsys.py:118-141), q -= c_j Vsub_j with complex c_j.
+ * Every basis vector is read once per sweep (the real-embedding path reads v_j and its twin i v_j).
+ * KRY_ORTH_CGS: at most 32 vectors per call.  No pre-subtraction argument: the Lanczos recurrence has
+ * real coefficients (utils.py:1003-1009) and runs on the real kernels. */
+int kry_orth_fused_z(kry_ctx* ctx, long long n, const void* Vdot, const void* Vsub, long long ldv,
+                     int j0, int nv, void* q, int passes, int algo,
+                     double* h_dev, double* nrm_dev, void* vnext);
 
 /* Fused Lanczos step for a DIAGONAL inner-product matrix B = diag(bdiag) (BASELINE config C5),
  * krypy/utils.py:1000-1045 with inner(X, Y, ip_B) = X^H (B Y) (utils.py:190-193), ONE cooperative

@@ -262,6 +262,39 @@ class Context(object):
         vals = t.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)).to(self.device)
         return CsrDev(rowptr, colidx, vals, A.shape)
 
+    def upload_csr_z(self, A):
+        """scipy.sparse matrix -> CsrDev for the NATIVE complex SpMV (kry_spmv_csr_z): complex128 values for
+        a complex matrix (20 bytes per entry), float64 for a real matrix applied to complex vectors (12);
+        the real embedding (_cplx.expand_sparse) holds 48 bytes per entry."""
+        import scipy.sparse as sp
+        t = torch()
+        A = sp.csr_matrix(A) if not sp.isspmatrix_csr(A) else A
+        if not A.has_sorted_indices:
+            A = A.sorted_indices()
+        if A.nnz >= 2 ** 31 - 1:
+            raise NotImplementedError("nnz >= 2^31 needs 64-bit row pointers (not built)")
+        npdt = np.complex128 if np.iscomplexobj(A.data) else np.float64
+        rowptr = t.from_numpy(np.ascontiguousarray(A.indptr, dtype=np.int32)).to(self.device)
+        colidx = t.from_numpy(np.ascontiguousarray(A.indices, dtype=np.int32)).to(self.device)
+        vals = t.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)).to(self.device)
+        obj = CsrDev(rowptr, colidx, vals, A.shape)
+        obj.native_z = True
+        return obj
+
+    def spmv_z(self, A, x, y):
+        """y = A x on complex128 vectors, natively (A from upload_csr_z)"""
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            tm.bracket("spmv", (A.shape[0], A.nnz), lambda: self.spmv_z(A, x, y))
+            self.timer = tm
+            return
+        t = torch()
+        if x.dtype != t.complex128 or y.dtype != t.complex128:
+            raise TypeError("spmv_z works on complex128 vectors")
+        check(self.lib.kry_spmv_csr_z(self.h, 1 if A.vals.dtype == t.complex128 else 0, A.shape[0], A.shape[1],
+                                      A.nnz, A.rowptr.data_ptr(), A.colidx.data_ptr(), A.vals.data_ptr(),
+                                      x.data_ptr(), y.data_ptr()))
+
     # ---- operators -------------------------------------------------------
     @realviews
     def spmv(self, A, x, y, w=None, dot_out=None):
@@ -348,6 +381,24 @@ class Context(object):
         check(self.lib.kry_orth_fused(self.h, code(q), q.numel(), _p(Vdot), _p(Vsub), ld, int(j0), int(nv),
                                       q.data_ptr(), int(passes), int(algo), _p(pre_vec), _p(pre_coef),
                                       hp, _p(nrm), _p(vnext)))
+
+    def orth_fused_z(self, Vdot, Vsub, ldv, j0, nv, q, passes, algo, h_ptr, nrm=None, vnext=None):
+        """kry_orth_fused_z: the fused Gram-Schmidt step on complex128 vectors, natively.  Vdot / Vsub: tensor
+        (or address) of complex vector 0 of the basis, ``ldv`` complex elements between consecutive vectors
+        (twin storage: the even rows, ldv = the real row stride); q, vnext: complex vectors (any view of
+        their 2N doubles); h_ptr: address of the interleaved coefficient array (2 doubles per vector, +=);
+        nrm: device double."""
+        n = q.numel() if q.dtype == torch().complex128 else q.numel() // 2
+        if self.timer is not None:
+            tm, self.timer = self.timer, None
+            tm.bracket("orth", (2 * n, 2 * (int(nv) - int(j0)), int(passes), int(algo), vnext is not None),
+                       lambda: self.orth_fused_z(Vdot, Vsub, ldv, j0, nv, q, passes, algo, h_ptr, nrm, vnext))
+            self.timer = tm
+            return
+        if self.comm is not None:
+            raise NotImplementedError("complex row-partitioned runs are not implemented")
+        check(self.lib.kry_orth_fused_z(self.h, n, _p(Vdot), _p(Vsub), int(ldv), int(j0), int(nv), q.data_ptr(),
+                                        int(passes), int(algo), _p(h_ptr), _p(nrm), _p(vnext)))
 
     def _orth_split(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef, h_ptr,
                     halo_op=None):

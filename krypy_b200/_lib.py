@@ -51,6 +51,10 @@ PROTOTYPES = {
     "kry_orth_fused": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int,
                                c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p, c_void_p,
                                c_void_p]),
+    "kry_orth_fused_z": (c_int, [c_void_p, c_ll, c_void_p, c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_int,
+                                 c_void_p, c_void_p, c_void_p]),
+    "kry_spmv_csr_z": (c_int, [c_void_p, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p,
+                               c_void_p]),
     "kry_lanczos_diag": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                  c_void_p, c_void_p]),
     "kry_lanczos_diag_dist": (c_int, [c_void_p, c_int, c_ll, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,

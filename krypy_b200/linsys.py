@@ -539,7 +539,7 @@ class Cg(_KrylovSolver):
         euclid = utils._is_identity_ip(ls.ip_B)
         if euclid and type(op) is utils.MatrixLinearOperator:
             A = op._dev(p.dtype)
-            if isinstance(A, _device.CsrDev):
+            if isinstance(A, _device.CsrDev) and not getattr(A, "native_z", False):
                 ctx.spmv(A, p[0], Ap[0], w=p[0], dot_out=pAp)      # fused <p,Ap> epilogue
                 return
         if euclid and hasattr(op, "_apply_dot_dev"):

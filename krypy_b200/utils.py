@@ -583,10 +583,11 @@ class MatrixLinearOperator(_DeviceOperator):
         self._devcache = {}
 
     def _dev(self, tdtype, adj=False):
-        key = (tdtype, adj)
+        ctx = _ctx()
+        native_z = bool(_NATIVE_Z) and ctx.comm is None and tdtype == _device.torch().complex128
+        key = (tdtype, adj, native_z)
         obj = self._devcache.get(key)
         if obj is None:
-            ctx = _ctx()
             if adj and self._A_adj is None:
                 self._A_adj = self._A.T.conj()
             A = self._A_adj if adj else self._A
@@ -594,7 +595,10 @@ class MatrixLinearOperator(_DeviceOperator):
             if tdtype == t.complex128:
                 # complex vectors: the real kernels apply the 2N x 2N real embedding of A to the
                 # interleaved real views (entry a+ib -> [[a, -b], [b, a]], krypy_b200/_cplx.py)
-                if _isspmatrix(A):
+                # (sparse, default: the matrix as it is for the native complex SpMV kry_spmv_csr_z)
+                if _isspmatrix(A) and native_z:
+                    obj = ctx.upload_csr_z(A)
+                elif _isspmatrix(A):
                     obj = ctx.upload_csr(_cplx.expand_sparse(A), t.float64)
                 else:
                     obj = t.from_numpy(_cplx.expand_dense(numpy.asarray(A))).to(ctx.device)
@@ -615,8 +619,11 @@ class MatrixLinearOperator(_DeviceOperator):
         if out is None:
             out = ctx.empty((k, self.shape[1] if adj else self.shape[0]), Xd.dtype)
         sparse = isinstance(A, _device.CsrDev)
+        native_z = sparse and getattr(A, "native_z", False)
         for j in range(k):
-            if sparse:
+            if native_z:
+                ctx.spmv_z(A, Xd[j], out[j])
+            elif sparse:
                 ctx.spmv(A, Xd[j], out[j])
             else:
                 ctx.gemv(A, Xd[j], out[j])
@@ -1565,6 +1572,11 @@ _CGS_CHUNK = 64   # KRY_MAX_SLOTS of csrc/kry_common.cuh
 # default since round 2 (validated on B200: +30 % on config C5); KRY_LANCZOS_DIAGB=0 selects the
 # generic seven-launch sequence
 _LANCZOS_DIAGB = __import__("os").environ.get("KRY_LANCZOS_DIAGB", "1") not in ("0", "")
+# native complex128 kernels of the Arnoldi hot loop (csrc/kry_cplx.cu: kry_orth_fused_z reads every basis vector
+# once instead of the vector and its twin; kry_spmv_csr_z moves 20 instead of 48 bytes per matrix entry);
+# KRY_NATIVE_Z=0 selects the real-embedding kernels for these two as well (krypy_b200/_cplx.py)
+_NATIVE_Z = __import__("os").environ.get("KRY_NATIVE_Z", "1") not in ("0", "")
+_CGS_CHUNK_Z = 32   # complex vectors per kry_orth_fused_z call (two reduction slots each)
 
 
 class DeviceBlock(object):
@@ -1854,7 +1866,22 @@ class Arnoldi(object):
             nrm = self._hcol[nr * (k + 1):]
             pre_vec = pre_coef = None
         vnext = Vt[nr * (k + 1)]
-        if self._euclid:
+        if self._euclid and cplx and not lanczos and _NATIVE_Z and ctx.comm is None:
+            # native complex sweep (kry_orth_fused_z) over the vectors themselves: the even rows of the twin
+            # storage, one read per basis vector; complex coefficients interleaved in hcol as on the twin path
+            fused_tail = self.M is None
+            ldz = Vt.stride(0)               # complex elements between v_j and v_{j+1} (two real rows)
+            j0, nvz = 0, k + 1
+            while True:
+                j1 = nvz if self._algo != KRY_ORTH_CGS else min(j0 + _CGS_CHUNK_Z, nvz)
+                last = j1 == nvz
+                ctx.orth_fused_z(Vt, Vsub, ldz, j0, j1, q0, self._passes, self._algo, h_ptr,
+                                 nrm=nrm if (last and fused_tail) else None,
+                                 vnext=vnext if (last and fused_tail) else None)
+                if last:
+                    break
+                j0 = j1
+        elif self._euclid:
             fused_tail = self.M is None
             if self._algo == KRY_ORTH_CGS and (r1 - r0) > _CGS_CHUNK:
                 # more basis vectors than reduction slots: block-wise CGS

@@ -1,0 +1,452 @@
+// TEST INFRASTRUCTURE (CPU tier) -- runs the DEVICE code of kry_orth_fused_z / kry_spmv_csr_z
+// (krypy_b200/csrc/kry_zorth.cuh, kry_zspmv.cuh, included unchanged) on the host over the CUDA execution
+// emulator of tests/csrc/cuda_emul and compares with extended-precision references.  See cuda_runtime.h there
+// for what the emulation is and what it proves.  Driven by tests/test_cplx_emul_cpu.py:
+//     cplx_emul_host orth <algo 0|1> <passes> <nv> <j0> <n> <grid> <separate_P 0|1>
+//     cplx_emul_host spmv <kind> <cplx 0|1> <grid>
+// prints one line "ok <max error> ..." or "FAIL ..." and exits 0 / 1.
+#define KRY_EMUL 1
+#include <pthread.h>
+#include <sched.h>
+#include <sys/mman.h>
+#include <sys/wait.h>
+#include <unistd.h>
+
+#include <complex>
+#include <functional>
+#include <map>
+#include <random>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+// ------------------------------------------------------------------ emulator runtime
+thread_local uint3 threadIdx;
+uint3 blockIdx;
+dim3 blockDim, gridDim;
+
+struct WarpX {
+    pthread_barrier_t bar;
+    double buf[32];
+};
+static pthread_barrier_t g_block_bar, g_named_bar;
+static WarpX g_warps[32];
+static pthread_barrier_t* g_grid_bar;
+static unsigned char* g_dyn_smem;
+
+void __syncthreads() { pthread_barrier_wait(&g_block_bar); }
+void __syncwarp() { pthread_barrier_wait(&g_warps[threadIdx.x >> 5].bar); }
+void __threadfence() { __sync_synchronize(); }
+void __threadfence_system() { __sync_synchronize(); }
+unsigned int atomicAdd(unsigned int* p, unsigned int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
+unsigned char* kry_emul_dynamic_smem() { return g_dyn_smem; }
+double __shfl_xor_sync(unsigned int, double v, int lane_mask) {
+    WarpX& w = g_warps[threadIdx.x >> 5];
+    const int lane = threadIdx.x & 31;
+    w.buf[lane] = v;
+    pthread_barrier_wait(&w.bar);
+    const double r = w.buf[lane ^ lane_mask];
+    pthread_barrier_wait(&w.bar);
+    return r;
+}
+void kry_emul_grid_sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) pthread_barrier_wait(g_grid_bar);
+    __syncthreads();
+}
+
+// mbarrier + bulk copy (the PTX wrappers of kry_zspmv.cuh)
+struct EmBar {
+    uint32_t count;
+    int32_t pending;
+    int64_t tx;
+    uint32_t phase;
+};
+static std::map<uintptr_t, EmBar> g_bars;
+static pthread_mutex_t g_bar_mu = PTHREAD_MUTEX_INITIALIZER;
+static void embar_check(EmBar& b) {
+    if (b.tx < 0) {
+        fprintf(stderr, "emulated mbarrier: more bytes completed than expected\n");
+        _exit(3);
+    }
+    if (b.pending == 0 && b.tx == 0) {
+        b.phase++;
+        b.pending = (int32_t)b.count;
+    }
+}
+static EmBar& embar(uint64_t* bar) {
+    auto it = g_bars.find((uintptr_t)bar);
+    if (it == g_bars.end()) {
+        fprintf(stderr, "emulated mbarrier used before init\n");
+        _exit(3);
+    }
+    return it->second;
+}
+void z_mbar_init(uint64_t* bar, uint32_t count) {
+    pthread_mutex_lock(&g_bar_mu);
+    g_bars[(uintptr_t)bar] = EmBar{count, (int32_t)count, 0, 0};
+    pthread_mutex_unlock(&g_bar_mu);
+}
+void z_mbar_fence_init() {}
+void z_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    pthread_mutex_lock(&g_bar_mu);
+    EmBar& b = embar(bar);
+    b.tx += bytes;
+    b.pending--;
+    embar_check(b);
+    pthread_mutex_unlock(&g_bar_mu);
+}
+void z_mbar_arrive(uint64_t* bar) {
+    pthread_mutex_lock(&g_bar_mu);
+    EmBar& b = embar(bar);
+    b.pending--;
+    if (b.pending < 0) {
+        fprintf(stderr, "emulated mbarrier: too many arrivals\n");
+        _exit(3);
+    }
+    embar_check(b);
+    pthread_mutex_unlock(&g_bar_mu);
+}
+void z_mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (long spins = 0;; ++spins) {
+        pthread_mutex_lock(&g_bar_mu);
+        const bool done = (embar(bar).phase & 1u) != parity;
+        pthread_mutex_unlock(&g_bar_mu);
+        if (done) return;
+        if (spins > 4000000) {
+            fprintf(stderr, "emulated mbarrier: wait timed out (deadlock in the ring protocol)\n");
+            _exit(4);
+        }
+        usleep(20);
+    }
+}
+static size_t g_smem_bytes = 0;
+void z_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    // the hardware requires 16-byte aligned addresses and sizes; the destination must lie in the CTA's window
+    if (((uintptr_t)dst_smem & 15) || ((uintptr_t)src_gmem & 15) || (bytes & 15)) {
+        fprintf(stderr, "bulk copy: misaligned address or size (%p %p %u)\n", dst_smem, src_gmem, bytes);
+        _exit(5);
+    }
+    if ((unsigned char*)dst_smem < g_dyn_smem || (unsigned char*)dst_smem + bytes > g_dyn_smem + g_smem_bytes) {
+        fprintf(stderr, "bulk copy: destination outside the dynamic shared memory window\n");
+        _exit(5);
+    }
+    memcpy(dst_smem, src_gmem, bytes);
+    pthread_mutex_lock(&g_bar_mu);
+    EmBar& b = embar(bar);
+    b.tx -= bytes;
+    embar_check(b);
+    pthread_mutex_unlock(&g_bar_mu);
+}
+void z_consumer_bar_sync() { pthread_barrier_wait(&g_named_bar); }
+
+#include "kry_zorth.cuh"
+#include "kry_zspmv.cuh"
+
+template <typename T> static T* dev_alloc(size_t count) {
+    void* p = mmap(nullptr, count * sizeof(T) + 64, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) {
+        perror("mmap");
+        exit(2);
+    }
+    return (T*)p;
+}
+
+struct ThreadArg {
+    int t;
+    const std::function<void()>* body;
+};
+static void* thread_main(void* p) {
+    ThreadArg* a = (ThreadArg*)p;
+    threadIdx.x = (unsigned)a->t;
+    threadIdx.y = threadIdx.z = 0;
+    (*a->body)();
+    return nullptr;
+}
+
+// one process per CTA, one OS thread per CUDA thread; returns false if any CTA died
+static bool emul_launch(int G, int nthreads, size_t smem_bytes, const std::function<void()>& body) {
+    g_grid_bar = dev_alloc<pthread_barrier_t>(1);
+    pthread_barrierattr_t ba;
+    pthread_barrierattr_init(&ba);
+    pthread_barrierattr_setpshared(&ba, PTHREAD_PROCESS_SHARED);
+    pthread_barrier_init(g_grid_bar, &ba, (unsigned)G);
+    gridDim = dim3(G);
+    blockDim = dim3(nthreads);
+    std::vector<pid_t> pids;
+    for (int b = 0; b < G; ++b) {
+        pid_t pid = fork();
+        if (pid == 0) {
+            alarm(600);                                   // a deadlocked kernel must not hang the test tier
+            blockIdx.x = (unsigned)b;
+            blockIdx.y = blockIdx.z = 0;
+            pthread_barrier_init(&g_block_bar, nullptr, (unsigned)nthreads);
+            pthread_barrier_init(&g_named_bar, nullptr, 256u);
+            for (int w = 0; w < (nthreads + 31) / 32; ++w) pthread_barrier_init(&g_warps[w].bar, nullptr, 32u);
+            g_smem_bytes = smem_bytes;
+            g_dyn_smem = (unsigned char*)aligned_alloc(128, (smem_bytes + 127) / 128 * 128 + 128);
+            std::vector<pthread_t> th(nthreads);
+            std::vector<ThreadArg> args(nthreads);
+            pthread_attr_t at;
+            pthread_attr_init(&at);
+            pthread_attr_setstacksize(&at, 1 << 20);
+            for (int t = 0; t < nthreads; ++t) {
+                args[t] = ThreadArg{t, &body};
+                if (pthread_create(&th[t], &at, thread_main, &args[t])) {
+                    perror("pthread_create");
+                    _exit(6);
+                }
+            }
+            for (int t = 0; t < nthreads; ++t) pthread_join(th[t], nullptr);
+            _exit(0);
+        }
+        pids.push_back(pid);
+    }
+    bool ok = true;
+    for (pid_t p : pids) {
+        int st = 0;
+        waitpid(p, &st, 0);
+        if (!WIFEXITED(st) || WEXITSTATUS(st) != 0) ok = false;
+    }
+    return ok;
+}
+
+typedef std::complex<long double> CL;
+typedef std::complex<double> CD;
+
+// ------------------------------------------------------------------ kry_orth_fused_z
+static int run_orth(int algo, int passes, int nv, int j0, long long n, int G, int separate_P) {
+    std::mt19937_64 rng(1234 + 7 * nv + n);
+    std::normal_distribution<double> nd;
+    const long long ldv = n + 3;                          // rows need not be contiguous
+    const int nvs = nv > 0 ? nv : 1;
+    Z* V = dev_alloc<Z>((size_t)nvs * ldv);
+    Z* P = separate_P ? dev_alloc<Z>((size_t)nvs * ldv) : V;
+    Z* q = dev_alloc<Z>(n);
+    Z* vnext = dev_alloc<Z>(n);
+    double* h = dev_alloc<double>(2 * nvs + 2);
+    double* partials = dev_alloc<double>(2ull * KRY_MAX_SLOTS * KRY_MAX_PARTIAL_BLOCKS);
+    const double sc = 1.0 / std::sqrt(2.0 * (double)n);
+    for (long long i = 0; i < (long long)nvs * ldv; ++i) {
+        V[i] = make_double2(nd(rng) * sc, nd(rng) * sc);
+        if (separate_P) P[i] = make_double2(nd(rng) * sc, nd(rng) * sc);
+    }
+    std::vector<CD> q0(n);
+    for (long long i = 0; i < n; ++i) {
+        q[i] = make_double2(nd(rng), nd(rng));
+        q0[i] = CD(q[i].x, q[i].y);
+        vnext[i] = make_double2(NAN, NAN);
+    }
+    for (int j = 0; j < 2 * nvs + 2; ++j) h[j] = (j & 1) ? -0.25 : 0.5;
+    // reference (krypy/utils.py:1012-1029 for MGS; block classical Gram-Schmidt for CGS), long double
+    std::vector<CL> qr(q0.begin(), q0.end()), hr(nvs, CL(0, 0));
+    auto Vc = [&](const Z* B, int j, long long i) { return CL(B[(long long)j * ldv + i].x, B[(long long)j * ldv + i].y); };
+    for (int p = 0; p < passes; ++p) {
+        if (algo == KRY_ORTH_CGS) {
+            std::vector<CL> c(nvs, CL(0, 0));
+            for (int j = j0; j < nv; ++j)
+                for (long long i = 0; i < n; ++i) c[j] += std::conj(Vc(V, j, i)) * qr[i];
+            for (int j = j0; j < nv; ++j) {
+                hr[j] += c[j];
+                for (long long i = 0; i < n; ++i) qr[i] -= c[j] * Vc(P, j, i);
+            }
+        } else {
+            for (int j = j0; j < nv; ++j) {
+                CL c(0, 0);
+                for (long long i = 0; i < n; ++i) c += std::conj(Vc(V, j, i)) * qr[i];
+                hr[j] += c;
+                for (long long i = 0; i < n; ++i) qr[i] -= c * Vc(P, j, i);
+            }
+        }
+    }
+    long double nr2 = 0;
+    for (long long i = 0; i < n; ++i) nr2 += std::norm(qr[i]);
+    const long double nr = sqrtl(nr2);
+
+    ZOrthArgs a = {n, V, P, ldv, j0, nv, passes, algo, q, h, h + 2 * nvs, vnext, partials};
+    if (!emul_launch(G, KRY_THREADS, 0, [a]() { zorth_kernel(a); })) {
+        printf("FAIL a CTA died\n");
+        return 1;
+    }
+    double eh = 0, eq = 0, ev = 0, en;
+    for (int j = 0; j < nvs; ++j) {
+        const CD want = (j >= j0 && j < nv) ? CD(0.5, -0.25) + CD((double)hr[j].real(), (double)hr[j].imag()) : CD(0.5, -0.25);
+        eh = fmax(eh, std::abs(CD(h[2 * j], h[2 * j + 1]) - want));
+    }
+    en = fabs(h[2 * nvs] - (double)nr) / (double)nr;
+    if (h[2 * nvs + 1] != -0.25) en = 1.0;                // only one double is written for the norm
+    double qmax = 0;
+    for (long long i = 0; i < n; ++i) qmax = fmax(qmax, std::abs(q0[i]));
+    for (long long i = 0; i < n; ++i) {
+        const CD w((double)qr[i].real(), (double)qr[i].imag());
+        eq = fmax(eq, std::abs(CD(q[i].x, q[i].y) - w) / qmax);
+        ev = fmax(ev, std::abs(CD(vnext[i].x, vnext[i].y) - w / (double)nr));
+    }
+    const bool ok = eh <= 1e-13 && eq <= 1e-13 && ev <= 1e-13 && en <= 1e-13;
+    printf("%s orth algo=%d passes=%d nv=%d j0=%d n=%lld G=%d: h %.2e q %.2e vnext %.2e nrm %.2e\n", ok ? "ok" : "FAIL",
+           algo, passes, nv, j0, n, G, eh, eq, ev, en);
+    return ok ? 0 : 1;
+}
+
+// ------------------------------------------------------------------ kry_spmv_csr_z
+struct Csr {
+    long long nrows, ncols;
+    std::vector<int> rowptr, colidx;
+    std::vector<CD> vals;
+};
+
+static Csr make_matrix(const char* kind, std::mt19937_64& rng) {
+    std::normal_distribution<double> nd;
+    Csr A;
+    auto finish_row = [&]() { A.rowptr.push_back((int)A.colidx.size()); };
+    auto put = [&](int c) {
+        A.colidx.push_back(c);
+        A.vals.push_back(CD(nd(rng), nd(rng)));
+    };
+    A.rowptr.push_back(0);
+    if (!strcmp(kind, "stencil5")) {                      // 5 per row: CPR 6; 2563 rows = 11 tiles
+        const int nx = 11, ny = 233;
+        A.nrows = A.ncols = (long long)nx * ny;
+        for (int r = 0; r < nx * ny; ++r) {
+            const int i = r / ny, j = r % ny;
+            if (i > 0) put(r - ny);
+            if (j > 0) put(r - 1);
+            put(r);
+            if (j < ny - 1) put(r + 1);
+            if (i < nx - 1) put(r + ny);
+            finish_row();
+        }
+    } else if (!strcmp(kind, "band7")) {                  // 7 per row: CPR 8
+        A.nrows = A.ncols = 2100;
+        const int offs[7] = {-30, -2, -1, 0, 1, 2, 30};
+        for (int r = 0; r < 2100; ++r) {
+            for (int o : offs)
+                if (r + o >= 0 && r + o < 2100) put(r + o);
+            finish_row();
+        }
+    } else if (!strcmp(kind, "rand12")) {                 // ~12 per row: CPR 16, ragged rows incl. empty ones
+        A.nrows = 1500;
+        A.ncols = 1700;
+        for (int r = 0; r < 1500; ++r) {
+            const int cnt = (r % 7 == 3) ? 0 : (int)(rng() % 25);
+            int c = (int)(rng() % 40);
+            for (int t = 0; t < cnt && c < 1700; ++t) {
+                put(c);
+                c += 1 + (int)(rng() % 60);
+            }
+            finish_row();
+        }
+    } else if (!strcmp(kind, "ragged")) {                 // mostly one entry per row, one tile far beyond the stage
+        A.nrows = A.ncols = 3000;                         // capacity (direct global loads), nnz % 4 != 0
+        for (int r = 0; r < 3000; ++r) {
+            if (r >= 600 && r < 606) {
+                for (int c = r % 2; c < 3000; c += 2) put(c);
+            } else if (r % 11 != 5) {
+                put(r);
+            }
+            finish_row();
+        }
+        if (A.colidx.size() % 4 == 0) {                   // force an unaligned tail
+            A.colidx.push_back(2999);
+            A.vals.push_back(CD(1.5, -0.5));
+            A.rowptr.back() += 1;
+        }
+    } else if (!strcmp(kind, "tiny")) {
+        A.nrows = A.ncols = 3;
+        put(0); put(1); finish_row();
+        finish_row();
+        put(1); put(2); finish_row();
+    } else if (!strcmp(kind, "long")) {                   // ~60 per row: warp-per-row kernel
+        A.nrows = 300;
+        A.ncols = 900;
+        for (int r = 0; r < 300; ++r) {
+            for (int c = (int)(rng() % 15); c < 900; c += 1 + (int)(rng() % 28)) put(c);
+            finish_row();
+        }
+    } else {
+        fprintf(stderr, "unknown matrix kind %s\n", kind);
+        exit(2);
+    }
+    return A;
+}
+
+template <typename TV> static TV to_val(CD v);
+template <> double2 to_val<double2>(CD v) { return make_double2(v.real(), v.imag()); }
+template <> double to_val<double>(CD v) { return v.real(); }
+
+template <typename TV>
+static int run_spmv_t(const char* kind, int G) {
+    std::mt19937_64 rng(99);
+    std::normal_distribution<double> nd;
+    Csr A = make_matrix(kind, rng);
+    const long long nnz = (long long)A.vals.size();
+    int* rowptr = dev_alloc<int>(A.nrows + 1);
+    int* colidx = dev_alloc<int>(nnz + 4);
+    TV* vals = dev_alloc<TV>(nnz + 4);
+    Z* x = dev_alloc<Z>(A.ncols);
+    Z* y = dev_alloc<Z>(A.nrows);
+    memcpy(rowptr, A.rowptr.data(), sizeof(int) * (A.nrows + 1));
+    memcpy(colidx, A.colidx.data(), sizeof(int) * nnz);
+    for (long long k = 0; k < nnz; ++k) vals[k] = to_val<TV>(A.vals[k]);
+    for (long long i = 0; i < A.ncols; ++i) x[i] = make_double2(nd(rng), nd(rng));
+    for (long long i = 0; i < A.nrows; ++i) y[i] = make_double2(NAN, NAN);
+    const double avg = (double)nnz / (double)A.nrows;
+    const long long nrows = A.nrows;
+    bool ran;
+    const char* path;
+    if (avg <= 5.5) {
+        path = "staged6";
+        ran = emul_launch(G, ZSPMV_THREADS, ZSpmvCfg<TV, 6, 2>::SMEM_BYTES,
+                          [=]() { zspmv_staged_kernel<TV, 6, 2>(nrows, nnz, rowptr, colidx, vals, x, y); });
+    } else if (avg <= 7.5) {
+        path = "staged8";
+        ran = emul_launch(G, ZSPMV_THREADS, ZSpmvCfg<TV, 8, 2>::SMEM_BYTES,
+                          [=]() { zspmv_staged_kernel<TV, 8, 2>(nrows, nnz, rowptr, colidx, vals, x, y); });
+    } else if (avg <= 15.0) {
+        path = "staged16";
+        ran = emul_launch(G, ZSPMV_THREADS, ZSpmvCfg<TV, 16, 2>::SMEM_BYTES,
+                          [=]() { zspmv_staged_kernel<TV, 16, 2>(nrows, nnz, rowptr, colidx, vals, x, y); });
+    } else {
+        path = "warp";
+        ran = emul_launch(G, KRY_THREADS, 0, [=]() { zspmv_warp_kernel<TV>(nrows, rowptr, colidx, vals, x, y); });
+    }
+    if (!ran) {
+        printf("FAIL a CTA died\n");
+        return 1;
+    }
+    double err = 0;
+    long long exact = 0;
+    for (long long r = 0; r < A.nrows; ++r) {
+        CL s(0, 0);
+        long double scale = 1e-300L;
+        CD sd(0, 0);                                      // the kernel's own order and roundings (staged path)
+        for (int k = A.rowptr[r]; k < A.rowptr[r + 1]; ++k) {
+            const CD a = sizeof(TV) == 16 ? A.vals[k] : CD(A.vals[k].real(), 0.0);
+            const CD xv(x[A.colidx[k]].x, x[A.colidx[k]].y);
+            s += CL(a) * CL(xv);
+            scale += std::abs(a) * std::abs(xv);
+            const double pr = sizeof(TV) == 16 ? a.real() * xv.real() - a.imag() * xv.imag() : a.real() * xv.real();
+            const double pi = sizeof(TV) == 16 ? a.real() * xv.imag() + a.imag() * xv.real() : a.real() * xv.imag();
+            sd = CD(sd.real() + pr, sd.imag() + pi);
+        }
+        const CD got(y[r].x, y[r].y);
+        if (got == sd) ++exact;
+        const double e = (double)(std::abs(CL(got) - s) / scale);
+        if (!(e <= err)) err = e;                         // (NaN propagates into err)
+    }
+    const int maxrow = [&]() { int m = 0; for (long long r = 0; r < A.nrows; ++r) m = std::max(m, A.rowptr[r + 1] - A.rowptr[r]); return m; }();
+    const bool ok = err <= 3e-16 * std::max(1, maxrow) && (strcmp(path, "warp") == 0 || exact == A.nrows);
+    printf("%s spmv %s vals=%s path=%s G=%d rows=%lld nnz=%lld: err %.2e, rows bit-identical to the ordered sum %lld\n",
+           ok ? "ok" : "FAIL", kind, sizeof(TV) == 16 ? "complex" : "real", path, G, A.nrows, nnz, err, exact);
+    return ok ? 0 : 1;
+}
+
+int main(int argc, char** argv) {
+    if (argc >= 9 && !strcmp(argv[1], "orth"))
+        return run_orth(atoi(argv[2]), atoi(argv[3]), atoi(argv[4]), atoi(argv[5]), atoll(argv[6]), atoi(argv[7]),
+                        atoi(argv[8]));
+    if (argc >= 5 && !strcmp(argv[1], "spmv"))
+        return atoi(argv[3]) ? run_spmv_t<double2>(argv[2], atoi(argv[4])) : run_spmv_t<double>(argv[2], atoi(argv[4]));
+    fprintf(stderr, "usage: see the header of this file\n");
+    return 2;
+}

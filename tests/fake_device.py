@@ -49,6 +49,11 @@ def _rot(c, s, x0, x1):
     return c * x0 + s * x1, -s * x0 + c * x1
 
 
+def rviewc(x):
+    """complex128 view of a vector given as complex tensor or as its interleaved float64 view"""
+    return x if x.dtype == torch.complex128 else x.view(torch.complex128)
+
+
 class _Event(object):
     def record(self):
         pass
@@ -120,6 +125,21 @@ class FakeContext(object):
         npdt = _device.torch_to_np_dtype(dtype)
         return _device.CsrDev(torch.from_numpy(A.indptr.astype(np.int32)), torch.from_numpy(A.indices.astype(np.int32)),
                               torch.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)), A.shape)
+
+    def upload_csr_z(self, A):
+        A = sp.csr_matrix(A)
+        npdt = np.complex128 if np.iscomplexobj(A.data) else np.float64
+        obj = _device.CsrDev(torch.from_numpy(A.indptr.astype(np.int32)), torch.from_numpy(A.indices.astype(np.int32)),
+                             torch.from_numpy(np.ascontiguousarray(A.data, dtype=npdt)), A.shape)
+        obj.native_z = True
+        return obj
+
+    # ---- kry_spmv_csr_z ----
+    def spmv_z(self, A, x, y):
+        self._count("spmv_z")
+        assert x.dtype == torch.complex128 and y.dtype == torch.complex128 and getattr(A, "native_z", False)
+        M = sp.csr_matrix((A.vals.numpy(), A.colidx.numpy(), A.rowptr.numpy()), shape=A.shape)
+        y.copy_(torch.from_numpy(np.asarray(M @ x.numpy(), dtype=np.complex128)))
 
     # ---- operators (kry_spmv_csr, kry_gemv_dense, kry_diag_mul) ----
     @realviews
@@ -229,6 +249,39 @@ class FakeContext(object):
             nrm[0] = n2
             if vnext is not None:
                 vnext.copy_((qq / n2 if n2 > 0 else torch.zeros_like(qq)).to(vnext.dtype))
+
+    # ---- kry_orth_fused_z ----
+    def orth_fused_z(self, Vdot, Vsub, ldv, j0, nv, q, passes, algo, h_ptr, nrm=None, vnext=None):
+        """complex vectors j0..nv-1 start ldv complex elements apart at Vdot / Vsub (tensors: row 0 of a real
+        twin storage, the vectors are its even rows); h: 2 doubles per vector, +="""
+        self._count("orth_fused_z")
+        qc = rviewc(q)
+        n = qc.numel()
+
+        def vec(B, j):
+            # B: real (rows, >= 2n) view whose row 2j holds complex vector j (ldv = its real row stride)
+            return B[2 * j][: 2 * n].view(torch.complex128)
+        assert int(ldv) == Vdot.stride(0) and int(ldv) == Vsub.stride(0)
+        hv = _view(h_ptr, 2 * max(int(nv), 1)).view(np.complex128) if isinstance(h_ptr, int) else \
+            h_ptr.numpy()[: 2 * max(int(nv), 1)].view(np.complex128)
+        qq = qc.clone()
+        for _ in range(int(passes)):
+            if algo == KRY_ORTH_CGS:
+                cs = [complex(torch.vdot(vec(Vdot, j), qq)) for j in range(int(j0), int(nv))]
+                for j, c in zip(range(int(j0), int(nv)), cs):
+                    hv[j] += c
+                    qq = qq - c * vec(Vsub, j)
+            else:
+                for j in range(int(j0), int(nv)):
+                    c = complex(torch.vdot(vec(Vdot, j), qq))
+                    hv[j] += c
+                    qq = qq - c * vec(Vsub, j)
+        qc.copy_(qq)
+        if nrm is not None:
+            n2 = float(np.sqrt(float(torch.vdot(qq, qq).real)))
+            nrm[0] = n2
+            if vnext is not None:
+                rviewc(vnext).copy_(qq / n2 if n2 > 0 else torch.zeros_like(qq))
 
     # ---- kry_lanczos_diag ----
     def lanczos_diag(self, vprev, vk, bdiag, q, pre_coef, h3, vnext):

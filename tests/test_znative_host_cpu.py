@@ -1,0 +1,76 @@
+"""CPU tier twin of tests/test_zzz_native_gpu.py: the same checks driven over the numpy test double of the
+device layer (tests/fake_device.py).  Validates the host logic around the native complex kernels (which
+calls are made with which layout: even rows of the twin storage, interleaved coefficients, chunking, the
+KRY_NATIVE_Z switch, the operator's device-format cache) and that the GPU test file itself is sound."""
+import numpy as np
+import pytest
+
+import fake_device
+import test_zzz_native_gpu as zn
+
+
+@pytest.fixture()
+def fake(monkeypatch):
+    return fake_device.install(monkeypatch)
+
+
+@pytest.mark.parametrize("algo", ["cgs", "mgs"])
+@pytest.mark.parametrize("nv,j0,n,passes", [(1, 0, 1, 1), (5, 0, 7, 2), (9, 0, 300, 1), (12, 3, 4096, 2), (32, 0, 50, 1)])
+def test_orth_fused_z_contract(fake, algo, nv, j0, n, passes):
+    zn.check_orth_fused_z(fake, algo, passes, nv, j0, n)
+    zn.check_orth_fused_z(fake, algo, passes, nv, j0, n, separate_P=True)
+
+
+def test_orth_fused_z_edge_contracts(fake):
+    zn.test_orth_fused_z_without_tail_and_empty_range(fake)
+    zn.test_orth_fused_z_zero_vector(fake)
+    zn.test_orth_fused_z_agrees_with_the_twin_kernel(fake)
+
+
+@pytest.mark.parametrize("cplx", [True, False])
+@pytest.mark.parametrize("kind", ["lap2d", "band7", "rand12", "long", "ragged", "tiny"])
+def test_spmv_z_contract(fake, kind, cplx):
+    zn.check_spmv_z(fake, kind, cplx)
+
+
+def test_operator_formats(fake):
+    zn.test_spmv_z_matches_the_embedded_operator(fake)
+
+
+@pytest.mark.parametrize("ortho", ["mgs", "cgs2"])
+@pytest.mark.parametrize("variant", ["plain", "restarted", "precond"])
+def test_native_and_embedding_paths_agree(fake, ortho, variant):
+    zn.test_native_and_embedding_paths_agree(fake, ortho, variant)
+
+
+def test_switch_selects_the_kernels(fake):
+    """native: the Arnoldi step of a complex GMRES is kry_spmv_csr_z + kry_orth_fused_z; KRY_NATIVE_Z=0: the
+    real kernels on the embedding; complex Lanczos (real coefficients) stays on the real kernel either way"""
+    zn.test_native_kernels_are_the_default_and_take_fewer_passes(fake)
+    fake.reset_launch_count()
+    zn._solve_complex(True, "mgs")
+    c = dict(fake.calls)
+    assert c.get("orth_fused_z", 0) > 0 and c.get("spmv_z", 0) > 0
+    assert c.get("orth_fused", 0) == 0 and c.get("spmv", 0) == 0
+    fake.reset_launch_count()
+    zn._solve_complex(False, "mgs")
+    c = dict(fake.calls)
+    assert c.get("orth_fused_z", 0) == 0 and c.get("spmv_z", 0) == 0
+    assert c.get("orth_fused", 0) > 0 and c.get("spmv", 0) > 0
+    # complex MINRES: Lanczos with real coefficients on the real kernel, the matrix in the native format
+    import test_zcomplex_gpu as z
+    fake.reset_launch_count()
+    z.test_complex_cases_match_reference_fixture_and_oracle("z_minres_herm")
+    c = dict(fake.calls)
+    assert c.get("spmv_z", 0) > 0 and c.get("orth_fused", 0) > 0 and c.get("orth_fused_z", 0) == 0
+
+
+def test_complex_cg_and_minres_with_native_matrix(fake):
+    zn.test_complex_cg_and_minres_with_native_matrix(fake)
+
+
+def test_chunked_native_calls(fake):
+    fake.reset_launch_count()
+    zn.test_arnoldi_more_vectors_than_one_native_call(fake)
+    # cgs2 with up to 40 vectors: steps 32..39 take two calls each; dmgs / mgs one call per step
+    assert fake.calls["orth_fused_z"] == (40 + 8) + 40 + 40
