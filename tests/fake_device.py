@@ -74,6 +74,17 @@ class FakeContext(object):
     def _count(self, name):
         self.calls[name] = self.calls.get(name, 0) + 1
 
+    def _timed(self, tag, meta, fn):
+        """the KernelTimer brackets of the real Context (bench.py, tools/bench_cplx.py)"""
+        if self.timer is None:
+            return False
+        tm, self.timer = self.timer, None
+        try:
+            tm.bracket(tag, meta, fn)
+        finally:
+            self.timer = tm
+        return True
+
     # ---- plumbing ----
     def use_current_stream(self):
         pass
@@ -136,6 +147,8 @@ class FakeContext(object):
 
     # ---- kry_spmv_csr_z ----
     def spmv_z(self, A, x, y):
+        if self._timed("spmv", (A.shape[0], A.nnz), lambda: self.spmv_z(A, x, y)):
+            return
         self._count("spmv_z")
         assert x.dtype == torch.complex128 and y.dtype == torch.complex128 and getattr(A, "native_z", False)
         M = sp.csr_matrix((A.vals.numpy(), A.colidx.numpy(), A.rowptr.numpy()), shape=A.shape)
@@ -144,6 +157,8 @@ class FakeContext(object):
     # ---- operators (kry_spmv_csr, kry_gemv_dense, kry_diag_mul) ----
     @realviews
     def spmv(self, A, x, y, w=None, dot_out=None):
+        if self._timed("spmv", (A.shape[0], A.nnz), lambda: self.spmv(A, x, y, w, dot_out)):
+            return
         self._count("spmv")
         M = sp.csr_matrix((A.vals.numpy().astype(np.float64), A.colidx.numpy(), A.rowptr.numpy()), shape=A.shape)
         r = M @ x.numpy().astype(np.float64)
@@ -226,6 +241,10 @@ class FakeContext(object):
     @realviews
     def orth_fused(self, Vdot, Vsub, j0, nv, q, passes, algo, h, nrm=None, vnext=None, pre_vec=None,
                    pre_coef=None, h_ptr=None, halo_op=None):
+        if self._timed("orth", (q.numel(), int(nv) - int(j0), int(passes), int(algo), vnext is not None),
+                       lambda: self.orth_fused(Vdot, Vsub, j0, nv, q, passes, algo, h, nrm, vnext, pre_vec, pre_coef,
+                                               h_ptr, halo_op)):
+            return
         self._count("orth_fused")
         hv = _view(h_ptr if h_ptr is not None else h, max(int(nv), 1)) if (h is not None or h_ptr is not None) else None
         qq = q.double()
@@ -254,9 +273,12 @@ class FakeContext(object):
     def orth_fused_z(self, Vdot, Vsub, ldv, j0, nv, q, passes, algo, h_ptr, nrm=None, vnext=None):
         """complex vectors j0..nv-1 start ldv complex elements apart at Vdot / Vsub (tensors: row 0 of a real
         twin storage, the vectors are its even rows); h: 2 doubles per vector, +="""
-        self._count("orth_fused_z")
         qc = rviewc(q)
         n = qc.numel()
+        if self._timed("orth", (2 * n, 2 * (int(nv) - int(j0)), int(passes), int(algo), vnext is not None),
+                       lambda: self.orth_fused_z(Vdot, Vsub, ldv, j0, nv, q, passes, algo, h_ptr, nrm, vnext)):
+            return
+        self._count("orth_fused_z")
 
         def vec(B, j):
             # B: real (rows, >= 2n) view whose row 2j holds complex vector j (ldv = its real row stride)

@@ -74,3 +74,44 @@ def test_chunked_native_calls(fake):
     zn.test_arnoldi_more_vectors_than_one_native_call(fake)
     # cgs2 with up to 40 vectors: steps 32..39 take two calls each; dmgs / mgs one call per step
     assert fake.calls["orth_fused_z"] == (40 + 8) + 40 + 40
+
+
+def test_bench_cplx_tool_dry_run(monkeypatch, capsys):
+    """tools/bench_cplx.py over the test double at a tiny grid (Python-level soundness of the measurement tool:
+    keys, byte models, the KernelTimer legs); says nothing about performance"""
+    import json
+    import os
+    import runpy
+    import sys
+    import time
+
+    import torch
+
+    fake_device.install(monkeypatch)
+
+    class Ev(object):
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t) + 1e-3
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bench_cplx.py")
+    monkeypatch.setattr(sys, "argv", [tool, "20"])
+    runpy.run_path(tool, run_name="__main__")
+    d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    assert set(d["runs"]) == {"native_cgs", "embedding_cgs", "native_mgs", "embedding_mgs"}
+    for key, r in d["runs"].items():
+        assert r["iterations"] > 0 and r["it_per_s"] > 0
+        assert r["kernels"]["spmv"]["launches"] > 0 and r["kernels"]["orth"]["GBs"] > 0
+    for o in ("cgs", "mgs"):
+        assert d["runs"]["native_" + o]["history_max_rel_diff_vs_embedding"] < 1e-7   # (tiny grid: the solve reaches the rounding floor)
+        assert d["runs"]["native_" + o]["algorithmic_GBs"] > 0

@@ -39,27 +39,25 @@ def crandn(rng, *shape):
 # ------------------------------------------------------------------ kry_orth_fused_z
 def _zcgs_ref(V, P, q, j0, passes):
     """block classical Gram-Schmidt with the reference's inner product (krypy/utils.py:183: X^H Y)"""
-    q = q.astype(np.clongdouble)
-    V, P = V.astype(np.clongdouble), P.astype(np.clongdouble)
-    h = np.zeros(V.shape[0], dtype=np.clongdouble)
+    q = q.astype(np.complex128).copy()
+    h = np.zeros(V.shape[0], dtype=np.complex128)
     for _ in range(passes):
         c = V[j0:].conj() @ q
         h[j0:] += c
         q = q - c @ P[j0:]
-    return q.astype(np.complex128), h.astype(np.complex128), float(np.linalg.norm(q.astype(np.complex128)))
+    return q, h, float(np.linalg.norm(q))
 
 
 def _zmgs_ref(V, P, q, j0, passes):
     """the reference's modified Gram-Schmidt loop on complex data (krypy/utils.py:1012-1029)"""
-    q = q.astype(np.clongdouble)
-    V, P = V.astype(np.clongdouble), P.astype(np.clongdouble)
-    h = np.zeros(V.shape[0], dtype=np.clongdouble)
+    q = q.astype(np.complex128).copy()
+    h = np.zeros(V.shape[0], dtype=np.complex128)
     for _ in range(passes):
         for j in range(j0, V.shape[0]):
             c = np.vdot(V[j], q)
             h[j] += c
             q = q - c * P[j]
-    return q.astype(np.complex128), h.astype(np.complex128), float(np.linalg.norm(q.astype(np.complex128)))
+    return q, h, float(np.linalg.norm(q))
 
 
 def _twin_block(ctx, Z):
