@@ -370,6 +370,9 @@ def run_b200(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     ctx.timer = None
     launches = ctx.launch_count()
+    l2w = getattr(ctx, "_l2win", None)       # the L2 residency window of w = A v_k, if the product set one (KRY_L2_WINDOW)
+    l2_info = ({"enabled": True, "set_aside_bytes": l2w[1][2], "window_bytes": l2w[1][3], "hit_ratio": l2w[1][4]}
+               if (l2w and l2w[1]) else {"enabled": False, "note": getattr(ctx, "l2_window_error", None)})
     if world > 1:
         # graph replays are not counted by the library's launch counter: count the kernels of one
         # eagerly launched cycle instead (same sequence the graphs replay) and scale
@@ -529,6 +532,7 @@ def run_b200(args, rank, world, local_rank):
         which = {1: [("c5", 6), ("c4", 0), ("c3", 4)], 4: [("c5", 6)], 8: [("c3", 4)]}.get(world, [])
         if getattr(args, "extra", None):
             which = [(c, {"c5": 6, "c3": 4}.get(c, 0)) for c in args.extra.split(",") if c]
+        ctx.l2_window(None)                  # C2's window (if any) goes with C2's buffers
         if which:
             # release C2's device memory first
             ws.bufs.clear(); ws.graphs.clear()
@@ -558,7 +562,7 @@ def run_b200(args, rank, world, local_rank):
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": config_dict(args, world), "iterations": iters, "clocks": clk,
             "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "final_resnorm": float(hist[-1][-1]),
+            "final_resnorm": float(hist[-1][-1]), "l2_window": l2_info,
         }
         line.update(extra)
         sys.stdout.write("\n" + json.dumps(line) + "\n")

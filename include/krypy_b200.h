@@ -59,6 +59,16 @@ int         kry_sync(kry_ctx* ctx);          /* cudaStreamSynchronize(stream)   
 long long   kry_launch_count(kry_ctx* ctx);  /* kernels launched through this ctx    */
 void        kry_reset_launch_count(kry_ctx* ctx);
 
+/* L2 residency window (cudaStreamAttributeAccessPolicyWindow on the context's stream): kernels launched
+ * afterwards keep [base, base + bytes) in the L2 set-aside ("persisting"; the part of the window beyond the
+ * set-aside is "streaming").  Used for the vector an Arnoldi step re-reads four times, w = A v_k of
+ * krypy/utils.py:968 that utils.py:1012-1045 orthogonalises and normalises: its passes after the first are
+ * served by the 126 MB L2 instead of HBM.  base == NULL or bytes <= 0 removes the window.  A pure performance
+ * hint: results are unchanged.  info (may be NULL): [0] max set-aside, [1] max window, [2] set-aside in
+ * effect, [3] window bytes, [4] hit ratio * 1e6.  KRY_ERR_UNSUPPORTED when the device or the stream does not
+ * take the hint (never an error of the solve). */
+int         kry_l2_window(kry_ctx* ctx, const void* base, long long bytes, long long info[5]);
+
 /* ---- operators -------------------------------------------------------- */
 /* y = A x for CSR A (int32 indices).  Replaces scipy csr_matvec behind
  * krypy/utils.py:1593-1594 (MatrixLinearOperator._dot) as called from

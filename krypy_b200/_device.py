@@ -196,6 +196,30 @@ class Context(object):
     def reset_launch_count(self):
         self.lib.kry_reset_launch_count(self.h)
 
+    def l2_window(self, t):
+        """Keep the device tensor ``t`` resident in the L2 set-aside for the kernels launched from now on
+        (kry_l2_window); ``None`` removes the window.  A performance hint only; returns the info tuple
+        (max set-aside, max window, set-aside, window bytes, hit ratio) or None when nothing was set."""
+        cur = getattr(self, "_l2win", None)
+        if t is None:
+            if cur is not None:
+                self._l2win = None
+                self.lib.kry_l2_window(self.h, None, 0, None)        # (a hint: its failure is not an error)
+            return None
+        key = (t.data_ptr(), t.numel() * t.element_size(), self.stream_handle)
+        if cur is not None and cur[0] == key:
+            return cur[1]
+        info = (ctypes.c_longlong * 5)()
+        rc = self.lib.kry_l2_window(self.h, ctypes.c_void_p(key[0]), key[1], info)
+        if rc != 0:
+            msg = self.lib.kry_last_error()
+            self.l2_window_error = msg.decode() if msg else "?"
+            self._l2win = (key, None)                                # do not retry for the same buffer
+            return None
+        res = (int(info[0]), int(info[1]), int(info[2]), int(info[3]), info[4] * 1e-6)
+        self._l2win = (key, res)
+        return res
+
     # ---- allocation / conversion ---------------------------------------
     def empty(self, shape, dtype):
         return torch().empty(shape, dtype=dtype, device=self.device)

@@ -34,6 +34,7 @@ PROTOTYPES = {
     "kry_sync": (c_int, [c_void_p]),
     "kry_launch_count": (c_ll, [c_void_p]),
     "kry_reset_launch_count": (None, [c_void_p]),
+    "kry_l2_window": (c_int, [c_void_p, c_void_p, c_ll, ctypes.POINTER(c_ll)]),
     "kry_spmv_csr": (c_int, [c_void_p, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p,
                              c_void_p, c_void_p, c_void_p, c_void_p]),
     "kry_gemv_dense": (c_int, [c_void_p, c_int, c_ll, c_ll, c_void_p, c_ll, c_void_p, c_void_p]),

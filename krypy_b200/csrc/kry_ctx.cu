@@ -103,6 +103,75 @@ int kry_device_info(kry_ctx* ctx, long long info[8]) {
     return KRY_OK;
 }
 
+// L2 residency window on the context's stream (cudaStreamAttributeAccessPolicyWindow): accesses of kernels
+// launched afterwards to [base, base + bytes) are "persisting" (kept in the L2 set-aside), the rest of the window
+// beyond the set-aside "streaming".  base == NULL or bytes <= 0 removes the window and demotes the persisting lines.
+// info: [0] persistingL2CacheMaxSize, [1] accessPolicyMaxWindowSize, [2] set-aside in effect, [3] window bytes,
+// [4] hit ratio * 1e6.  Returns KRY_ERR_UNSUPPORTED (not an error of the solve) when the device or the stream
+// does not take the hint.
+// (a failing hint must not poison the error state the next launch check reads: clear it)
+#define KRY_L2_TRY(expr)                                                                      \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            kry_set_error("kry_l2_window: %s failed: %s", #expr, cudaGetErrorString(_e));      \
+            (void)cudaGetLastError();                                                         \
+            return KRY_ERR_UNSUPPORTED;                                                       \
+        }                                                                                     \
+    } while (0)
+
+int kry_l2_window(kry_ctx* ctx, const void* base, long long bytes, long long info[5]) {
+    KRY_REQUIRE(ctx != nullptr, "ctx is NULL");
+    KRY_CHECK_CUDA(cudaSetDevice(ctx->device));
+    int max_persist = 0, max_window = 0;
+    KRY_L2_TRY(cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, ctx->device));
+    KRY_L2_TRY(cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, ctx->device));
+    if (info) {
+        info[0] = max_persist;
+        info[1] = max_window;
+        info[2] = info[3] = info[4] = 0;
+    }
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof(attr));
+    if (base == nullptr || bytes <= 0) {
+        attr.accessPolicyWindow.base_ptr = nullptr;
+        attr.accessPolicyWindow.num_bytes = 0;
+        attr.accessPolicyWindow.hitRatio = 0.0f;
+        attr.accessPolicyWindow.hitProp = cudaAccessPropertyNormal;
+        attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        KRY_L2_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        KRY_L2_TRY(cudaCtxResetPersistingL2Cache());
+        return KRY_OK;
+    }
+    if (max_persist <= 0 || max_window <= 0) {
+        kry_set_error("kry_l2_window: the device has no persisting L2 set-aside");
+        return KRY_ERR_UNSUPPORTED;
+    }
+    const long long carve = bytes < (long long)max_persist ? bytes : (long long)max_persist;
+    static long long carve_set[16] = {0};                  // per device: the limit is only touched when it changes
+    if (carve_set[ctx->device & 15] != carve) {
+        KRY_L2_TRY(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)carve));
+        carve_set[ctx->device & 15] = carve;
+    }
+    size_t got = 0;
+    KRY_L2_TRY(cudaDeviceGetLimit(&got, cudaLimitPersistingL2CacheSize));
+    const long long win = bytes < (long long)max_window ? bytes : (long long)max_window;
+    double ratio = win > 0 ? (double)got / (double)win : 0.0;
+    if (ratio > 1.0) ratio = 1.0;
+    attr.accessPolicyWindow.base_ptr = const_cast<void*>(base);
+    attr.accessPolicyWindow.num_bytes = (size_t)win;
+    attr.accessPolicyWindow.hitRatio = (float)ratio;
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    KRY_L2_TRY(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (info) {
+        info[2] = (long long)got;
+        info[3] = win;
+        info[4] = (long long)(ratio * 1e6);
+    }
+    return KRY_OK;
+}
+
 double* kry_mailbox_host(kry_ctx* ctx) { return ctx ? ctx->h_mailbox : nullptr; }
 double* kry_mailbox_dev(kry_ctx* ctx) { return ctx ? ctx->d_mailbox : nullptr; }
 

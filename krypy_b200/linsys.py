@@ -410,6 +410,8 @@ class _KrylovSolver(object):
             self._solve()
         finally:
             _mark(self, "solve_end")
+            if self.__dict__.get("_ws") is None:
+                ctx.l2_window(None)                 # (a restarted solve keeps its window until its last cycle)
         self._finalize()
 
     # -- hooks -----------------------------------------------------------------
@@ -1238,28 +1240,31 @@ class _RestartedSolver(object):
         if Solver is Gmres and "_workspace" not in kwargs:
             kwargs["_workspace"] = utils.SolverWorkspace()
         self._workspace = kwargs.get("_workspace")
-        while restart == 0 or (self.resnorms[-1] > tol and restart <= max_restarts):
-            try:
-                if xk_dev is not None:
-                    kwargs.update({"x0": xk_dev})        # stays in HBM between cycles
-                if Solver is Gmres:
-                    kwargs["_prelaunch"] = restart < max_restarts      # another cycle follows unless this one converges
-                sol = Solver(linear_system, **kwargs)
-            except utils.ConvergenceError as e:
-                sol = e.solver
-            xk_dev = sol.__dict__["_xk_dev"]
-            if xk_dev is None:
-                xk_dev = _ctx().to_block(sol.xk, sol._td)
-            xk_dev = xk_dev.reshape(-1)                  # flat: keeps flat_vecs semantics neutral
-            kwargs["_x0_residual"] = sol.__dict__.get("_last_residual")
-            self._last = sol
-            tol = sol.tol
-            del self.resnorms[-1]
-            self.resnorms += sol.resnorms
-            if linear_system.exact_solution is not None:
-                del self.errnorms[-1]
-                self.errnorms += sol.errnorms
-            restart += 1
+        try:
+            while restart == 0 or (self.resnorms[-1] > tol and restart <= max_restarts):
+                try:
+                    if xk_dev is not None:
+                        kwargs.update({"x0": xk_dev})        # stays in HBM between cycles
+                    if Solver is Gmres:
+                        kwargs["_prelaunch"] = restart < max_restarts      # another cycle follows unless this one converges
+                    sol = Solver(linear_system, **kwargs)
+                except utils.ConvergenceError as e:
+                    sol = e.solver
+                xk_dev = sol.__dict__["_xk_dev"]
+                if xk_dev is None:
+                    xk_dev = _ctx().to_block(sol.xk, sol._td)
+                xk_dev = xk_dev.reshape(-1)                  # flat: keeps flat_vecs semantics neutral
+                kwargs["_x0_residual"] = sol.__dict__.get("_last_residual")
+                self._last = sol
+                tol = sol.tol
+                del self.resnorms[-1]
+                self.resnorms += sol.resnorms
+                if linear_system.exact_solution is not None:
+                    del self.errnorms[-1]
+                    self.errnorms += sol.errnorms
+                restart += 1
+        finally:
+            _ctx().l2_window(None)
         self.xk = sol.xk
         self.tol = tol
         if self.resnorms[-1] > tol:

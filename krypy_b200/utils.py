@@ -1577,6 +1577,10 @@ _LANCZOS_DIAGB = __import__("os").environ.get("KRY_LANCZOS_DIAGB", "1") not in (
 # KRY_NATIVE_Z=0 selects the real-embedding kernels for these two as well (krypy_b200/_cplx.py)
 _NATIVE_Z = __import__("os").environ.get("KRY_NATIVE_Z", "1") not in ("0", "")
 _CGS_CHUNK_Z = 32   # complex vectors per kry_orth_fused_z call (two reduction slots each)
+# L2 residency window on w = A v_k, the vector an Arnoldi step reads four times and writes twice (kry_l2_window):
+# its passes after the first are served by the 126 MB L2.  Single GPU, vectors of 8 MB and more.  KRY_L2_WINDOW=0|1
+_L2_WINDOW = __import__("os").environ.get("KRY_L2_WINDOW", "0") not in ("0", "")
+_L2_WINDOW_MIN_BYTES = 1 << 23
 
 
 class DeviceBlock(object):
@@ -1750,6 +1754,8 @@ class Arnoldi(object):
             self._t = ctx.empty((1, N), td)
         self._hcol = self._hcol_store[nr:]      # one leading zero: H[-1, 0] of linsys.py:828
         self._hfro2 = 0.0
+        if _L2_WINDOW and ctx.comm is None and self._q.numel() * self._q.element_size() >= _L2_WINDOW_MIN_BYTES:
+            ctx.l2_window(self._q)                  # (a no-op when the window already covers this buffer)
 
         if _prelaunched:
             self.vnorm = Mv_norm

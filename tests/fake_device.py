@@ -86,6 +86,11 @@ class FakeContext(object):
         return True
 
     # ---- plumbing ----
+    def l2_window(self, t):
+        """kry_l2_window: a performance hint, nothing to emulate; the calls are recorded"""
+        self.l2_calls = getattr(self, "l2_calls", []) + [None if t is None else (t.data_ptr(), t.numel() * t.element_size())]
+        return None
+
     def use_current_stream(self):
         pass
 

@@ -115,3 +115,66 @@ def test_bench_cplx_tool_dry_run(monkeypatch, capsys):
     for o in ("cgs", "mgs"):
         assert d["runs"]["native_" + o]["history_max_rel_diff_vs_embedding"] < 1e-7   # (tiny grid: the solve reaches the rounding floor)
         assert d["runs"]["native_" + o]["algorithmic_GBs"] > 0
+
+
+def _stub_cuda(monkeypatch):
+    import contextlib
+    import time
+
+    import torch
+
+    class Ev(object):
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t) + 1e-3
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "Stream", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "current_stream", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "stream", lambda s: contextlib.nullcontext())
+    monkeypatch.setattr(torch.cuda, "empty_cache", lambda: None)
+
+
+def test_l2_window_host_logic(fake, monkeypatch):
+    """KRY_L2_WINDOW: the window is set once per restarted solve on the Arnoldi vector w = A v_k (the workspace
+    buffer, so later cycles find it in place) and removed when the solve ends; off: never set"""
+    from krypy_b200 import utils
+    monkeypatch.setattr(utils, "_L2_WINDOW_MIN_BYTES", 1)
+    for on in (True, False):
+        monkeypatch.setattr(utils, "_L2_WINDOW", on)
+        fake.l2_calls = []
+        zn._solve_complex(True, "cgs", restarted=True)
+        sets = [c for c in fake.l2_calls if c is not None]
+        if on:
+            assert len(sets) >= 1 and len(set(sets)) == 1        # one buffer, the same in every cycle
+            assert fake.l2_calls[-1] is None                      # removed at the end
+        else:
+            assert sets == []
+
+
+def test_bench_l2window_tool_dry_run(monkeypatch, capsys):
+    import json
+    import os
+    import runpy
+    import sys
+
+    fake_device.install(monkeypatch)
+    _stub_cuda(monkeypatch)
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "bench_l2window.py")
+    monkeypatch.setattr(sys, "argv", [tool, "c2", "c5", "24"])
+    runpy.run_path(tool, run_name="__main__")
+    d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.startswith("{")][-1])
+    assert len(d["runs"]) == 12
+    for k, r in d["runs"].items():
+        assert r["iterations"] > 0
+        if k.endswith("window1"):
+            assert r["bitwise_identical_history"] is True
