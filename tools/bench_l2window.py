@@ -72,7 +72,7 @@ def ab(name, make, warm):
             del s, best
         ctx.l2_window(None)
         a, b = res["%s_%s_window0" % (name, stream_mode)], res["%s_%s_window1" % (name, stream_mode)]
-        b["speedup_over_window_off"] = b["it_per_s"] / a["it_per_s"]
+        b["speedup_over_window_off"] = b["it_per_s"] / a["it_per_s"] if a["it_per_s"] > 0 else None
         b["bitwise_identical_history"] = bool(a["resnorm_checksum"] == b["resnorm_checksum"]
                                               and a["final_resnorm"] == b["final_resnorm"])
     utils._L2_WINDOW = False
@@ -100,7 +100,7 @@ if "c2" in which:
 if "c5" in which:
     import bench_configs
     P = bench_configs.problem("c5", n=small[0] if small else None)
-    ls = kp.linsys.LinearSystem(P["A"], P["b"], **P["ls"])
+    ls = kp.linsys.LinearSystem(P["A"], P["b"], dtype=np.float32, **P["ls"])
     out["runs"].update(ab("c5_minres",
                           lambda: kp.linsys.Minres(ls, maxiter=50, tol=1e-5),
                           lambda: kp.linsys.Minres(ls, maxiter=5, tol=1e-5)))
