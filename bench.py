@@ -371,7 +371,11 @@ def run_b200(args, rank, world, local_rank):
     ctx.timer = None
     launches = ctx.launch_count()
     l2w = getattr(ctx, "_l2win", None)       # the L2 residency window of w = A v_k, if the product set one (KRY_L2_WINDOW)
-    l2_info = ({"enabled": True, "set_aside_bytes": l2w[1][2], "window_bytes": l2w[1][3], "hit_ratio": l2w[1][4]}
+    l2_info = ({"enabled": True, "set_aside_bytes": l2w[1][2], "window_bytes": l2w[1][3], "hit_ratio": l2w[1][4],
+                "note": "w = A v_k is kept in the L2 set-aside (kry_l2_window): its re-reads are served by L2, so the "
+                        "algorithmic GB/s of the Gram-Schmidt kernel can exceed the DRAM copy peak (roofline.frac > 1); "
+                        "roofline.traffic was captured with the window off (profiles/r2_traffic.json); same-box A/B: "
+                        "profiles/r2_l2window_ab.json"}
                if (l2w and l2w[1]) else {"enabled": False, "note": getattr(ctx, "l2_window_error", None)})
     if world > 1:
         # graph replays are not counted by the library's launch counter: count the kernels of one

@@ -1578,8 +1578,11 @@ _LANCZOS_DIAGB = __import__("os").environ.get("KRY_LANCZOS_DIAGB", "1") not in (
 _NATIVE_Z = __import__("os").environ.get("KRY_NATIVE_Z", "1") not in ("0", "")
 _CGS_CHUNK_Z = 32   # complex vectors per kry_orth_fused_z call (two reduction slots each)
 # L2 residency window on w = A v_k, the vector an Arnoldi step reads four times and writes twice (kry_l2_window):
-# its passes after the first are served by the 126 MB L2.  Single GPU, vectors of 8 MB and more.  KRY_L2_WINDOW=0|1
-_L2_WINDOW = __import__("os").environ.get("KRY_L2_WINDOW", "0") not in ("0", "")
+# its passes after the first are served by the 126 MB L2 instead of HBM.  Single GPU, vectors of 8 MB and more.
+# Default since round 2 -- same-box A/B on a B200 (profiles/r2_l2window_ab.json): exact MGS (the drop-in default
+# ortho) 980 -> 1,191 it/s on C2, C5 2,282 -> 2,401 it/s, block CGS 1,605 -> 1,623 it/s, results bitwise identical.
+# KRY_L2_WINDOW=0 turns it off.
+_L2_WINDOW = __import__("os").environ.get("KRY_L2_WINDOW", "1") not in ("0", "")
 _L2_WINDOW_MIN_BYTES = 1 << 23
 
 
@@ -2121,8 +2124,11 @@ class Arnoldi(object):
 def arnoldi(*args, **kwargs):
     """krypy/utils.py:1077-1081."""
     _arnoldi = Arnoldi(*args, **kwargs)
-    while _arnoldi.iter < _arnoldi.maxiter and not _arnoldi.invariant:
-        _arnoldi.advance()
+    try:
+        while _arnoldi.iter < _arnoldi.maxiter and not _arnoldi.invariant:
+            _arnoldi.advance()
+    finally:
+        _ctx().l2_window(None)        # the L2 set-aside of the process's vector goes back (an idle one costs L2)
     return _arnoldi.get()
 
 
