@@ -139,6 +139,7 @@ struct PeerArgs {
     unsigned long long* const* flags;     // [rank] -> that rank's [world] u64
 };
 
+#ifndef KRY_EMUL   // (the CPU tier's execution emulator supplies host versions, tests/csrc/cuda_emul)
 __device__ __forceinline__ void dst_release_sys(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -162,6 +163,8 @@ __device__ __forceinline__ unsigned long long dglobal_timer_ns() {
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
     return t;
 }
+
+#endif
 
 __device__ __forceinline__ double nan_f64() { return __longlong_as_double(0x7ff8000000000000ll); }
 
