@@ -533,9 +533,10 @@ def run_b200(args, rank, world, local_rank):
     if not args.no_extra_configs and n == N_GRID:
         import bench_configs
         del sol
-        which = {1: [("c5", 6), ("c4", 0), ("c3", 4)], 4: [("c5", 6)], 8: [("c3", 4)]}.get(world, [])
+        # (c2z: the complex128 twin of C2 on the native complex kernels -- not a BASELINE configuration)
+        which = {1: [("c5", 6), ("c4", 0), ("c3", 4), ("c2z", 3)], 4: [("c5", 6)], 8: [("c3", 4)]}.get(world, [])
         if getattr(args, "extra", None):
-            which = [(c, {"c5": 6, "c3": 4}.get(c, 0)) for c in args.extra.split(",") if c]
+            which = [(c, {"c5": 6, "c3": 4, "c2z": 3}.get(c, 0)) for c in args.extra.split(",") if c]
         ctx.l2_window(None)                  # C2's window (if any) goes with C2's buffers
         if which:
             # release C2's device memory first

@@ -31,6 +31,9 @@ def bytes_per_iteration(name, N, nnz, sz, iters=None):
         return spmv + 11 * N * sz
     if name == "c5":        # B_spmv(A) + 2 B_spmv(B) + 13 Ns = 144 N (fp32)
         return spmv + 2 * (N * (sz + 4) + 4 * (N + 1) + 2 * N * sz) + 13 * N * sz
+    if name == "c2z":       # complex twin of C2, native complex kernels: B_spmv + mean_k (2(k+1)+5) Ns over a
+        m = 30              # 30-step cycle + the twin row of v_{k+1} (2 Ns), s = 16
+        return spmv + (2 * (m + 1) / 2.0 + 5) * N * sz + 2 * N * sz
     if name == "c4":        # GMRES step k: B_spmv + (2k+9) Ns, mean over the steps done, + 672 N projector
         m = max(int(iters or 1), 1)
         return spmv + (m - 1 + 9) * N * sz + (4 * 20 + 4) * N * sz
@@ -66,6 +69,17 @@ def problem(name, n=None, rows=None):
                     ls=dict(ip_B=Bloc, self_adjoint=True), solver="minres", kw=dict(tol=1e-5),
                     label="C5: Minres(lanczos), ip_B = diag(linspace(1,2,N)), A = B^-1(L - 0.3 I), 2-D n=%d, "
                           "N=%d, fp32 storage" % (n, N))
+    if name == "c2z":
+        # not a BASELINE configuration: the complex128 twin of C2 (half of the reference's own test matrix is
+        # complex, test/test_linsys.py:118-141), 80 MB per vector like C2
+        n = n or 2236
+        N = n * n
+        A = (problems.laplace2d(n).astype(np.complex128) - (0.02 + 0.01j) * sp.identity(N, dtype=np.complex128)).tocsr()
+        rng = np.random.default_rng(0)
+        b = rng.standard_normal(N) + 1j * rng.standard_normal(N)
+        return dict(A=A, b=b, N=N, nnz_global=int(A.nnz), sz=16, ls=dict(), solver="gmres", kw=dict(tol=1e-12),
+                    label="C2z: complex128 twin of C2, GMRES(30) (ortho=cgs), 2-D 5-point Laplacian - (0.02+0.01i) I, "
+                          "n=%d, N=%d, native complex kernels (kry_orth_fused_z, kry_spmv_csr_z)" % (n, N))
     if name == "c4":
         n = n or 2000
         N = n * n
@@ -96,6 +110,9 @@ def reference_history(name, P, steps, U=None, krypy=None):
             elif name == "c3":
                 ls = krypy.linsys.LinearSystem(P["A"], P["b"], M=P["M"], self_adjoint=True, positive_definite=True)
                 cls, kw = krypy.linsys.Cg, {}
+            elif name == "c2z":
+                ls = krypy.linsys.LinearSystem(P["A"], P["b"])
+                cls, kw = krypy.linsys.Gmres, {}
             else:
                 ls = krypy.linsys.LinearSystem(P["A"], P["b"])
                 cls, kw = krypy.deflation.DeflatedGmres, dict(U=U)
@@ -109,6 +126,8 @@ def reference_history(name, P, steps, U=None, krypy=None):
         run, sysm, kw = ko.minres, ko.System(P["A"], P["b"], B=P["B"]), {}
     elif name == "c3":
         run, sysm, kw = ko.cg, ko.System(P["A"], P["b"], M=P["M"]), {}
+    elif name == "c2z":
+        run, sysm, kw = ko.gmres, ko.System(P["A"], P["b"]), {}
     else:
         run, sysm, kw = ko.gmres, ko.System(P["A"], P["b"]), dict(U=U)
     try:
@@ -185,6 +204,16 @@ def run_device(name, peak, dist=None, rank=0, world=1, maxiter=None, n=None, ref
         s, dt = _timed(torch, dist, lambda: kp.linsys.Cg(ls, maxiter=maxiter, **P["kw"]), kp)
         hist = list(map(float, s.resnorms))
         trunc = lambda k: kp.linsys.Cg(ls, maxiter=k, **P["kw"])
+    elif name == "c2z":
+        if world > 1:
+            raise NotImplementedError("complex row-partitioned runs are not implemented")
+        maxiter = maxiter or 30
+        ls = mk_ls()
+        mk = lambda restarts: kp.linsys.RestartedGmres(ls, maxiter=maxiter, max_restarts=restarts, ortho="cgs", **P["kw"])
+        _timed(torch, dist, lambda: mk(0), kp)                                               # warm-up: one cycle
+        s, dt = _timed(torch, dist, lambda: mk(4), kp)                                       # five cycles
+        hist = list(map(float, s.resnorms))
+        trunc = lambda k: kp.linsys.Gmres(ls, maxiter=k, ortho="cgs", **P["kw"])
     elif name == "c5":
         maxiter = maxiter or 50
         ls = mk_ls(np.float32)
@@ -264,6 +293,8 @@ def run_device(name, peak, dist=None, rank=0, world=1, maxiter=None, n=None, ref
 
 
 def problem_size(name, n=None):
+    if name == "c2z":
+        return (n or 2236) ** 2
     if name == "c3":
         return (n or 400) ** 3
     if name == "c5":

@@ -178,3 +178,18 @@ def test_bench_l2window_tool_dry_run(monkeypatch, capsys):
         assert r["iterations"] > 0
         if k.endswith("window1"):
             assert r["bitwise_identical_history"] is True
+
+
+def test_bench_extra_config_c2z_dry_run(monkeypatch):
+    """bench_configs.run_device('c2z') (the complex twin of C2 as an extra key of the bench line) over the test
+    double at a tiny grid, with reference parity against the unmodified reference / the oracle port"""
+    import bench_configs
+
+    fake_device.install(monkeypatch)
+    _stub_cuda(monkeypatch)
+    out = bench_configs.run_device("c2z", 6538.9, n=16, ref_steps=3, maxiter=10)
+    assert "error" not in out and out["iterations"] > 0 and out["it_per_s"] > 0
+    assert out["algorithmic_bytes_per_iteration"] > 0 and 0 < out["frac_of_measured_peak"]
+    par = out["parity_vs_reference"]
+    assert par["entries"] == 4 and par["max_rel_updated"] < 1e-10 and par["rel_last_explicit"] < 1e-10
+    assert bench_configs.problem_size("c2z") == 2236 ** 2
