@@ -46,9 +46,13 @@ double __shfl_xor_sync(unsigned int, double v, int lane_mask) {
     pthread_barrier_wait(&w.bar);
     return r;
 }
+static inline void emul_jitter(int one_in);
 void kry_emul_grid_sync() {
     __syncthreads();
-    if (threadIdx.x == 0) pthread_barrier_wait(g_grid_bar);
+    if (threadIdx.x == 0) {
+        emul_jitter(2);
+        pthread_barrier_wait(g_grid_bar);
+    }
     __syncthreads();
 }
 
@@ -138,9 +142,33 @@ void z_bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* 
 void z_consumer_bar_sync() { pthread_barrier_wait(&g_named_bar); }
 
 
+// Schedule jitter (EMUL_JITTER=<max microseconds>): random sleeps in front of every release, in a fraction of the
+// acquires and at kernel boundaries, drawn per process, so that repeated runs see different interleavings of
+// the emulated ranks and CTAs (a rank a whole step ahead of its neighbours, a publisher that is late, ...).
+static inline void emul_jitter(int one_in) {
+    static int max_us = -1;
+    static thread_local unsigned long long st = 0;
+    if (max_us < 0) {
+        const char* e = getenv("EMUL_JITTER");
+        max_us = e ? atoi(e) : 0;
+    }
+    if (max_us <= 0) return;
+    if (st == 0) st = 0x9E3779B97F4A7C15ull * (unsigned long long)(getpid() * 1000003 + (int)threadIdx.x + 1);
+    st ^= st << 13;
+    st ^= st >> 7;
+    st ^= st << 17;
+    if ((st >> 20) % (unsigned)one_in == 0) usleep((useconds_t)((st >> 33) % (unsigned)max_us));
+}
+
 // peer-exchange helpers (kry_common.cuh, #ifndef KRY_EMUL): the emulated ranks share their memory
-static inline void dst_release_sys(unsigned long long* p, unsigned long long v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
-static inline unsigned long long dld_acquire_sys(const unsigned long long* p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
+static inline void dst_release_sys(unsigned long long* p, unsigned long long v) {
+    emul_jitter(1);
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+}
+static inline unsigned long long dld_acquire_sys(const unsigned long long* p) {
+    emul_jitter(64);
+    return __atomic_load_n(p, __ATOMIC_ACQUIRE);
+}
 static inline unsigned long long dld_volatile_u64(const unsigned long long* p) { return *(const volatile unsigned long long*)p; }
 static inline double dld_volatile_f64(const double* p) { return *(const volatile double*)p; }
 static inline unsigned long long dglobal_timer_ns() {

@@ -9,6 +9,7 @@
 // basis, the Hessenberg columns (bitwise identical on all ranks), the halo copies (bitwise the owners' values),
 // the Givens residuals, the epoch counters.  Driven by tests/test_dist_emul_cpu.py:
 //     dist_emul_host <ranks> <sweep CTAs> <steps> <n per rank> <givens 0|1> <guard step or -1>
+// Environment: EMUL_JITTER=<max us> (random schedule jitter, emul_runtime.h), EMUL_SLOW_RANK=<rank>:<us>.
 #define KRY_EMUL 1
 #include <random>
 
@@ -107,6 +108,14 @@ int main(int argc, char** argv) {
         pa.slots = slot_tab;
         pa.flags = flag_tab;
         const long long stride = (long long)gridDim.x * blockDim.x;
+        // EMUL_SLOW_RANK=<rank>:<microseconds>: one rank is held back at every kernel boundary, the others run as far
+        // ahead as the flag protocol lets them
+        int slow_rank = -1, slow_us = 0;
+        if (const char* e = getenv("EMUL_SLOW_RANK")) sscanf(e, "%d:%d", &slow_rank, &slow_us);
+        auto boundary = [&]() {
+            if (r == slow_rank && threadIdx.x == 0) usleep((useconds_t)slow_us);
+            kry_emul_grid_sync();
+        };
         for (int k = 0; k < K; ++k) {
             double* w = m.qreg + (k & 1) * qld;
             // "SpMV": w = A v_k.  The guard step makes w almost a combination of the basis (heavy cancellation).
@@ -116,9 +125,9 @@ int main(int argc, char** argv) {
                 else
                     w[i] = m.wgen[(long long)k * n + i];
             }
-            kry_emul_grid_sync();                          // kernel boundary
+            boundary();                                   // kernel boundary
             dist_dot_kernel<double, 2>(n, m.V, ldv, k + 1, w, 1, m.partials, m.ticket, pa);
-            kry_emul_grid_sync();
+            boundary();
             UpdScaleArgs<double> a;
             a.n = n;
             a.V = m.V;
@@ -144,7 +153,7 @@ int main(int argc, char** argv) {
             a.ticket = m.ticket + 2;
             a.pa = pa;
             dist_update_scale_kernel<double, 2>(a);
-            kry_emul_grid_sync();
+            boundary();
             // the host's booking of the column (the Givens tail leaves it in the mailbox and zeroes the accumulator)
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 for (int i = 0; i < k + 2; ++i) {
@@ -152,7 +161,7 @@ int main(int argc, char** argv) {
                     if (!givens) m.hcol[i] = 0.0;
                 }
             }
-            kry_emul_grid_sync();
+            boundary();
         }
     };
     if (!emul_launch_ranks(R, G, KRY_THREADS, 0, body)) {

@@ -26,8 +26,9 @@ def emul(tmp_path_factory):
                            "-I", os.path.join(HERE, "csrc", "cuda_emul"), "-I", os.path.join(ROOT, "krypy_b200", "csrc"),
                            "-o", out, os.path.join(HERE, "csrc", "dist_emul_host.cpp")])
 
-    def run(*args):
-        p = subprocess.run([out] + [str(a) for a in args], capture_output=True, text=True, timeout=900)
+    def run(*args, **env):
+        p = subprocess.run([out] + [str(a) for a in args], capture_output=True, text=True, timeout=900,
+                           env=dict(os.environ, **{k: str(v) for k, v in env.items()}))
         assert p.returncode == 0 and p.stdout.startswith("ok"), (args, p.stdout, p.stderr)
         assert "halo copies bitwise 1, H identical on all ranks 1" in p.stdout
         return p.stdout
@@ -52,3 +53,12 @@ def test_exact_norm_guard_over_emulated_ranks(emul):
 def test_without_givens_tail_and_odd_sizes(emul):
     emul(2, 2, 4, 701, 0, -1)        # odd local length (scalar tail of the sweeps)
     emul(3, 1, 9, 257, 1, -1)        # nine vectors: full block of 8 + remainder in the update sweep
+
+
+@pytest.mark.parametrize("slow", [0, 1, 2])
+def test_a_rank_held_back_and_schedule_jitter(emul, slow):
+    """one rank is held back at every kernel boundary (the others run as far ahead as the flag protocol lets them:
+    at most one step, so the two buffers of w and the two slot arrays are enough), with random sleeps in front of
+    every release and in a fraction of the acquires: the results do not depend on the interleaving"""
+    emul(3, 2, 6, 600, 1, 2, EMUL_SLOW_RANK="%d:30000" % slow, EMUL_JITTER=3000)
+    emul(3, 2, 5, 400, 0, -1, EMUL_SLOW_RANK="%d:20000" % slow)
