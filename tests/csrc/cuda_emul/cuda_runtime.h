@@ -31,6 +31,9 @@ static inline double2 make_double2(double x, double y) { return double2{x, y}; }
 struct float4 {
     float x, y, z, w;
 };
+struct float2 {
+    float x, y;
+};
 struct uint3 {
     unsigned int x, y, z;
 };
