@@ -428,6 +428,12 @@ def run_b200(args, rank, world, local_rank):
                           "CUDA events in one eager cycle after the timed region (timed region replays CUDA "
                           "graphs); " + ("SpMV + two Gram-Schmidt kernels per Arnoldi step, one NVLink peer all-reduce" if fused2 else
                                          "split kernels + NVLink peer all-reduces") + ", per-rank bytes"}
+        if l2_info.get("enabled"):
+            # w = A v_k is resident in the L2 set-aside: part of the ALGORITHMIC bytes never reaches HBM, so the
+            # fraction against the DRAM copy peak can exceed 1; `traffic` is the ncu capture with the window off
+            roof["l2_resident_vector"] = ("w = A v_k (%d of the mean %.0f vector passes per launch are re-reads / the "
+                                          "rewrite of w that the L2 set-aside can serve); frac > 1 is possible"
+                                          % (3, by / max(o["launches"], 1) / (8.0 * N / world)))
     if "orth" in summ:
         # per-k profile of the fused Gram-Schmidt kernel: average microseconds and algorithmic GB/s by
         # the number of basis vectors involved (shows the small-k inefficiency; A/B of KRY_ORTH_SMALLK)

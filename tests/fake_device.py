@@ -89,7 +89,13 @@ class FakeContext(object):
     def l2_window(self, t):
         """kry_l2_window: a performance hint, nothing to emulate; the calls are recorded"""
         self.l2_calls = getattr(self, "l2_calls", []) + [None if t is None else (t.data_ptr(), t.numel() * t.element_size())]
-        return None
+        if t is None:
+            self._l2win = None
+            return None
+        nb = t.numel() * t.element_size()
+        res = (82903040, 134213632, min(nb, 82903040), nb, min(1.0, 82903040.0 / nb))     # the B200's limits
+        self._l2win = ((t.data_ptr(), nb, 0), res)
+        return res
 
     def use_current_stream(self):
         pass

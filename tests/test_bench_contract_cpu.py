@@ -168,3 +168,47 @@ def test_named_configurations_dry_run_with_reference_parity(monkeypatch):
     assert abs(bench_configs.bytes_per_iteration("c3", N, 7 * N, 8) / N - 192.0) < 1e-6
     N = 4000 ** 2
     assert abs(bench_configs.bytes_per_iteration("c5", N, 5 * N, 4) / N - 144.0) < 1e-5
+
+
+def test_b200_arm_reports_the_l2_window(monkeypatch, capsys):
+    """the same dry run with the L2 residency window in effect (threshold lowered to the tiny grid): the line says
+    so and explains why the Gram-Schmidt kernel's algorithmic GB/s may exceed the DRAM copy peak"""
+    import time
+    import types
+
+    import torch
+
+    import bench
+    import fake_device
+    from krypy_b200 import utils
+
+    fake_device.install(monkeypatch)
+    monkeypatch.setattr(utils, "_L2_WINDOW", True)
+    monkeypatch.setattr(utils, "_L2_WINDOW_MIN_BYTES", 1)
+
+    class Ev(object):
+        def __init__(self, enable_timing=False):
+            self.t = 0.0
+
+        def record(self):
+            self.t = time.perf_counter()
+
+        def elapsed_time(self, other):
+            return 1e3 * (other.t - self.t) + 1e-3
+
+        def synchronize(self):
+            pass
+
+    monkeypatch.setattr(torch.cuda, "Event", Ev)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    monkeypatch.setattr(torch.cuda, "set_device", lambda *a, **k: None)
+    monkeypatch.setattr(torch.Tensor, "pin_memory", lambda self: self)
+    real_empty = torch.empty
+    monkeypatch.setattr(torch, "empty", lambda *a, **k: real_empty(*a, **{x: y for x, y in k.items() if x != "device"}))
+    args = types.SimpleNamespace(gpus=1, steps=2, warmup=1, impl="b200", n=24, ortho="cgs",
+                                 no_cpu_baseline=True, no_e2e=True, cpu_iters=3, no_mgs=True,
+                                 no_extra_configs=True, ref_iters=3)
+    bench.run_b200(args, 0, 1, 0)
+    d = json.loads([ln for ln in capsys.readouterr().out.splitlines() if ln.strip().startswith("{")][-1])
+    assert d["l2_window"]["enabled"] is True and d["l2_window"]["hit_ratio"] == 1.0
+    assert "l2_resident_vector" in d["roofline"]
