@@ -1,5 +1,9 @@
 """Complex arithmetic by real embedding.
 
+(The two kernels of the Arnoldi hot loop have native complex versions -- kry_orth_fused_z works on the even rows
+of the twin storage described here and never reads the twins, kry_spmv_csr_z takes the complex matrix as it is;
+krypy_b200/utils.py ``_NATIVE_Z``, DESIGN.md section 4a.  Everything else in the complex path is what follows.)
+
 The kernels are real.  A complex vector of length N is stored as 2N interleaved reals
 ``[re0, im0, re1, im1, ...]`` and a complex matrix entry ``a+ib`` becomes the 2x2 block
 ``[[a, -b], [b, a]]`` (so the expanded real operator applied to an embedded vector IS the complex

@@ -12,9 +12,11 @@ Complex systems run on the same (real) kernels by real embedding: a complex bloc
 ``torch.complex128`` tensor whose interleaved real view is what the kernels see, and every block
 that is the left operand of inner products or a combination basis is kept in *twin storage*
 (``_Twin``: rows ``v_0, i v_0, v_1, i v_1, ...``), which turns complex Gram-Schmidt against k
-vectors into real Gram-Schmidt against 2k vectors (krypy_b200/_cplx.py).
+vectors into real Gram-Schmidt against 2k vectors (krypy_b200/_cplx.py).  The Arnoldi hot loop of a
+complex solve runs on native complex kernels instead (``kry_orth_fused_z`` on the even rows of the twin
+storage, ``kry_spmv_csr_z`` on the matrix as it is; ``_NATIVE_Z``).
 
-There is no CPU fallback: anything the device path cannot do (``ortho='house'``, complex
+There is no CPU fallback: anything the device path cannot do (complex or Householder
 row-partitioned runs) raises ``NotImplementedError``.
 """
 import time
