@@ -62,3 +62,13 @@ def test_zspmv_kernels_emulated(emul, kind, cplx):
         rows = int(out.split("rows=")[1].split()[0])
         assert int(out.rsplit(" ", 1)[1]) == rows
     emul("spmv", kind, cplx, 3)
+
+
+def test_the_product_build_never_defines_the_emulation_switch():
+    """KRY_EMUL only swaps PTX wrappers / the dynamic shared-memory declaration for host versions in the test
+    harnesses; the library is built without it (and has no CPU path)"""
+    for rel in ("krypy_b200/csrc/Makefile", "__graft_entry__.py", "krypy_b200/_lib.py", "krypy_b200/_device.py"):
+        assert "KRY_EMUL" not in open(os.path.join(ROOT, rel)).read(), rel
+    import glob
+    for path in glob.glob(os.path.join(ROOT, "krypy_b200", "csrc", "*.cu")):
+        assert "define KRY_EMUL" not in open(path).read(), path
