@@ -41,7 +41,8 @@ ORTH = [  # nv, j0, n: every dots tile size 1..8, every update remainder 0..7, o
 @pytest.mark.parametrize("algo", [0, 1], ids=["cgs", "mgs"])
 @pytest.mark.parametrize("passes", [1, 2])
 def test_zorth_kernel_emulated(emul, algo, passes):
-    for nv, j0, n in ORTH:
+    # (exact MGS has no tiles -- one sweep and one grid-wide reduction per vector: a few counts cover it)
+    for nv, j0, n in (ORTH if algo == 0 else [s for s in ORTH if s[0] <= 9 or s[0] == 17]):
         emul("orth", algo, passes, nv, j0, n, 2, 0)
 
 
